@@ -1,0 +1,135 @@
+/*
+ * qsvc_b200.h -- C ABI of the B200-native MCTF hot path (libqsvc_b200.so).
+ *
+ * The reference (claudio382/QSVC) has no in-process plugin API for this path:
+ * its interface is one process per tool, argv flags, and headerless files in
+ * the current directory.  Each entry point below is the
+ * in-process equivalent of one reference tool `main()`; the flag-compatible
+ * command-line tools in qsvc_b200/tools/ and bin/mctf are thin wrappers that
+ * read the files, call one of these functions, and write the files.
+ *
+ * Conventions
+ *   - plain C, no CUDA or torch types; all pointers are HOST pointers to
+ *     caller-owned contiguous buffers unless the name ends in `_resident`;
+ *   - frames are I420 u8: Y (Y*X), U, V ((Y/2)*(X/2)); `even` holds
+ *     n_pairs+1 frames, `odd`/`high` hold n_pairs frames;
+ *   - motion fields: per pair 4 planes PREV.X, PREV.Y, NEXT.X, NEXT.Y of
+ *     (Y/block_size)*(X/block_size) int16 (reference motion.cpp:9-15,93-101);
+ *   - frame types: one byte per pair, 'I' or 'B';
+ *   - return 0 on success, a negative QSVC_E* code otherwise; the message is
+ *     available from qsvc_last_error() (per thread);
+ *   - one context per GPU; a context is not thread-safe; contexts are
+ *     independent of each other.  There is no CPU fallback: without a CUDA
+ *     device every call fails with QSVC_ECUDA.
+ */
+#ifndef QSVC_B200_H
+#define QSVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSVC_OK 0
+#define QSVC_EINVAL (-1)  /* bad argument / unsupported geometry            */
+#define QSVC_ECUDA (-2)   /* CUDA runtime error (no device, launch failure) */
+#define QSVC_ENOMEM (-3)  /* device or host allocation failed               */
+#define QSVC_EDOMAIN (-4) /* input outside the reference's defined domain   */
+
+typedef struct qsvc_ctx qsvc_ctx;
+
+/* Library / device management. */
+int qsvc_version(void);
+int qsvc_device_count(void);
+qsvc_ctx *qsvc_create(int device);
+void qsvc_destroy(qsvc_ctx *ctx);
+const char *qsvc_last_error(void);
+/* Number of kernels this context has launched so far (bench.py gpu_launches). */
+long long qsvc_launch_count(const qsvc_ctx *ctx);
+/* Device-side timing on the context's own stream (CUDA events). */
+int qsvc_timer_start(qsvc_ctx *ctx);
+int qsvc_timer_stop(qsvc_ctx *ctx, float *elapsed_ms);
+int qsvc_synchronize(qsvc_ctx *ctx);
+
+/* Replaces `motion_estimate` main(), reference motion_estimate.cpp:490-912
+ * (search: :70-184, pyramid driver: :260-413).
+ * first_pair_is_global_first: 1 when even[0] is the first frame the reference
+ * process would have read; GOP shards other than the first
+ * pass 0. */
+int qsvc_motion_estimate(qsvc_ctx *ctx, const uint8_t *even, const uint8_t *odd, int n_pairs,
+                         int pixels_in_x, int pixels_in_y, int block_size, int border_size,
+                         int search_range, int subpixel_accuracy,
+                         int first_pair_is_global_first, int16_t *motion_out);
+
+/* Replaces `decorrelate` main() (-D ANALYZE), reference decorrelate.cpp:199-1078
+ * (predict: :69-189, I/B decision: :934-1027, entropy.cpp:20-34).
+ * prediction_out may be NULL (the reference always writes prediction_<even_fn>). */
+int qsvc_decorrelate(qsvc_ctx *ctx, const uint8_t *even, const uint8_t *odd,
+                     const int16_t *motion_in, int n_pairs, int pixels_in_x, int pixels_in_y,
+                     int block_size, int block_overlaping, int search_range,
+                     int subpixel_accuracy, int always_B, uint8_t *high_out,
+                     char *frame_types_out, int16_t *motion_out, uint8_t *prediction_out);
+
+/* Replaces `correlate` main() (no ANALYZE), reference decorrelate.cpp:705-721,1029-1066. */
+int qsvc_correlate(qsvc_ctx *ctx, const uint8_t *even, const uint8_t *high,
+                   const int16_t *motion_in, const char *frame_types, int n_pairs,
+                   int pixels_in_x, int pixels_in_y, int block_size, int block_overlaping,
+                   int search_range, int subpixel_accuracy, uint8_t *odd_out,
+                   uint8_t *prediction_out);
+
+/* Replaces `update` (inverse=0: even_t -> low_t) and `un_update` (inverse=1:
+ * low_t -> even_t) main(), reference update.cpp:158-684 (scatter: :71-148).
+ * frames_in / frames_out hold n_pairs+1 frames. */
+int qsvc_update(qsvc_ctx *ctx, int inverse, const uint8_t *frames_in, const uint8_t *high,
+                const int16_t *motion, const char *frame_types, int n_pairs, int pixels_in_x,
+                int pixels_in_y, int block_size, float update_factor, uint8_t *frames_out);
+
+/* Whole-sequence temporal analysis with the frames kept resident in HBM between
+ * levels: the device-side equivalent of analyze.py:107-153 driving
+ * analyze_step.py:115-232 (split -> motion_estimate -> decorrelate -> update per
+ * temporal level; split is index arithmetic on the resident frames).
+ *
+ *   load     : host low_0 (n_frames I420 frames) -> HBM
+ *   analyze  : runs TRLs-1 levels on the resident frames, results stay in HBM
+ *   fetch_*  : copies one level's results back to host buffers
+ * n_frames must be GOPs * 2^(TRLs-1) + 1.  block_size_min follows analyze.py:118-151.
+ */
+typedef struct qsvc_analyze_params {
+  int pixels_in_x, pixels_in_y;
+  int TRLs;
+  int block_size, block_size_min, border_size, block_overlaping;
+  int search_range, subpixel_accuracy;
+  int always_B;
+  float update_factor;
+  int first_gop_is_global_first; /* 1 unless this is a later GOP shard */
+} qsvc_analyze_params;
+
+int qsvc_resident_load(qsvc_ctx *ctx, const uint8_t *low0, int n_frames, int pixels_in_x,
+                       int pixels_in_y);
+int qsvc_resident_analyze(qsvc_ctx *ctx, const qsvc_analyze_params *params);
+/* level t in [1, TRLs-1]; any output pointer may be NULL.  Sizes: high n_pairs(t)
+ * frames, motion/motion_filtered n_pairs(t) fields, frame_types n_pairs(t) bytes,
+ * low n_pairs(t)+1 frames. */
+int qsvc_resident_fetch(qsvc_ctx *ctx, int level, uint8_t *high, int16_t *motion,
+                        int16_t *motion_filtered, char *frame_types, uint8_t *low);
+/* Work done by the last qsvc_resident_analyze: SAD operations issued by the
+ * search kernels and device milliseconds spent in them (summed over levels). */
+int qsvc_resident_stats(qsvc_ctx *ctx, double *sad_ops, float *search_ms, float *total_ms);
+
+/* Inverse: un_update -> correlate -> merge per level from TRLs-1 down to 1
+ * (synthesize.py:95-153, synthesize_step.py:84-143), frames resident in HBM.
+ * Inputs are pushed per level with qsvc_resident_push, then synthesize runs and
+ * the reconstructed low_0 (GOPs*2^(TRLs-1)+1 frames) is read with fetch_low0. */
+int qsvc_resident_push(qsvc_ctx *ctx, int level, int n_pairs, const uint8_t *high,
+                       const int16_t *motion, const char *frame_types,
+                       const uint8_t *low_top /* only for level == TRLs-1, else NULL */,
+                       int pixels_in_x, int pixels_in_y, int block_size);
+int qsvc_resident_synthesize(qsvc_ctx *ctx, const qsvc_analyze_params *params);
+int qsvc_resident_fetch_low0(qsvc_ctx *ctx, uint8_t *low0, int n_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSVC_B200_H */

@@ -1,0 +1,917 @@
+// api.cu -- context, per-level orchestration and the C ABI of libqsvc_b200.so.
+//
+// Host-side control flow mirrors the reference tools' main() functions
+// (motion_estimate.cpp:714-907, decorrelate.cpp:508-1075, update.cpp:439-679)
+// and the Python drivers (analyze.py:107-153, synthesize.py:95-153); all pixel
+// work runs in the kernels of kernels_*.cu on the context's CUDA stream.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/qsvc_b200.h"
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------ errors
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(QSVC_ECUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call,               \
+                  cudaGetErrorString(e_));                                              \
+  } while (0)
+#define TRY(call)            \
+  do {                       \
+    int rc_ = (call);        \
+    if (rc_ != QSVC_OK) return rc_; \
+  } while (0)
+
+// ----------------------------------------------------------------- context
+
+struct PoolBlock {
+  void *ptr;
+  size_t size;
+  bool used;
+};
+
+struct LevelResult {
+  int n_pairs = 0, block_size = 0, search_range = 0;
+  uint8_t *high = nullptr;      // n_pairs frames
+  short *motion = nullptr;      // n_pairs fields
+  short *motion_filtered = nullptr;
+  uint8_t *low = nullptr;       // n_pairs+1 frames
+  std::string types;
+};
+
+struct qsvc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  long long launches = 0;
+  std::vector<PoolBlock> pool;
+  size_t me_budget = (size_t)40 << 30;  // bytes of HBM for the ME image planes of one chunk
+  // resident sequence
+  uint8_t *low0 = nullptr;
+  int n_frames = 0, X = 0, Y = 0;
+  std::vector<LevelResult> levels;  // index t (0 unused)
+  double sad_ops = 0;
+  float search_ms = 0, total_ms = 0;
+  Launch L() { return Launch{stream, &launches}; }
+};
+
+static int pool_alloc(qsvc_ctx *c, size_t bytes, void **out) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes == 0) bytes = 256;
+  int best = -1;
+  for (size_t i = 0; i < c->pool.size(); i++)
+    if (!c->pool[i].used && c->pool[i].size >= bytes &&
+        (best < 0 || c->pool[i].size < c->pool[best].size))
+      best = (int)i;
+  if (best >= 0 && c->pool[best].size <= bytes * 2 + (1 << 20)) {
+    c->pool[best].used = true;
+    *out = c->pool[best].ptr;
+    return QSVC_OK;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    // release cached blocks and retry once
+    for (auto &b : c->pool)
+      if (!b.used && b.ptr) {
+        cudaFree(b.ptr);
+        b.ptr = nullptr;
+        b.size = 0;
+      }
+    cudaGetLastError();
+    e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess)
+      return fail(QSVC_ENOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  }
+  c->pool.push_back(PoolBlock{p, bytes, true});
+  *out = p;
+  return QSVC_OK;
+}
+
+static void pool_free(qsvc_ctx *c, void *p) {
+  if (!p) return;
+  for (auto &b : c->pool)
+    if (b.ptr == p) {
+      b.used = false;
+      return;
+    }
+}
+
+// Scoped set of pool allocations released on scope exit.
+struct Scratch {
+  qsvc_ctx *c;
+  std::vector<void *> ptrs;
+  explicit Scratch(qsvc_ctx *ctx) : c(ctx) {}
+  ~Scratch() {
+    for (void *p : ptrs) pool_free(c, p);
+  }
+  int get(size_t bytes, void **out) {
+    int rc = pool_alloc(c, bytes, out);
+    if (rc == QSVC_OK) ptrs.push_back(*out);
+    return rc;
+  }
+};
+
+// ---------------------------------------------------------------- geometry
+
+static inline long long frame_bytes(int X, int Y) {
+  return (long long)X * Y + 2LL * (X / 2) * (Y / 2);
+}
+static inline long long comp_offset(int X, int Y, int c) {
+  return c == 0 ? 0 : (long long)X * Y + (long long)(c - 1) * (X / 2) * (Y / 2);
+}
+static inline int desp(int x, int l) {  // motion_estimate.cpp:232-236
+  for (int i = 0; i < l; i++) x = (x + 1) / 2;
+  return x;
+}
+static inline int me_levels(int sr) {  // motion_estimate.cpp:277
+  return (int)rint(log((double)sr) / log(2.0)) - 1;
+}
+
+// glibc chunk geometry of one texture row (see common.cuh Plane)
+static inline int heap_row_shorts(int x_dim, int b) {
+  long long W = (long long)x_dim + 2LL * b;
+  long long chunk = (2 * W + 8 + 15) & ~15LL;
+  if (chunk < 32) chunk = 32;
+  return (int)(chunk / 2);
+}
+
+struct PlaneAlloc {
+  Plane p;
+  size_t bytes;
+  short *raw;
+};
+
+// heap-emulating plane set (ME)
+static int alloc_heap_planes(Scratch &s, int nslots, int y_dim, int x_dim, int b, PlaneAlloc *out) {
+  int S = heap_row_shorts(x_dim, b);
+  long long rows = (long long)y_dim + 2LL * b;
+  long long slot_shorts = (rows + 2) * S;
+  size_t bytes = (size_t)slot_shorts * nslots * sizeof(short);
+  void *raw;
+  TRY(s.get(bytes, &raw));
+  out->raw = (short *)raw;
+  out->bytes = bytes;
+  out->p.base = (short *)raw + S;
+  out->p.slot_stride = slot_shorts;
+  out->p.S = S;
+  out->p.y_dim = y_dim;
+  out->p.x_dim = x_dim;
+  out->p.b = b;
+  return QSVC_OK;
+}
+
+// dense plane set (b = 0: no heap emulation)
+static int alloc_dense_planes(Scratch &s, int nslots, int y_dim, int x_dim, PlaneAlloc *out) {
+  int S = (x_dim + 7) & ~7;
+  long long slot_shorts = (long long)y_dim * S;
+  size_t bytes = (size_t)slot_shorts * nslots * sizeof(short);
+  void *raw;
+  TRY(s.get(bytes, &raw));
+  out->raw = (short *)raw;
+  out->bytes = bytes;
+  out->p.base = (short *)raw;
+  out->p.slot_stride = slot_shorts;
+  out->p.S = S;
+  out->p.y_dim = y_dim;
+  out->p.x_dim = x_dim;
+  out->p.b = 0;
+  return QSVC_OK;
+}
+
+static int check_geometry(int X, int Y, int bs, int a) {
+  if (X < 2 || Y < 2 || X > 16384) return fail(QSVC_EINVAL, "unsupported picture size %dx%d", X, Y);
+  if (bs < 1 || bs > X || bs > Y) return fail(QSVC_EINVAL, "unsupported block_size %d", bs);
+  if (a < 0 || a > 4 || ((long long)X << a) > 16384)
+    return fail(QSVC_EINVAL, "unsupported subpixel_accuracy %d for width %d (line limit 16384, texture.cpp:9)", a, X);
+  return QSVC_OK;
+}
+
+// ------------------------------------------------------- motion estimation
+
+// SAD operations of one pair
+static double me_sad_ops(int BY, int BX, int bs, int bd, int L, int a) {
+  double ops = 0;
+  double w = bs + 2.0 * bd;
+  for (int l = 0; l <= L; l++) ops += w * w * desp(BY, l) * desp(BX, l);
+  for (int l = 1; l <= a; l++) {
+    double wl = (double)(bs << l) + 2.0 * (bd >> l);
+    ops += wl * wl * BY * BX;
+  }
+  return 18.0 * ops;
+}
+
+// even frame k at even + k*even_stride, odd frame i at odd + i*odd_stride (device).
+static int me_level(qsvc_ctx *c, const uint8_t *even, long long even_stride, const uint8_t *odd,
+                    long long odd_stride, int n_pairs, int X, int Y, int bs, int bd, int sr, int a,
+                    int first_global, short *mv_out) {
+  TRY(check_geometry(X, Y, bs, a));
+  if (sr < 1 || bd < 0) return fail(QSVC_EINVAL, "bad search_range/border_size");
+  const int BY = Y / bs, BX = X / bs;
+  if (n_pairs <= 0 || BY == 0 || BX == 0) return QSVC_OK;
+  int L = me_levels(sr);
+  if (L < 0) L = 0;
+  if (L >= 1 && ((Y >> (L - 1)) < 2 || (X >> (L - 1)) < 2))
+    return fail(QSVC_EINVAL, "search_range %d needs %d pyramid levels: picture too small", sr, L);
+  const int B = sr + bd;
+  const int Ya = Y << a, Xa = X << a, Ba = B << a;
+  // pyramid descent is an exact inverse of the analysis iff floor- and
+  // ceil-halving agree on every level used
+  bool pr = true;
+  for (int l = 0; l < L; l++)
+    if ((Y >> l) != desp(Y, l) || (X >> l) != desp(X, l)) pr = false;
+
+  const long long field = 4LL * BY * BX;
+  const int n_search = 1 + L + a;
+  Launch Lh = c->L();
+
+  // chunk the level so that the image planes fit the budget
+  int S = heap_row_shorts(Xa, Ba);
+  size_t slot_bytes = (size_t)((long long)Ya + 2LL * Ba + 2) * S * sizeof(short);
+  int per_pair_slots = pr ? 2 : 3;
+  long long max_pairs = (long long)(c->me_budget / slot_bytes - 1) / per_pair_slots;
+  if (max_pairs < 1) max_pairs = 1;
+
+  for (int i0 = 0; i0 < n_pairs; i0 += (int)max_pairs) {
+    const int m = (int)std::min<long long>(max_pairs, n_pairs - i0);
+    Scratch s(c);
+    const int n_copy = pr ? 0 : m - 1;  // separate R0-role buffers for frames i0+1 .. i0+m-1
+    const int nslots = 2 * m + 1 + n_copy;
+    PlaneAlloc pa;
+    TRY(alloc_heap_planes(s, nslots, Ya, Xa, Ba, &pa));
+    Plane img = pa.p;
+    short *mv_tmp;
+    int *d_slots;
+    TRY(s.get((size_t)m * field * sizeof(short), (void **)&mv_tmp));
+    TRY(s.get((size_t)m * 3 * sizeof(int), (void **)&d_slots));
+    std::vector<int> slots(3 * m);
+    for (int i = 0; i < m; i++) {
+      slots[3 * i] = (!pr && i >= 1) ? 2 * m + i : i;
+      slots[3 * i + 1] = i + 1;
+      slots[3 * i + 2] = m + 1 + i;
+    }
+    CU(cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(pa.raw, 0, pa.bytes, c->stream));
+    launch_size_fields(Lh, img, 0, nslots, Ya + 2 * Ba);
+    // fresh(even_k): zero interior, luma in the top-left Y x X, fill_border with the
+    // UNSHIFTED sizes (motion_estimate.cpp:803-820)
+    launch_load_u8(Lh, img, 0, m + 1, even, even_stride, 0, i0, 1, Y, X);
+    launch_load_u8(Lh, img, m + 1, m, odd, odd_stride, 0, i0, 1, Y, X);
+    launch_fill_border(Lh, img, 0, m + 1, Y, X, B);
+    if (n_copy > 0) {
+      launch_load_u8(Lh, img, 2 * m + 1, n_copy, even, even_stride, 0, i0 + 1, 1, Y, X);
+      launch_fill_border(Lh, img, 2 * m + 1, n_copy, Y, X, B);
+    }
+    if (!pr) {
+      // reference[0] of every pair but the process's first is the buffer the
+      // previous pair left behind: one full pass of the (non-invertible) pyramid.
+      auto used_state = [&](int slot0, int n) {
+        if (n <= 0) return;
+        dwt_analyze(Lh, img, slot0, n, Y, X, L);
+        for (int l = L - 1; l >= 0; --l) dwt_synthesize(Lh, img, slot0, n, desp(Y, l), desp(X, l), 1);
+        for (int l = 1; l <= a; l++) dwt_synthesize(Lh, img, slot0, n, Y << l, X << l, 1);
+        dwt_analyze(Lh, img, slot0, n, Ya, Xa, a);
+      };
+      if (!(first_global && i0 == 0)) used_state(0, 1);
+      used_state(2 * m + 1, n_copy);
+    }
+
+    short *bufs[2] = {mv_out + (long long)i0 * field, mv_tmp};
+    int j = 0;  // search index; search j writes bufs[(j + n_search - 1) & 1] so the last lands in mv_out
+    auto run_search = [&](int mode, int nby, int nbx, int bsl, int bdl, int lim) {
+      SearchParams q;
+      q.img = img;
+      q.slots = d_slots;
+      q.mv_out = bufs[(j + n_search - 1) & 1];
+      q.mv_in = bufs[(j + n_search) & 1];
+      q.BY = BY;
+      q.BX = BX;
+      q.nby = nby;
+      q.nbx = nbx;
+      q.bs = bsl;
+      q.bd = bdl;
+      q.mode = mode;
+      q.lim = lim;
+      launch_search(Lh, q, m);
+      j++;
+    };
+    dwt_analyze(Lh, img, 0, nslots, Y, X, L);
+    run_search(ME_INIT, desp(BY, L), desp(BX, L), bs, bd, 0);
+    for (int l = L - 1; l >= 0; --l) {
+      dwt_synthesize(Lh, img, 0, nslots, desp(Y, l), desp(X, l), 1);
+      run_search(ME_DESCEND, desp(BY, l), desp(BX, l), bs, bd, sr);
+    }
+    for (int l = 1; l <= a; l++) {
+      dwt_synthesize(Lh, img, 0, nslots, Y << l, X << l, 1);
+      run_search(ME_SUBPEL, BY, BX, bs << l, bd >> l, sr << a);
+    }
+    CU(cudaGetLastError());
+    c->sad_ops += me_sad_ops(BY, BX, bs, bd, L, a) * m;
+    // the scratch planes are reused by later work on the same stream only
+  }
+  return QSVC_OK;
+}
+
+// ------------------------------------------------- decorrelate / correlate
+
+// entropy.cpp:20-34 with the reference's expression shape: float division,
+// logf on the float probability, quotient in double, float accumulate.  Runs on
+// the host so that it goes through the same libm as the reference binary.
+static float ref_entropy(const int *count, int n) {
+  float entropy = 0.0f;
+  int total = 0;
+  for (int i = 0; i < n; i++) total += count[i];
+  for (int i = 0; i < n; i++)
+    if (count[i]) {
+      float prob = (float)count[i] / total;
+      entropy += prob * (float)(logf(prob) / log(2.0));
+    }
+  return -entropy;
+}
+
+// Up-sampled reference planes of one even frame (decorrelate.cpp:583-686):
+// three components at luma size << a by zero-high-band synthesis.
+static void prepare_reference(qsvc_ctx *c, Plane ref, int slot_set, const uint8_t *frame, int X,
+                              int Y, int a) {
+  Launch Lh = c->L();
+  const int s0 = slot_set * 3;
+  cudaMemsetAsync(ref.base + (long long)s0 * ref.slot_stride, 0,
+                  (size_t)3 * ref.slot_stride * sizeof(short), c->stream);
+  launch_load_u8(Lh, ref, s0, 1, frame, 0, 0, 0, 0, Y, X);
+  launch_load_u8(Lh, ref, s0 + 1, 1, frame, 0, comp_offset(X, Y, 1), 0, 0, Y / 2, X / 2);
+  launch_load_u8(Lh, ref, s0 + 2, 1, frame, 0, comp_offset(X, Y, 2), 0, 0, Y / 2, X / 2);
+  dwt_synthesize(Lh, ref, s0 + 1, 2, Y, X, 1);
+  for (int s = 1; s <= a; s++) dwt_synthesize(Lh, ref, s0, 3, Y << s, X << s, 1);
+}
+
+// analysis != 0: decorrelate (in = odd frames, out = high frames);
+// analysis == 0: correlate   (in = high frames, out = odd frames, types given).
+static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long even_stride,
+                    const uint8_t *in, long long in_stride, const short *mv_in, int n_pairs, int X,
+                    int Y, int bs, int ov, int sr, int a, int always_B, const char *types_in,
+                    uint8_t *out, long long out_stride, std::string *types_out, short *mv_out,
+                    uint8_t *prediction_out) {
+  TRY(check_geometry(X, Y, bs, a));
+  if (ov != 0)
+    return fail(QSVC_EINVAL, "block_overlaping=%d: the OBMC path (decorrelate.cpp:110-172) is not implemented", ov);
+  const int BY = Y / bs, BX = X / bs;
+  const long long field = 4LL * BY * BX;
+  const long long fb = frame_bytes(X, Y);
+  const int Ya = Y << a, Xa = X << a, bsa = bs << a;
+  const int ba = (4 * sr + ov) << a;
+  Launch Lh = c->L();
+  Scratch s(c);
+  PlaneAlloc ref, pred;
+  TRY(alloc_dense_planes(s, 6, Ya, Xa, &ref));
+  TRY(alloc_dense_planes(s, 3, Ya, Xa, &pred));
+  CU(cudaMemsetAsync(pred.raw, 0, pred.bytes, c->stream));
+  int *d_hist = nullptr;
+  const int HS = 1024;  // per pair: 256 predicted, 256 residue, 257 motion (+pad)
+  const bool need_hist = analysis && !always_B;
+  if (need_hist) {
+    TRY(s.get((size_t)n_pairs * HS * sizeof(int), (void **)&d_hist));
+    CU(cudaMemsetAsync(d_hist, 0, (size_t)n_pairs * HS * sizeof(int), c->stream));
+  }
+  const int padh = heap_row_shorts(Xa, ba) - (Xa + 2 * ba);
+
+  if (n_pairs > 0) prepare_reference(c, ref.p, 0, even, X, Y, a);
+  for (int i = 0; i < n_pairs; i++) {
+    prepare_reference(c, ref.p, (i + 1) & 1, even + (long long)(i + 1) * even_stride, X, Y, a);
+    const short *mv = mv_in + (long long)i * field;
+    PredictParams q;
+    q.ref = ref.p;
+    q.pred = pred.p;
+    q.mv = mv;
+    q.r0_slot = i & 1;
+    q.r1_slot = (i + 1) & 1;
+    q.BY = BY;
+    q.BX = BX;
+    q.bsa = bsa;
+    q.Ya = Ya;
+    q.Xa = Xa;
+    q.ba = ba;
+    q.padh = padh;
+    launch_predict(Lh, q);
+    launch_clip_uncovered(Lh, pred.p, Ya, Xa, BY * bsa, BX * bsa);
+    dwt_analyze(Lh, pred.p, 0, 3, Ya, Xa, a);
+    dwt_analyze(Lh, pred.p, 1, 2, Y, X, 1);
+    ResidueParams r;
+    r.pred = pred.p;
+    r.odd = in + (long long)i * in_stride;
+    r.out = out + (long long)i * out_stride;
+    r.prediction = prediction_out ? prediction_out + (long long)i * fb : nullptr;
+    r.hist = need_hist ? d_hist + (long long)i * HS : nullptr;
+    r.X = X;
+    r.Y = Y;
+    r.synth = analysis ? 0 : 1;
+    r.is_I = (!analysis && types_in[i] == 'I') ? 1 : 0;
+    launch_residue(Lh, r);
+    if (need_hist) launch_mv_hist(Lh, mv, (int)field, d_hist + (long long)i * HS + 512);
+  }
+  CU(cudaGetLastError());
+  if (!analysis) return QSVC_OK;
+
+  types_out->assign((size_t)n_pairs, 'B');
+  int rc = QSVC_OK;
+  if (need_hist) {
+    std::vector<int> hist((size_t)n_pairs * HS);
+    CU(cudaMemcpyAsync(hist.data(), d_hist, hist.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n_pairs; i++) {
+      const int *h = hist.data() + (size_t)i * HS;
+      if (h[512 + 256] != 0) rc = 1;  // motion component outside the reference's histogram
+      // decorrelate.cpp:934-979
+      float predicted_entropy = ref_entropy(h, 256);
+      float residue_entropy = ref_entropy(h + 256, 256);
+      float motion_entropy = ref_entropy(h + 512, 256);
+      int predicted_size = (int)(predicted_entropy * (float)Y * (float)X);
+      int residue_size = (int)(residue_entropy * (float)Y * (float)X);
+      int motion_size = (int)(motion_entropy * (float)BY * (float)BX);
+      if (predicted_size <= (residue_size + motion_size)) (*types_out)[i] = 'I';
+    }
+  }
+  // 'I': high = raw odd frame, motion_out = 0; 'B': motion_out = motion_in
+  for (int i = 0; i < n_pairs; i++) {
+    if ((*types_out)[i] == 'I') {
+      launch_copy_bytes(Lh, out + (long long)i * out_stride, in + (long long)i * in_stride, (size_t)fb);
+      if (mv_out) CU(cudaMemsetAsync(mv_out + (long long)i * field, 0, field * sizeof(short), c->stream));
+    } else if (mv_out && mv_out != mv_in) {
+      launch_copy_bytes(Lh, mv_out + (long long)i * field, mv_in + (long long)i * field, field * sizeof(short));
+    }
+  }
+  CU(cudaGetLastError());
+  if (rc == 1)
+    return fail(QSVC_EDOMAIN,
+                "motion component outside [-128,127] with always_B=0: the reference indexes its "
+                "256-bin histogram out of bounds here (decorrelate.cpp:809-812); use --always_B=1");
+  return QSVC_OK;
+}
+
+// ------------------------------------------------------- update / un_update
+
+static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long in_stride,
+                        const uint8_t *high, long long high_stride, const short *mv,
+                        const char *types, int n_pairs, int X, int Y, int bs, float uf, uint8_t *out,
+                        long long out_stride) {
+  TRY(check_geometry(X, Y, bs, 0));
+  const int BY = Y / bs, BX = X / bs;
+  const long long field = 4LL * BY * BX;
+  const long long fb = frame_bytes(X, Y);
+  Launch Lh = c->L();
+  Scratch s(c);
+  PlaneAlloc ref, res;
+  TRY(alloc_dense_planes(s, 3, Y, X, &ref));
+  TRY(alloc_dense_planes(s, 3, Y, X, &res));
+  // residue[1|2] is only ever written in its top-left quarter (update.cpp:512-520,
+  // UPDATE_STEP undefined); the rest stays at the allocator's zeros.
+  CU(cudaMemsetAsync(res.raw, 0, res.bytes, c->stream));
+  for (int k = 0; k <= n_pairs; k++) {
+    const uint8_t *frame = in + (long long)k * in_stride;
+    uint8_t *dst = out + (long long)k * out_stride;
+    bool upd_next = k >= 1 && types[k - 1] == 'B';
+    bool upd_prev = k < n_pairs && types[k] == 'B';
+    if (!(upd_next || upd_prev) || BY == 0 || BX == 0) {
+      // chroma up (zero-high synthesis) and down (analysis) are exact inverses
+      launch_copy_bytes(Lh, dst, frame, (size_t)fb);
+      continue;
+    }
+    CU(cudaMemsetAsync(ref.raw, 0, ref.bytes, c->stream));
+    launch_load_u8(Lh, ref.p, 0, 1, frame, 0, 0, 0, 0, Y, X);
+    launch_load_u8(Lh, ref.p, 1, 1, frame, 0, comp_offset(X, Y, 1), 0, 0, Y / 2, X / 2);
+    launch_load_u8(Lh, ref.p, 2, 1, frame, 0, comp_offset(X, Y, 2), 0, 0, Y / 2, X / 2);
+    dwt_synthesize(Lh, ref.p, 1, 2, Y, X, 1);
+    for (int pass = 0; pass < 2; pass++) {
+      // frame k first receives pair k-1's NEXT update, then pair k's PREV update
+      int pair = pass == 0 ? k - 1 : k;
+      if (pass == 0 ? !upd_next : !upd_prev) continue;
+      const uint8_t *h = high + (long long)pair * high_stride;
+      launch_load_residue(Lh, res.p, 0, h, Y, X);
+      launch_load_residue(Lh, res.p, 1, h + comp_offset(X, Y, 1), Y / 2, X / 2);
+      launch_load_residue(Lh, res.p, 2, h + comp_offset(X, Y, 2), Y / 2, X / 2);
+      UpdateParams q;
+      q.ref = ref.p;
+      q.res = res.p;
+      q.mv = mv + (long long)pair * field;
+      q.dir = pass == 0 ? MV_NEXT_X : MV_PREV_X;
+      q.BY = BY;
+      q.BX = BX;
+      q.bs = bs;
+      q.Y = Y;
+      q.X = X;
+      q.uf = uf;
+      q.inverse = inverse;
+      launch_update(Lh, q);
+    }
+    dwt_analyze(Lh, ref.p, 1, 2, Y, X, 1);
+    launch_store_u8(Lh, ref.p, 0, 1, dst, 0, 0, 0, 0, Y, X);
+    launch_store_u8(Lh, ref.p, 1, 1, dst, 0, comp_offset(X, Y, 1), 0, 0, Y / 2, X / 2);
+    launch_store_u8(Lh, ref.p, 2, 1, dst, 0, comp_offset(X, Y, 2), 0, 0, Y / 2, X / 2);
+  }
+  CU(cudaGetLastError());
+  return QSVC_OK;
+}
+
+// ------------------------------------------------------------------- C ABI
+
+extern "C" {
+
+int qsvc_version(void) { return 1; }
+
+int qsvc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *qsvc_last_error(void) { return g_err.c_str(); }
+
+qsvc_ctx *qsvc_create(int device) {
+  int n = qsvc_device_count();
+  if (n <= 0) {
+    fail(QSVC_ECUDA, "no CUDA device: libqsvc_b200 has no CPU fallback");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    fail(QSVC_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    fail(QSVC_ECUDA, "cudaSetDevice(%d) failed", device);
+    return nullptr;
+  }
+  qsvc_ctx *c = new qsvc_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess) {
+    fail(QSVC_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return nullptr;
+  }
+  int e = dwt_init_attributes();
+  if (e != 0) {
+    fail(QSVC_ECUDA, "kernel attribute setup failed: %s (is this an sm_100 device?)",
+         cudaGetErrorString((cudaError_t)e));
+    delete c;
+    return nullptr;
+  }
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->me_budget = std::min<size_t>((size_t)64 << 30, free_b / 3);
+  return c;
+}
+
+static void free_levels(qsvc_ctx *c) {
+  for (auto &lv : c->levels) {
+    pool_free(c, lv.high);
+    pool_free(c, lv.motion);
+    pool_free(c, lv.motion_filtered);
+    pool_free(c, lv.low);
+  }
+  c->levels.clear();
+}
+
+void qsvc_destroy(qsvc_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto &b : c->pool)
+    if (b.ptr) cudaFree(b.ptr);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev2);
+  cudaEventDestroy(c->ev3);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+long long qsvc_launch_count(const qsvc_ctx *c) { return c ? c->launches : 0; }
+
+int qsvc_timer_start(qsvc_ctx *c) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->ev0, c->stream));
+  return QSVC_OK;
+}
+int qsvc_timer_stop(qsvc_ctx *c, float *ms) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return QSVC_OK;
+}
+int qsvc_synchronize(qsvc_ctx *c) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return QSVC_OK;
+}
+
+#define ENTER(c)                                            \
+  if (!(c)) return fail(QSVC_EINVAL, "null context");       \
+  CU(cudaSetDevice((c)->device));
+
+int qsvc_motion_estimate(qsvc_ctx *c, const uint8_t *even, const uint8_t *odd, int n_pairs, int X,
+                         int Y, int bs, int bd, int sr, int a, int first_global, int16_t *mv_out) {
+  ENTER(c);
+  if (n_pairs < 0 || !even || !odd || !mv_out) return fail(QSVC_EINVAL, "bad arguments");
+  TRY(check_geometry(X, Y, bs, a));
+  if (n_pairs == 0) return QSVC_OK;
+  const long long fb = frame_bytes(X, Y), field = 4LL * (Y / bs) * (X / bs);
+  Scratch s(c);
+  uint8_t *d_even, *d_odd;
+  short *d_mv;
+  TRY(s.get((size_t)fb * (n_pairs + 1), (void **)&d_even));
+  TRY(s.get((size_t)fb * n_pairs, (void **)&d_odd));
+  TRY(s.get((size_t)std::max<long long>(field, 1) * n_pairs * sizeof(short), (void **)&d_mv));
+  CU(cudaMemcpyAsync(d_even, even, (size_t)fb * (n_pairs + 1), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_odd, odd, (size_t)fb * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  TRY(me_level(c, d_even, fb, d_odd, fb, n_pairs, X, Y, bs, bd, sr, a, first_global, d_mv));
+  CU(cudaMemcpyAsync(mv_out, d_mv, (size_t)field * n_pairs * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QSVC_OK;
+}
+
+int qsvc_decorrelate(qsvc_ctx *c, const uint8_t *even, const uint8_t *odd, const int16_t *mv_in,
+                     int n_pairs, int X, int Y, int bs, int ov, int sr, int a, int always_B,
+                     uint8_t *high_out, char *types_out, int16_t *mv_out, uint8_t *prediction_out) {
+  ENTER(c);
+  if (n_pairs < 0 || !even || !odd || !mv_in || !high_out || !types_out || !mv_out)
+    return fail(QSVC_EINVAL, "bad arguments");
+  TRY(check_geometry(X, Y, bs, a));
+  if (n_pairs == 0) return QSVC_OK;
+  const long long fb = frame_bytes(X, Y), field = 4LL * (Y / bs) * (X / bs);
+  Scratch s(c);
+  uint8_t *d_even, *d_odd, *d_high, *d_pred = nullptr;
+  short *d_mv, *d_mvo;
+  TRY(s.get((size_t)fb * (n_pairs + 1), (void **)&d_even));
+  TRY(s.get((size_t)fb * n_pairs, (void **)&d_odd));
+  TRY(s.get((size_t)fb * n_pairs, (void **)&d_high));
+  if (prediction_out) TRY(s.get((size_t)fb * n_pairs, (void **)&d_pred));
+  TRY(s.get((size_t)std::max<long long>(field, 1) * n_pairs * sizeof(short), (void **)&d_mv));
+  TRY(s.get((size_t)std::max<long long>(field, 1) * n_pairs * sizeof(short), (void **)&d_mvo));
+  CU(cudaMemcpyAsync(d_even, even, (size_t)fb * (n_pairs + 1), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_odd, odd, (size_t)fb * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_mv, mv_in, (size_t)field * n_pairs * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+  std::string types;
+  TRY(mc_level(c, 1, d_even, fb, d_odd, fb, d_mv, n_pairs, X, Y, bs, ov, sr, a, always_B, nullptr,
+               d_high, fb, &types, d_mvo, d_pred));
+  CU(cudaMemcpyAsync(high_out, d_high, (size_t)fb * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(mv_out, d_mvo, (size_t)field * n_pairs * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+  if (prediction_out)
+    CU(cudaMemcpyAsync(prediction_out, d_pred, (size_t)fb * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(types_out, types.data(), (size_t)n_pairs);
+  return QSVC_OK;
+}
+
+int qsvc_correlate(qsvc_ctx *c, const uint8_t *even, const uint8_t *high, const int16_t *mv_in,
+                   const char *types, int n_pairs, int X, int Y, int bs, int ov, int sr, int a,
+                   uint8_t *odd_out, uint8_t *prediction_out) {
+  ENTER(c);
+  if (n_pairs < 0 || !even || !high || !mv_in || !types || !odd_out)
+    return fail(QSVC_EINVAL, "bad arguments");
+  TRY(check_geometry(X, Y, bs, a));
+  if (n_pairs == 0) return QSVC_OK;
+  const long long fb = frame_bytes(X, Y), field = 4LL * (Y / bs) * (X / bs);
+  Scratch s(c);
+  uint8_t *d_even, *d_high, *d_odd, *d_pred = nullptr;
+  short *d_mv;
+  TRY(s.get((size_t)fb * (n_pairs + 1), (void **)&d_even));
+  TRY(s.get((size_t)fb * n_pairs, (void **)&d_high));
+  TRY(s.get((size_t)fb * n_pairs, (void **)&d_odd));
+  if (prediction_out) TRY(s.get((size_t)fb * n_pairs, (void **)&d_pred));
+  TRY(s.get((size_t)std::max<long long>(field, 1) * n_pairs * sizeof(short), (void **)&d_mv));
+  CU(cudaMemcpyAsync(d_even, even, (size_t)fb * (n_pairs + 1), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_high, high, (size_t)fb * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_mv, mv_in, (size_t)field * n_pairs * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+  TRY(mc_level(c, 0, d_even, fb, d_high, fb, d_mv, n_pairs, X, Y, bs, ov, sr, a, 1, types, d_odd,
+               fb, nullptr, nullptr, d_pred));
+  CU(cudaMemcpyAsync(odd_out, d_odd, (size_t)fb * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  if (prediction_out)
+    CU(cudaMemcpyAsync(prediction_out, d_pred, (size_t)fb * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QSVC_OK;
+}
+
+int qsvc_update(qsvc_ctx *c, int inverse, const uint8_t *in, const uint8_t *high,
+                const int16_t *mv, const char *types, int n_pairs, int X, int Y, int bs, float uf,
+                uint8_t *out) {
+  ENTER(c);
+  if (n_pairs < 0 || !in || !out || (n_pairs > 0 && (!high || !mv || !types)))
+    return fail(QSVC_EINVAL, "bad arguments");
+  TRY(check_geometry(X, Y, bs, 0));
+  const long long fb = frame_bytes(X, Y), field = 4LL * (Y / bs) * (X / bs);
+  Scratch s(c);
+  uint8_t *d_in, *d_high, *d_out;
+  short *d_mv;
+  TRY(s.get((size_t)fb * (n_pairs + 1), (void **)&d_in));
+  TRY(s.get((size_t)fb * (n_pairs + 1), (void **)&d_out));
+  TRY(s.get((size_t)fb * std::max(n_pairs, 1), (void **)&d_high));
+  TRY(s.get((size_t)std::max<long long>(field, 1) * std::max(n_pairs, 1) * sizeof(short), (void **)&d_mv));
+  CU(cudaMemcpyAsync(d_in, in, (size_t)fb * (n_pairs + 1), cudaMemcpyHostToDevice, c->stream));
+  if (n_pairs > 0) {
+    CU(cudaMemcpyAsync(d_high, high, (size_t)fb * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_mv, mv, (size_t)field * n_pairs * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+  }
+  TRY(update_level(c, inverse, d_in, fb, d_high, fb, d_mv, types, n_pairs, X, Y, bs, uf, d_out, fb));
+  CU(cudaMemcpyAsync(out, d_out, (size_t)fb * (n_pairs + 1), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QSVC_OK;
+}
+
+// ------------------------------------------------------ resident sequence
+
+int qsvc_resident_load(qsvc_ctx *c, const uint8_t *low0, int n_frames, int X, int Y) {
+  ENTER(c);
+  if (!low0 || n_frames < 1) return fail(QSVC_EINVAL, "bad arguments");
+  TRY(check_geometry(X, Y, 1, 0));
+  free_levels(c);
+  pool_free(c, c->low0);
+  c->low0 = nullptr;
+  const long long fb = frame_bytes(X, Y);
+  TRY(pool_alloc(c, (size_t)fb * n_frames, (void **)&c->low0));
+  CU(cudaMemcpyAsync(c->low0, low0, (size_t)fb * n_frames, cudaMemcpyHostToDevice, c->stream));
+  c->n_frames = n_frames;
+  c->X = X;
+  c->Y = Y;
+  return QSVC_OK;
+}
+
+int qsvc_resident_analyze(qsvc_ctx *c, const qsvc_analyze_params *p) {
+  ENTER(c);
+  if (!p || !c->low0) return fail(QSVC_EINVAL, "no resident sequence");
+  if (p->pixels_in_x != c->X || p->pixels_in_y != c->Y) return fail(QSVC_EINVAL, "geometry mismatch");
+  const int X = c->X, Y = c->Y;
+  int pictures = c->n_frames;
+  if (p->TRLs < 1) return fail(QSVC_EINVAL, "bad TRLs");
+  if (p->TRLs > 1 && (pictures - 1) % (1 << (p->TRLs - 1)) != 0)
+    return fail(QSVC_EINVAL, "n_frames=%d is not GOPs*2^(TRLs-1)+1 for TRLs=%d", pictures, p->TRLs);
+  free_levels(c);
+  c->levels.resize(p->TRLs);
+  c->sad_ops = 0;
+  const long long fb = frame_bytes(X, Y);
+  int sr = p->search_range, bs = p->block_size, bs_min = p->block_size_min;
+  if (bs < bs_min) bs_min = bs;  // analyze.py:118-119
+  const uint8_t *low = c->low0;
+  CU(cudaEventRecord(c->ev2, c->stream));
+  for (int t = 1; t < p->TRLs; t++) {
+    const int n = pictures / 2;
+    LevelResult &lv = c->levels[t];
+    lv.n_pairs = n;
+    lv.block_size = bs;
+    lv.search_range = sr;
+    const long long field = 4LL * (Y / bs) * (X / bs);
+    TRY(pool_alloc(c, (size_t)fb * n, (void **)&lv.high));
+    TRY(pool_alloc(c, (size_t)std::max<long long>(field, 1) * n * sizeof(short), (void **)&lv.motion));
+    TRY(pool_alloc(c, (size_t)std::max<long long>(field, 1) * n * sizeof(short), (void **)&lv.motion_filtered));
+    TRY(pool_alloc(c, (size_t)fb * (n + 1), (void **)&lv.low));
+    // split (split.cpp:229-341) is index arithmetic: even k = frame 2k, odd i = frame 2i+1
+    const uint8_t *even = low, *odd = low + fb;
+    TRY(me_level(c, even, 2 * fb, odd, 2 * fb, n, X, Y, bs, p->border_size, sr, p->subpixel_accuracy,
+                 p->first_gop_is_global_first, lv.motion));
+    TRY(mc_level(c, 1, even, 2 * fb, odd, 2 * fb, lv.motion, n, X, Y, bs, p->block_overlaping, sr,
+                 p->subpixel_accuracy, p->always_B, nullptr, lv.high, fb, &lv.types,
+                 lv.motion_filtered, nullptr));
+    TRY(update_level(c, 0, even, 2 * fb, lv.high, fb, lv.motion_filtered, lv.types.c_str(), n, X, Y,
+                     bs, p->update_factor, lv.low, fb));
+    low = lv.low;
+    pictures = (pictures + 1) / 2;
+    sr = std::min(sr * 2, 128);       // analyze.py:144-147
+    bs = std::max(bs / 2, bs_min);    // analyze.py:149-151
+  }
+  CU(cudaEventRecord(c->ev3, c->stream));
+  CU(cudaEventSynchronize(c->ev3));
+  CU(cudaEventElapsedTime(&c->total_ms, c->ev2, c->ev3));
+  return QSVC_OK;
+}
+
+int qsvc_resident_fetch(qsvc_ctx *c, int t, uint8_t *high, int16_t *motion, int16_t *motion_filtered,
+                        char *types, uint8_t *low) {
+  ENTER(c);
+  if (t < 1 || t >= (int)c->levels.size()) return fail(QSVC_EINVAL, "no such level %d", t);
+  LevelResult &lv = c->levels[t];
+  const long long fb = frame_bytes(c->X, c->Y);
+  const long long field = 4LL * (c->Y / lv.block_size) * (c->X / lv.block_size);
+  if (high) CU(cudaMemcpyAsync(high, lv.high, (size_t)fb * lv.n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  if (motion)
+    CU(cudaMemcpyAsync(motion, lv.motion, (size_t)field * lv.n_pairs * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+  if (motion_filtered)
+    CU(cudaMemcpyAsync(motion_filtered, lv.motion_filtered, (size_t)field * lv.n_pairs * sizeof(short),
+                       cudaMemcpyDeviceToHost, c->stream));
+  if (low) CU(cudaMemcpyAsync(low, lv.low, (size_t)fb * (lv.n_pairs + 1), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (types) memcpy(types, lv.types.data(), (size_t)lv.n_pairs);
+  return QSVC_OK;
+}
+
+int qsvc_resident_stats(qsvc_ctx *c, double *sad_ops, float *search_ms, float *total_ms) {
+  if (!c) return fail(QSVC_EINVAL, "null context");
+  if (sad_ops) *sad_ops = c->sad_ops;
+  if (search_ms) *search_ms = c->search_ms;
+  if (total_ms) *total_ms = c->total_ms;
+  return QSVC_OK;
+}
+
+int qsvc_resident_push(qsvc_ctx *c, int t, int n_pairs, const uint8_t *high, const int16_t *motion,
+                       const char *types, const uint8_t *low_top, int X, int Y, int bs) {
+  ENTER(c);
+  if (t < 1 || n_pairs < 1 || !high || !motion || !types) return fail(QSVC_EINVAL, "bad arguments");
+  TRY(check_geometry(X, Y, bs, 0));
+  if ((int)c->levels.size() <= t) c->levels.resize(t + 1);
+  if (c->X != X || c->Y != Y) {
+    c->X = X;
+    c->Y = Y;
+  }
+  LevelResult &lv = c->levels[t];
+  pool_free(c, lv.high);
+  pool_free(c, lv.motion);
+  pool_free(c, lv.low);
+  lv.high = nullptr;
+  lv.motion = nullptr;
+  lv.low = nullptr;
+  lv.n_pairs = n_pairs;
+  lv.block_size = bs;
+  lv.types.assign(types, (size_t)n_pairs);
+  const long long fb = frame_bytes(X, Y), field = 4LL * (Y / bs) * (X / bs);
+  TRY(pool_alloc(c, (size_t)fb * n_pairs, (void **)&lv.high));
+  TRY(pool_alloc(c, (size_t)std::max<long long>(field, 1) * n_pairs * sizeof(short), (void **)&lv.motion));
+  CU(cudaMemcpyAsync(lv.high, high, (size_t)fb * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(lv.motion, motion, (size_t)field * n_pairs * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+  if (low_top) {
+    TRY(pool_alloc(c, (size_t)fb * (n_pairs + 1), (void **)&lv.low));
+    CU(cudaMemcpyAsync(lv.low, low_top, (size_t)fb * (n_pairs + 1), cudaMemcpyHostToDevice, c->stream));
+  }
+  return QSVC_OK;
+}
+
+int qsvc_resident_synthesize(qsvc_ctx *c, const qsvc_analyze_params *p) {
+  ENTER(c);
+  if (!p) return fail(QSVC_EINVAL, "null params");
+  const int T = p->TRLs;
+  if (T < 2 || (int)c->levels.size() < T || !c->levels[T - 1].low)
+    return fail(QSVC_EINVAL, "push every level (and low_{TRLs-1}) before synthesize");
+  const int X = c->X, Y = c->Y;
+  const long long fb = frame_bytes(X, Y);
+  CU(cudaEventRecord(c->ev2, c->stream));
+  for (int t = T - 1; t >= 1; t--) {
+    LevelResult &lv = c->levels[t];
+    if (!lv.high || !lv.motion) return fail(QSVC_EINVAL, "level %d was not pushed", t);
+    const int n = lv.n_pairs;
+    // search_range of level t (synthesize.py:113-121,143-153)
+    int sr = p->search_range;
+    for (int j = 1; j < t; j++) sr = std::min(sr * 2, 128);
+    uint8_t *dst;  // low_{t-1}: 2n+1 frames, even_t at even positions, odd_t at odd positions
+    TRY(pool_alloc(c, (size_t)fb * (2 * n + 1), (void **)&dst));
+    TRY(update_level(c, 1, lv.low, fb, lv.high, fb, lv.motion, lv.types.c_str(), n, X, Y,
+                     lv.block_size, p->update_factor, dst, 2 * fb));
+    TRY(mc_level(c, 0, dst, 2 * fb, lv.high, fb, lv.motion, n, X, Y, lv.block_size,
+                 p->block_overlaping, sr, p->subpixel_accuracy, 1, lv.types.c_str(), dst + fb, 2 * fb,
+                 nullptr, nullptr, nullptr));
+    if (t - 1 >= 1) {
+      pool_free(c, c->levels[t - 1].low);
+      c->levels[t - 1].low = dst;
+      if (c->levels[t - 1].n_pairs != 2 * n)
+        return fail(QSVC_EINVAL, "level %d has %d pairs, expected %d", t - 1, c->levels[t - 1].n_pairs, 2 * n);
+    } else {
+      pool_free(c, c->low0);
+      c->low0 = dst;
+      c->n_frames = 2 * n + 1;
+    }
+  }
+  CU(cudaEventRecord(c->ev3, c->stream));
+  CU(cudaEventSynchronize(c->ev3));
+  CU(cudaEventElapsedTime(&c->total_ms, c->ev2, c->ev3));
+  return QSVC_OK;
+}
+
+int qsvc_resident_fetch_low0(qsvc_ctx *c, uint8_t *low0, int n_frames) {
+  ENTER(c);
+  if (!c->low0 || n_frames != c->n_frames) return fail(QSVC_EINVAL, "resident low_0 has %d frames", c->n_frames);
+  CU(cudaMemcpyAsync(low0, c->low0, (size_t)frame_bytes(c->X, c->Y) * n_frames, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QSVC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// kernels.cuh -- launchers of the MCTF device kernels (defined in kernels_*.cu).
+#pragma once
+#include "common.cuh"
+
+struct Launch {
+  cudaStream_t stream;
+  long long *counter;  // number of kernels launched (host side)
+};
+
+// ---- image preparation (kernels_img.cu) ----
+// dst.row(slot0 + s, y)[x] = src[(f0 + s*fstep)*frame_stride + comp_off + y*w + x], y<h, x<w
+void launch_load_u8(const Launch &L, Plane dst, int slot0, int nslots, const uint8_t *src,
+                    long long frame_stride, long long comp_off, int f0, int fstep, int h, int w);
+// glibc size fields in front of every physical row (heap-emulating planes only)
+void launch_size_fields(const Launch &L, Plane p, int slot0, int nslots, int rows);
+// texture::fill_border(data, y_dim, x_dim, b), the 8 regions in source order
+void launch_fill_border(const Launch &L, Plane p, int slot0, int nslots, int y_dim, int x_dim,
+                        int b);
+// store the top-left h x w of a plane as u8 with the reference's truncating cast
+void launch_store_u8(const Launch &L, Plane src, int slot0, int nslots, uint8_t *dst,
+                     long long frame_stride, long long comp_off, int f0, int fstep, int h, int w);
+
+// ---- 5/3 transforms (kernels_dwt.cu), in place, reference Mallat layout ----
+int dwt_init_attributes();
+// one level on the top-left ny x nx of each slot
+void launch_dwt_level(const Launch &L, Plane p, int slot0, int nslots, int ny, int nx,
+                      bool synth);
+// dwt2d::analyze(sig, y, x, levels) / dwt2d::synthesize(sig, y, x, levels)
+void dwt_analyze(const Launch &L, Plane p, int slot0, int nslots, int y, int x, int levels);
+void dwt_synthesize(const Launch &L, Plane p, int slot0, int nslots, int y, int x, int levels);
+
+// ---- motion search (kernels_me.cu) ----
+enum { ME_INIT = 0, ME_DESCEND = 1, ME_SUBPEL = 2 };
+struct SearchParams {
+  Plane img;
+  const int *slots;  // per pair: R0 slot, R1 slot, P slot
+  const short *mv_in;
+  short *mv_out;
+  int BY, BX;    // full field dimensions (row stride of a motion plane = BX)
+  int nby, nbx;  // blocks searched at this level
+  int bs, bd;    // block size and block border at this level
+  int mode, lim;
+};
+void launch_search(const Launch &L, const SearchParams &q, int npairs);
+
+// ---- motion compensation (kernels_mc.cu) ----
+struct PredictParams {
+  Plane ref;          // dense up-sampled references: slot = ref_slot*3 + c
+  Plane pred;         // dense prediction planes: slot = c
+  const short *mv;    // one field (4 planes of BY*BX)
+  int r0_slot, r1_slot;
+  int BY, BX, bsa;    // block size << a
+  int Ya, Xa, ba;     // up-sampled size and border << a
+  int padh;           // (malloc chunk - row bytes)/2 in shorts (heap alias rule)
+};
+void launch_predict(const Launch &L, const PredictParams &q);
+// clip to [0,255] everything outside the covered area [0,cy) x [0,cx)
+void launch_clip_uncovered(const Launch &L, Plane pred, int Ya, int Xa, int cy, int cx);
+
+struct ResidueParams {
+  Plane pred;            // LL in the top-left of slot c
+  const uint8_t *odd;    // analysis: odd frame; synthesis: high frame
+  uint8_t *out;          // analysis: high frame ('B' variant); synthesis: odd frame
+  uint8_t *prediction;   // nullable: prediction_<even> side output
+  int *hist;             // nullable: [0,256) predicted luma, [256,512) residue luma + 128
+  int X, Y;
+  int synth;             // 0: decorrelate, 1: correlate
+  int is_I;              // synthesis only: frame type of this pair
+};
+void launch_residue(const Launch &L, const ResidueParams &q);
+// histogram of one motion field (+128), out-of-range components counted in hist[256]
+void launch_mv_hist(const Launch &L, const short *mv, int n, int *hist);
+void launch_copy_bytes(const Launch &L, void *dst, const void *src, size_t n);
+
+struct UpdateParams {
+  Plane ref;            // dense, luma-sized planes: slot = c (the frame being updated)
+  Plane res;            // residue planes: slot = c (high - 128, chroma top-left only)
+  const short *mv;      // the pair's field
+  int dir;              // MV_PREV_X / MV_NEXT_X: which vectors displace the residue
+  int BY, BX, bs, Y, X;
+  float uf;
+  int inverse;
+};
+void launch_update(const Launch &L, const UpdateParams &q);
+// residue plane: top-left h x w = high - 128 (rest untouched)
+void launch_load_residue(const Launch &L, Plane dst, int slot, const uint8_t *src, int h, int w);

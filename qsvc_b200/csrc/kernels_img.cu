@@ -1,0 +1,110 @@
+// kernels_img.cu -- frame load/store and border emulation.
+//
+// Reference: texture.cpp:122-144 (u8 <-> i16 row I/O, truncating store),
+// texture.cpp:55-113 (fill_border, 8 regions), texture.cpp:34-46 (alloc).
+#include "kernels.cuh"
+
+#define COUNT(L) (++*(L).counter)
+
+__global__ void k_load_u8(Plane dst, int slot0, const uint8_t *__restrict__ src,
+                          long long frame_stride, long long comp_off, int f0, int fstep, int h,
+                          int w) {
+  int s = blockIdx.z;
+  const uint8_t *f = src + (long long)(f0 + s * fstep) * frame_stride + comp_off;
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    short *row = dst.row(slot0 + s, y);
+    const uint8_t *srow = f + (long long)y * w;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x)
+      row[x] = srow[x];
+  }
+}
+
+void launch_load_u8(const Launch &L, Plane dst, int slot0, int nslots, const uint8_t *src,
+                    long long frame_stride, long long comp_off, int f0, int fstep, int h, int w) {
+  if (nslots <= 0 || h <= 0 || w <= 0) return;
+  dim3 grid((w + 255) / 256, h < 1024 ? h : 1024, nslots);
+  k_load_u8<<<grid, 256, 0, L.stream>>>(dst, slot0, src, frame_stride, comp_off, f0, fstep, h, w);
+  COUNT(L);
+}
+
+__global__ void k_store_u8(Plane src, int slot0, uint8_t *__restrict__ dst, long long frame_stride,
+                           long long comp_off, int f0, int fstep, int h, int w) {
+  int s = blockIdx.z;
+  uint8_t *f = dst + (long long)(f0 + s * fstep) * frame_stride + comp_off;
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    const short *row = src.row(slot0 + s, y);
+    uint8_t *drow = f + (long long)y * w;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x)
+      drow[x] = (uint8_t)row[x];  // texture.cpp:139-141: truncation mod 256, no clamp
+  }
+}
+
+void launch_store_u8(const Launch &L, Plane src, int slot0, int nslots, uint8_t *dst,
+                     long long frame_stride, long long comp_off, int f0, int fstep, int h, int w) {
+  if (nslots <= 0 || h <= 0 || w <= 0) return;
+  dim3 grid((w + 255) / 256, h < 1024 ? h : 1024, nslots);
+  k_store_u8<<<grid, 256, 0, L.stream>>>(src, slot0, dst, frame_stride, comp_off, f0, fstep, h, w);
+  COUNT(L);
+}
+
+// glibc chunk size field (chunk | PREV_INUSE) as the 4 shorts before each row.
+__global__ void k_size_fields(Plane p, int slot0, int rows) {
+  int s = blockIdx.y;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  unsigned long long sz = ((unsigned long long)p.S * 2ull) | 1ull;
+  short *u = p.base + (long long)(slot0 + s) * p.slot_stride + (long long)r * p.S;
+  u[-4] = (short)(sz & 0xffff);
+  u[-3] = (short)((sz >> 16) & 0xffff);
+  u[-2] = (short)((sz >> 32) & 0xffff);
+  u[-1] = (short)((sz >> 48) & 0xffff);
+}
+
+void launch_size_fields(const Launch &L, Plane p, int slot0, int nslots, int rows) {
+  if (nslots <= 0) return;
+  dim3 grid((rows + 127) / 128, nslots);
+  k_size_fields<<<grid, 128, 0, L.stream>>>(p, slot0, rows);
+  COUNT(L);
+}
+
+// One fill_border region per launch: destinations of different regions can
+// alias through the row-pointer bug, so the source order is preserved by
+// stream order.  Within a region sources are interior cells and never alias a
+// destination.
+__global__ void k_fill_region(Plane p, int slot0, int region, int Y, int X, int b) {
+  int s = slot0 + blockIdx.z;
+  // destination rectangle and source rule per region (texture.cpp:57-112)
+  int y_lo, y_hi, x_lo, x_hi;
+  switch (region) {
+    case 1: y_lo = -b; y_hi = 0; x_lo = -b; x_hi = 0; break;
+    case 2: y_lo = -b; y_hi = 0; x_lo = 0; x_hi = X; break;
+    case 3: y_lo = -b; y_hi = 0; x_lo = X; x_hi = X + b; break;
+    case 4: y_lo = 0; y_hi = Y; x_lo = -b; x_hi = 0; break;
+    case 5: y_lo = 0; y_hi = Y; x_lo = X; x_hi = X + b; break;
+    case 6: y_lo = Y; y_hi = Y + b; x_lo = -b; x_hi = 0; break;
+    case 7: y_lo = Y; y_hi = Y + b; x_lo = 0; x_hi = X; break;
+    default: y_lo = Y; y_hi = Y + b; x_lo = X; x_hi = X + b; break;
+  }
+  for (int y = y_lo + blockIdx.y; y < y_hi; y += gridDim.y) {
+    int sy = y < 0 ? 0 : (y >= Y ? Y - 1 : y);
+    const short *srow = p.row(s, sy);
+    short *drow = p.row(s, y);
+    for (int x = x_lo + blockIdx.x * blockDim.x + threadIdx.x; x < x_hi;
+         x += gridDim.x * blockDim.x) {
+      int sx = x < 0 ? 0 : (x >= X ? X - 1 : x);
+      if (region == 6) sx = X - 1;  // texture.cpp:95: bottom-left takes the bottom-right pixel
+      drow[x] = srow[sx];
+    }
+  }
+}
+
+void launch_fill_border(const Launch &L, Plane p, int slot0, int nslots, int Y, int X, int b) {
+  if (nslots <= 0 || b <= 0) return;
+  for (int region = 1; region <= 8; region++) {
+    int h = (region >= 4 && region <= 5) ? Y : b;
+    int w = (region == 2 || region == 7) ? X : b;
+    dim3 grid((w + 127) / 128, h < 512 ? h : 512, nslots);
+    k_fill_region<<<grid, 128, 0, L.stream>>>(p, slot0, region, Y, X, b);
+    COUNT(L);
+  }
+}

@@ -1,0 +1,261 @@
+// kernels_mc.cu -- motion-compensated predict / update lifting steps.
+//
+// Reference: decorrelate.cpp:69-108 (predict, block_overlaping == 0),
+// :841-848 (clip), :920-929 / :1009-1022 / :1038-1066 (residue, re-bias,
+// inverse), :799-816 / :940-953 (histograms); update.cpp:71-148 (update).
+#include "kernels.cuh"
+
+#define COUNT(L) (++*(L).counter)
+
+// P[c][y][x] = (R0[c][y+mv0] + R1[c][y+mv1]) / 2 over the covered area, then the
+// [0,255] clip of decorrelate.cpp:841-848 fused in.  The luma vector (1/2^a pel)
+// is applied unchanged to the up-sampled chroma planes (decorrelate.cpp:93-96).
+__global__ void __launch_bounds__(256) k_predict(PredictParams q) {
+  const int c = blockIdx.z;
+  const int cy = q.BY * q.bsa, cx = q.BX * q.bsa;
+  const long long plane = (long long)q.BY * q.BX;
+  const short *U0 = q.ref.row(q.r0_slot * 3 + c, 0);
+  const short *U1 = q.ref.row(q.r1_slot * 3 + c, 0);
+  for (int y = blockIdx.y; y < cy; y += gridDim.y) {
+    short *prow = q.pred.row(c, y);
+    const int by = y / q.bsa;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < cx; x += gridDim.x * blockDim.x) {
+      const long long b = (long long)by * q.BX + x / q.bsa;
+      int y0 = y + q.mv[MV_PREV_Y * plane + b], x0 = x + q.mv[MV_PREV_X * plane + b];
+      int y1 = y + q.mv[MV_NEXT_Y * plane + b], x1 = x + q.mv[MV_NEXT_X * plane + b];
+      int v = ((int)bordered_ref(U0, q.ref.S, q.Ya, q.Xa, q.ba, q.padh, y0, x0) +
+               (int)bordered_ref(U1, q.ref.S, q.Ya, q.Xa, q.ba, q.padh, y1, x1)) / 2;
+      v = (short)v;
+      prow[x] = (short)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+  }
+}
+
+void launch_predict(const Launch &L, const PredictParams &q) {
+  int cy = q.BY * q.bsa, cx = q.BX * q.bsa;
+  if (cy <= 0 || cx <= 0) return;
+  dim3 grid((cx + 1023) / 1024, cy < 2048 ? cy : 2048, 3);
+  k_predict<<<grid, 256, 0, L.stream>>>(q);
+  COUNT(L);
+}
+
+// Rows >= cy and columns >= cx of the prediction planes are never written by
+// predict(); they keep what the previous pair's in-place analysis left there and
+// are clipped with everything else.
+__global__ void k_clip_uncovered(Plane pred, int Ya, int Xa, int cy, int cx) {
+  const int c = blockIdx.z;
+  for (int y = blockIdx.y; y < Ya; y += gridDim.y) {
+    short *row = pred.row(c, y);
+    int x_begin = y < cy ? cx : 0;
+    for (int x = x_begin + blockIdx.x * blockDim.x + threadIdx.x; x < Xa;
+         x += gridDim.x * blockDim.x) {
+      short v = row[x];
+      row[x] = v < 0 ? (short)0 : (v > 255 ? (short)255 : v);
+    }
+  }
+}
+
+void launch_clip_uncovered(const Launch &L, Plane pred, int Ya, int Xa, int cy, int cx) {
+  if (cy >= Ya && cx >= Xa) return;
+  dim3 grid(8, Ya < 1024 ? Ya : 1024, 3);
+  k_clip_uncovered<<<grid, 256, 0, L.stream>>>(pred, Ya, Xa, cy, cx);
+  COUNT(L);
+}
+
+// Analysis: r = clamp(odd - LL, -128, 127); high = clamp(r + 128, 0, 255) ('B'
+// variant; 'I' frames are patched afterwards with the raw odd frame).
+// Synthesis: odd = 'I' ? high : clamp(high - 128 + LL, 0, 255).
+__global__ void __launch_bounds__(256) k_residue(ResidueParams q) {
+  __shared__ int h_pred[256], h_res[256];
+  const int c = blockIdx.z;
+  const int w = c ? q.X / 2 : q.X, h = c ? q.Y / 2 : q.Y;
+  const long long off = c == 0 ? 0 : (long long)q.X * q.Y + (long long)(c - 1) * (q.X / 2) * (q.Y / 2);
+  const bool do_hist = q.hist && c == 0 && !q.synth;
+  if (do_hist) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h_pred[i] = h_res[i] = 0;
+    __syncthreads();
+  }
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    const short *ll = q.pred.row(c, y);
+    const uint8_t *in = q.odd + off + (long long)y * w;
+    uint8_t *out = q.out + off + (long long)y * w;
+    uint8_t *pout = q.prediction ? q.prediction + off + (long long)y * w : nullptr;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
+      int p = ll[x];
+      int s = in[x];
+      int o;
+      if (!q.synth) {
+        int r = s - p;
+        r = r < -128 ? -128 : (r > 127 ? 127 : r);
+        o = r + 128;  // already in [0,255]
+        if (do_hist) {
+          atomicAdd(&h_pred[s], 1);
+          atomicAdd(&h_res[o], 1);
+        }
+      } else if (q.is_I) {
+        o = s;
+      } else {
+        o = s - 128 + p;
+        o = o < 0 ? 0 : (o > 255 ? 255 : o);
+      }
+      out[x] = (uint8_t)o;
+      if (pout) pout[x] = (uint8_t)p;  // truncating store (texture.cpp:139-141)
+    }
+  }
+  if (do_hist) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+      if (h_pred[i]) atomicAdd(&q.hist[i], h_pred[i]);
+      if (h_res[i]) atomicAdd(&q.hist[256 + i], h_res[i]);
+    }
+  }
+}
+
+void launch_residue(const Launch &L, const ResidueParams &q) {
+  dim3 grid((q.X + 1023) / 1024, q.Y < 296 ? q.Y : 296, 3);
+  k_residue<<<grid, 256, 0, L.stream>>>(q);
+  COUNT(L);
+}
+
+// decorrelate.cpp:803-816: 256-bin histogram of mv + 128 over the 4 planes.
+// Components outside [-128,127] index outside the reference's static array
+// (undefined behaviour there); they are counted in hist[256] and reported.
+__global__ void k_mv_hist(const short *__restrict__ mv, int n, int *hist) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int v = mv[i] + 128;
+    atomicAdd(&hist[(unsigned)v < 256u ? v : 256], 1);
+  }
+}
+
+void launch_mv_hist(const Launch &L, const short *mv, int n, int *hist) {
+  if (n <= 0) return;
+  int blocks = (n + 255) / 256;
+  k_mv_hist<<<blocks < 64 ? blocks : 64, 256, 0, L.stream>>>(mv, n, hist);
+  COUNT(L);
+}
+
+__global__ void k_copy_bytes(uint8_t *dst, const uint8_t *src, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+    size_t n16 = n / 16;
+    const uint4 *s4 = (const uint4 *)src;
+    uint4 *d4 = (uint4 *)dst;
+    for (size_t k = i; k < n16; k += stride) d4[k] = s4[k];
+    for (size_t k = n16 * 16 + i; k < n; k += stride) dst[k] = src[k];
+  } else {
+    for (size_t k = i; k < n; k += stride) dst[k] = src[k];
+  }
+}
+
+void launch_copy_bytes(const Launch &L, void *dst, const void *src, size_t n) {
+  if (!n) return;
+  size_t blocks = (n / 16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_copy_bytes<<<(int)blocks, 256, 0, L.stream>>>((uint8_t *)dst, (const uint8_t *)src, n);
+  COUNT(L);
+}
+
+__global__ void k_load_residue(Plane dst, int slot, const uint8_t *__restrict__ src, int h, int w) {
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    short *row = dst.row(slot, y);
+    const uint8_t *srow = src + (long long)y * w;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x)
+      row[x] = (short)((int)srow[x] - 128);
+  }
+}
+
+void launch_load_residue(const Launch &L, Plane dst, int slot, const uint8_t *src, int h, int w) {
+  dim3 grid((w + 255) / 256, h < 1024 ? h : 1024);
+  k_load_residue<<<grid, 256, 0, L.stream>>>(dst, slot, src, h, w);
+  COUNT(L);
+}
+
+// update.cpp:71-148 as a target-centric gather.  The reference scatters
+// sequentially over (c, by, bx, y, x): ref[clip(src + mv)] = (short)clamp(
+// float(ref) +- residue * uf).  Several sources can hit one target (overlapping
+// displaced blocks, edge clipping) and every contribution is clamped and
+// truncated before the next one, so the order is part of the result.  One CTA
+// owns a 16x16 tile of targets: it scans the blocks in raster order, keeps those
+// whose displaced (clipped) footprint touches the tile, and each thread replays
+// the contributions to its own pixel in (by, bx, y, x) order.  PREV and NEXT
+// touch different frames and the three components different planes, so the
+// chains are independent (one launch per frame and direction).
+__global__ void __launch_bounds__(256) k_update(UpdateParams q) {
+  __shared__ int s_list[256];
+  __shared__ int s_count;
+  const int c = blockIdx.z;
+  const int tx = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int ty = blockIdx.y * 16 + (threadIdx.x >> 4);
+  const int tile_x0 = blockIdx.x * 16, tile_y0 = blockIdx.y * 16;
+  const int tile_x1 = min(tile_x0 + 15, q.X - 1), tile_y1 = min(tile_y0 + 15, q.Y - 1);
+  const bool active = tx < q.X && ty < q.Y;
+  const long long plane = (long long)q.BY * q.BX;
+  const short *mvx = q.mv + (long long)q.dir * plane;
+  const short *mvy = q.mv + (long long)(q.dir + 1) * plane;
+  const int nblocks = q.BY * q.BX;
+  float aux = 0.f;
+  short *target = nullptr;
+  if (active) {
+    target = q.ref.row(c, ty) + tx;
+    aux = (float)*target;
+  }
+  short cur = active ? *target : (short)0;
+  for (int base = 0; base < nblocks; base += 256) {
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    // ordered compaction of the blocks that can reach this tile
+    int b = base + threadIdx.x;
+    bool hit = false;
+    if (b < nblocks) {
+      int oy = (b / q.BX) * q.bs + mvy[b], ox = (b % q.BX) * q.bs + mvx[b];
+      int fy0 = iclamp(oy, 0, q.Y - 1), fy1 = iclamp(oy + q.bs - 1, 0, q.Y - 1);
+      int fx0 = iclamp(ox, 0, q.X - 1), fx1 = iclamp(ox + q.bs - 1, 0, q.X - 1);
+      hit = fy0 <= tile_y1 && fy1 >= tile_y0 && fx0 <= tile_x1 && fx1 >= tile_x0;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    __shared__ int s_warp[8];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int prefix = 0;
+    for (int w = 0; w < warp; w++) prefix += s_warp[w];
+    if (hit) s_list[prefix + __popc(m & ((1u << lane) - 1))] = b;
+    if (threadIdx.x == 255) s_count = prefix + __popc(m);
+    __syncthreads();
+    const int cnt = s_count;
+    if (active) {
+      for (int k = 0; k < cnt; k++) {
+        int bb = s_list[k];
+        int byy = bb / q.BX, bxx = bb % q.BX;
+        int oy = byy * q.bs + mvy[bb], ox = bxx * q.bs + mvx[bb];
+        // source rows y in [0,bs) with clip(oy + y) == ty, in increasing order
+        // (edge targets collect every source that clip() folds onto them)
+        int ylo = (ty == 0) ? 0 : ty - oy, yhi = (ty == q.Y - 1) ? q.bs - 1 : ty - oy;
+        int xlo = (tx == 0) ? 0 : tx - ox, xhi = (tx == q.X - 1) ? q.bs - 1 : tx - ox;
+        ylo = max(ylo, 0); yhi = min(yhi, q.bs - 1);
+        xlo = max(xlo, 0); xhi = min(xhi, q.bs - 1);
+        for (int y = ylo; y <= yhi; y++) {
+          const short *rrow = q.res.row(c, byy * q.bs + y) + bxx * q.bs;
+          for (int x = xlo; x <= xhi; x++) {
+            float prod = __fmul_rn((float)rrow[x], q.uf);
+            aux = (float)cur;
+            aux = q.inverse ? __fsub_rn(aux, prod) : __fadd_rn(aux, prod);
+            if (aux > 255.f) aux = 255.f;
+            else if (aux < 0.f) aux = 0.f;
+            cur = (short)aux;  // float -> short truncation toward zero
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (active) *target = cur;
+}
+
+void launch_update(const Launch &L, const UpdateParams &q) {
+  dim3 grid((q.X + 15) / 16, (q.Y + 15) / 16, 3);
+  k_update<<<grid, 256, 0, L.stream>>>(q);
+  COUNT(L);
+}

@@ -1,0 +1,124 @@
+// kernels_me.cu -- +-1 bidirectional block search (reference
+// motion_estimate.cpp:70-184 `local_me_for_block`, :196-225, :321-348, :372-399).
+//
+// One CTA per (block, pair).  The predicted block and, per direction, the
+// (W+2)x(W+2) window around the current centre are staged in shared memory;
+// all nine candidate SADs of both directions are accumulated from there.
+// Exact int16 path: samples are DWT coefficients / polluted interpolations and
+// do not fit in bytes; `__sad` compiles to one VABSDIFF.
+#include "kernels.cuh"
+
+#define COUNT(L) (++*(L).counter)
+
+// candidate order of the reference: (dy,dx)
+__constant__ int c_cand[9][2] = {{-1, -1}, {-1, 1}, {1, -1}, {1, 1}, {-1, 0},
+                                 {1, 0},   {0, 1},  {0, -1}, {0, 0}};
+
+__global__ void __launch_bounds__(128) k_search(SearchParams q) {
+  extern __shared__ short sm[];
+  const int bx = blockIdx.x, by = blockIdx.y, pair = blockIdx.z;
+  const int W = q.bs + 2 * q.bd;
+  const int RW = W + 2;
+  short *Ps = sm;
+  short *Rs0 = Ps + W * W;
+  short *Rs1 = Rs0 + RW * RW;
+  __shared__ int s_part[4][18];
+
+  const long long plane = (long long)q.BY * q.BX;
+  const short *mvi = q.mv_in + (long long)pair * 4 * plane;
+  short *mvo = q.mv_out + (long long)pair * 4 * plane;
+
+  // centre of the search (motion_estimate.cpp:314-348 / :372-399)
+  short c[4];
+  if (q.mode == ME_INIT) {
+    c[0] = c[1] = c[2] = c[3] = 0;
+  } else {
+    int src = (q.mode == ME_DESCEND) ? (by >> 1) * q.BX + (bx >> 1) : by * q.BX + bx;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      short v = mvi[k * plane + src];
+      v = (short)(v * 2);
+      if (v > q.lim) v = (short)q.lim;
+      if (v < -q.lim) v = (short)(-q.lim);
+      c[k] = v;
+    }
+  }
+
+  const int r0 = q.slots[3 * pair], r1 = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
+  const int luby = by * q.bs - q.bd, lubx = bx * q.bs - q.bd;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+
+  for (int y = ty; y < W; y += 4) {
+    const short *row = q.img.row(ps, luby + y) + lubx;
+    for (int x = tx; x < W; x += 32) Ps[y * W + x] = row[x];
+  }
+  for (int y = ty; y < RW; y += 4) {
+    const short *row0 = q.img.row(r0, luby + c[MV_PREV_Y] - 1 + y) + lubx + c[MV_PREV_X] - 1;
+    const short *row1 = q.img.row(r1, luby + c[MV_NEXT_Y] - 1 + y) + lubx + c[MV_NEXT_X] - 1;
+    for (int x = tx; x < RW; x += 32) {
+      Rs0[y * RW + x] = row0[x];
+      Rs1[y * RW + x] = row1[x];
+    }
+  }
+  __syncthreads();
+
+  unsigned acc[18];
+#pragma unroll
+  for (int k = 0; k < 18; k++) acc[k] = 0;
+  for (int y = ty; y < W; y += 4) {
+    for (int x = tx; x < W; x += 32) {
+      int p = Ps[y * W + x];
+      const short *a = Rs0 + (y + 1) * RW + x + 1;
+      const short *b = Rs1 + (y + 1) * RW + x + 1;
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        int off = c_cand[k][0] * RW + c_cand[k][1];
+        acc[k] = __sad(p, (int)a[off], acc[k]);       // PREV tests centre + delta
+        acc[9 + k] = __sad(p, (int)b[-off], acc[9 + k]);  // NEXT tests centre - delta
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 18; k++) {
+    unsigned v = acc[k];
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (tx == 0) s_part[ty][k] = (int)v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int d = threadIdx.x;  // 0: PREV, 1: NEXT
+    int best = 0, min_error = 0;
+    for (int k = 0; k < 9; k++) {
+      int e = s_part[0][d * 9 + k] + s_part[1][d * 9 + k] + s_part[2][d * 9 + k] +
+              s_part[3][d * 9 + k];
+      if (k == 0 || e <= min_error) {  // "<=": the later candidate wins ties
+        min_error = e;
+        best = k;
+      }
+    }
+    int sgn = d ? -1 : 1;
+    short vy = (short)(c[2 * d + 1] + sgn * c_cand[best][0]);
+    short vx = (short)(c[2 * d] + sgn * c_cand[best][1]);
+    long long dst = (long long)by * q.BX + bx;
+    mvo[(2 * d) * plane + dst] = vx;
+    mvo[(2 * d + 1) * plane + dst] = vy;
+  }
+}
+
+void launch_search(const Launch &L, const SearchParams &q, int npairs) {
+  if (npairs <= 0 || q.nby <= 0 || q.nbx <= 0) return;
+  int W = q.bs + 2 * q.bd, RW = W + 2;
+  size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW) * sizeof(short);
+  static size_t s_attr = 0;
+  if (smem > 48 * 1024 && smem > s_attr) {
+    cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    s_attr = smem;
+  }
+  dim3 grid(q.nbx, q.nby, npairs);
+  k_search<<<grid, 128, smem, L.stream>>>(q);
+  COUNT(L);
+}

@@ -1,0 +1,253 @@
+"""Host-side mirror of the reference's MCTF tool set on top of the C ABI.
+
+One `Context` per GPU.  Methods are named after the reference tools they
+replace (split | motion_estimate | decorrelate | update | un_update |
+correlate | merge) and take/return the tools' file payloads as numpy arrays:
+frames (n, frame_bytes) uint8, motion (n, 4, by, bx) int16, frame types bytes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import AnalyzeParams, check
+from .yuv import frame_bytes
+
+SEARCH_RANGE_MAX = 128  # analyze.py:26
+
+
+def _u8(a):
+    return a.ctypes.data_as(_lib.u8p)
+
+
+def _i16(a):
+    return a.ctypes.data_as(_lib.i16p)
+
+
+def gop_size(TRLs: int) -> int:
+    """GOP.py:23-24"""
+    return 2 ** (TRLs - 1)
+
+
+def level_schedule(GOPs, TRLs, block_size, search_range, block_size_min=32):
+    """Per-level (t, pictures, search_range, block_size) of analyze.py:107-153."""
+    pictures = GOPs * gop_size(TRLs) + 1
+    if block_size < block_size_min:
+        block_size_min = block_size
+    out = []
+    for t in range(1, TRLs):
+        out.append(dict(t=t, pictures=pictures, pairs=pictures // 2, search_range=search_range,
+                        block_size=block_size))
+        pictures = (pictures + 1) // 2
+        search_range = min(search_range * 2, SEARCH_RANGE_MAX)
+        block_size = max(block_size // 2, block_size_min)
+    return out
+
+
+def split(low: np.ndarray):
+    """split.cpp:229-341: frame 0 -> even, then alternately odd, even."""
+    return low[0::2], low[1::2]
+
+
+def merge(even: np.ndarray, odd: np.ndarray) -> np.ndarray:
+    n = odd.shape[0]
+    low = np.empty((2 * n + 1, even.shape[1]), np.uint8)
+    low[0::2] = even[: n + 1]
+    low[1::2] = odd
+    return low
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._L = _lib.lib()
+        self._h = self._L.qsvc_create(device)
+        if not self._h:
+            raise _lib.QsvcError(_lib.QSVC_ECUDA, _lib.last_error())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qsvc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- bookkeeping
+    @property
+    def launches(self) -> int:
+        return int(self._L.qsvc_launch_count(self._h))
+
+    def timer_start(self):
+        check(self._L.qsvc_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        check(self._L.qsvc_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        check(self._L.qsvc_synchronize(self._h))
+
+    # ---- per-tool calls (host buffers in, host buffers out)
+    def motion_estimate(self, even, odd, X, Y, block_size=32, search_range=4, subpixel_accuracy=0,
+                        border_size=0, first_pair_is_global_first=True):
+        even = np.ascontiguousarray(even, np.uint8)
+        odd = np.ascontiguousarray(odd, np.uint8)
+        n = odd.shape[0]
+        assert even.shape == (n + 1, frame_bytes(X, Y)) and odd.shape[1] == frame_bytes(X, Y)
+        mv = np.zeros((n, 4, Y // block_size, X // block_size), np.int16)
+        check(self._L.qsvc_motion_estimate(self._h, _u8(even), _u8(odd), n, X, Y, block_size,
+                                           border_size, search_range, subpixel_accuracy,
+                                           1 if first_pair_is_global_first else 0, _i16(mv)))
+        return mv
+
+    def decorrelate(self, even, odd, motion, X, Y, block_size=16, search_range=4,
+                    subpixel_accuracy=0, block_overlaping=0, always_B=0, want_prediction=False):
+        even = np.ascontiguousarray(even, np.uint8)
+        odd = np.ascontiguousarray(odd, np.uint8)
+        motion = np.ascontiguousarray(motion, np.int16)
+        n = odd.shape[0]
+        high = np.zeros((n, frame_bytes(X, Y)), np.uint8)
+        pred = np.zeros((n, frame_bytes(X, Y)), np.uint8) if want_prediction else None
+        types = C.create_string_buffer(max(n, 1))
+        mvo = np.zeros_like(motion)
+        check(self._L.qsvc_decorrelate(self._h, _u8(even), _u8(odd), _i16(motion), n, X, Y,
+                                       block_size, block_overlaping, search_range,
+                                       subpixel_accuracy, always_B, _u8(high), types, _i16(mvo),
+                                       _u8(pred) if want_prediction else None))
+        return high, types.raw[:n], mvo, pred
+
+    def correlate(self, even, high, motion, frame_types, X, Y, block_size=16, search_range=4,
+                  subpixel_accuracy=0, block_overlaping=0, want_prediction=False):
+        even = np.ascontiguousarray(even, np.uint8)
+        high = np.ascontiguousarray(high, np.uint8)
+        motion = np.ascontiguousarray(motion, np.int16)
+        n = high.shape[0]
+        odd = np.zeros((n, frame_bytes(X, Y)), np.uint8)
+        pred = np.zeros((n, frame_bytes(X, Y)), np.uint8) if want_prediction else None
+        types = C.create_string_buffer(bytes(frame_types), max(n, 1))
+        check(self._L.qsvc_correlate(self._h, _u8(even), _u8(high), _i16(motion), types, n, X, Y,
+                                     block_size, block_overlaping, search_range,
+                                     subpixel_accuracy, _u8(odd),
+                                     _u8(pred) if want_prediction else None))
+        return odd, pred
+
+    def update(self, frames_in, high, motion, frame_types, X, Y, block_size=16,
+               update_factor=0.25, inverse=False):
+        frames_in = np.ascontiguousarray(frames_in, np.uint8)
+        high = np.ascontiguousarray(high, np.uint8)
+        motion = np.ascontiguousarray(motion, np.int16)
+        n = high.shape[0]
+        out = np.zeros((n + 1, frame_bytes(X, Y)), np.uint8)
+        types = C.create_string_buffer(bytes(frame_types), max(n, 1))
+        check(self._L.qsvc_update(self._h, 1 if inverse else 0, _u8(frames_in), _u8(high),
+                                  _i16(motion), types, n, X, Y, block_size,
+                                  C.c_float(update_factor), _u8(out)))
+        return out
+
+    def un_update(self, low, high, motion, frame_types, X, Y, block_size=16, update_factor=0.25):
+        return self.update(low, high, motion, frame_types, X, Y, block_size, update_factor, True)
+
+    # ---- whole-sequence analysis / synthesis with frames resident in HBM
+    @staticmethod
+    def _params(X, Y, TRLs, block_size, search_range, subpixel_accuracy, update_factor, always_B,
+                block_overlaping, border_size, block_size_min, first_global=True):
+        return AnalyzeParams(X, Y, TRLs, block_size, block_size_min, border_size,
+                             block_overlaping, search_range, subpixel_accuracy, always_B,
+                             float(update_factor), 1 if first_global else 0)
+
+    def resident_load(self, low0, X, Y):
+        low0 = np.ascontiguousarray(low0, np.uint8)
+        assert low0.shape[1] == frame_bytes(X, Y)
+        check(self._L.qsvc_resident_load(self._h, _u8(low0), low0.shape[0], X, Y))
+        self._geom = (X, Y, low0.shape[0])
+
+    def resident_analyze(self, TRLs, block_size=32, search_range=4, subpixel_accuracy=0,
+                         update_factor=0.0, always_B=0, block_overlaping=0, border_size=0,
+                         block_size_min=32, first_global=True):
+        X, Y, _ = self._geom
+        p = self._params(X, Y, TRLs, block_size, search_range, subpixel_accuracy, update_factor,
+                         always_B, block_overlaping, border_size, block_size_min, first_global)
+        check(self._L.qsvc_resident_analyze(self._h, C.byref(p)))
+        self._last = (TRLs, block_size, search_range, block_size_min)
+
+    def resident_stats(self):
+        ops, sms, tms = C.c_double(), C.c_float(), C.c_float()
+        check(self._L.qsvc_resident_stats(self._h, C.byref(ops), C.byref(sms), C.byref(tms)))
+        return dict(sad_ops=ops.value, search_ms=sms.value, total_ms=tms.value)
+
+    def resident_fetch(self, t, n_pairs, block_size, want=("high", "motion", "motion_filtered",
+                                                           "frame_types", "low")):
+        X, Y, _ = self._geom
+        fb = frame_bytes(X, Y)
+        by, bx = Y // block_size, X // block_size
+        high = np.zeros((n_pairs, fb), np.uint8) if "high" in want else None
+        mv = np.zeros((n_pairs, 4, by, bx), np.int16) if "motion" in want else None
+        mvf = np.zeros((n_pairs, 4, by, bx), np.int16) if "motion_filtered" in want else None
+        low = np.zeros((n_pairs + 1, fb), np.uint8) if "low" in want else None
+        types = C.create_string_buffer(max(n_pairs, 1))
+        check(self._L.qsvc_resident_fetch(
+            self._h, t, _u8(high) if high is not None else None,
+            _i16(mv) if mv is not None else None, _i16(mvf) if mvf is not None else None, types,
+            _u8(low) if low is not None else None))
+        return dict(high=high, motion=mv, motion_filtered=mvf, frame_types=types.raw[:n_pairs],
+                    low=low)
+
+    def analyze(self, low0, X, Y, GOPs, TRLs, block_size=32, search_range=4, subpixel_accuracy=0,
+                update_factor=0.0, always_B=0, block_overlaping=0, border_size=0,
+                block_size_min=32, first_global=True):
+        """analyze.py equivalent on arrays: returns {file name: payload}."""
+        low0 = np.ascontiguousarray(low0, np.uint8)
+        assert low0.shape[0] == GOPs * gop_size(TRLs) + 1
+        self.resident_load(low0, X, Y)
+        self.resident_analyze(TRLs, block_size, search_range, subpixel_accuracy, update_factor,
+                              always_B, block_overlaping, border_size, block_size_min, first_global)
+        out = {}
+        for s in level_schedule(GOPs, TRLs, block_size, search_range, block_size_min):
+            r = self.resident_fetch(s["t"], s["pairs"], s["block_size"])
+            t = s["t"]
+            out[f"high_{t}"] = r["high"]
+            out[f"motion_{t}"] = r["motion"]
+            out[f"motion_filtered_{t}"] = r["motion_filtered"]
+            out[f"frame_types_{t}"] = r["frame_types"]
+            out[f"low_{t}"] = r["low"]
+        return out
+
+    def synthesize(self, subbands, X, Y, GOPs, TRLs, block_size=16, search_range=4,
+                   subpixel_accuracy=0, update_factor=0.25, block_overlaping=0):
+        """synthesize.py equivalent on arrays.  `subbands` maps high_t, motion_t,
+        frame_types_t (t = 1..TRLs-1) and low_{TRLs-1} to their payloads.  Returns low_0."""
+        fb = frame_bytes(X, Y)
+        for t in range(TRLs - 1, 0, -1):
+            high = np.ascontiguousarray(subbands[f"high_{t}"], np.uint8)
+            mv = np.ascontiguousarray(subbands[f"motion_{t}"], np.int16)
+            types = bytes(subbands[f"frame_types_{t}"])
+            n = high.shape[0]
+            low_top = None
+            if t == TRLs - 1:
+                low_top = np.ascontiguousarray(subbands[f"low_{t}"], np.uint8)
+                assert low_top.shape == (n + 1, fb)
+            tb = C.create_string_buffer(types, max(n, 1))
+            check(self._L.qsvc_resident_push(self._h, t, n, _u8(high), _i16(mv), tb,
+                                             _u8(low_top) if low_top is not None else None, X, Y,
+                                             block_size))
+        p = self._params(X, Y, TRLs, block_size, search_range, subpixel_accuracy, update_factor, 1,
+                         block_overlaping, 0, block_size)
+        check(self._L.qsvc_resident_synthesize(self._h, C.byref(p)))
+        frames = GOPs * gop_size(TRLs) + 1
+        out = np.zeros((frames, fb), np.uint8)
+        check(self._L.qsvc_resident_fetch_low0(self._h, _u8(out), frames))
+        self._geom = (X, Y, frames)
+        return out

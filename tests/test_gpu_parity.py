@@ -1,0 +1,122 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Bit-exact: motion fields, high/low/odd/even frames, frame types, predictions.
+Geometries follow SURVEY.md Appendix C item 10: each one triggers a distinct
+quirk of the reference (heap aliasing, border pollution at sub-pixel levels, odd
+pyramid sizes, heights that are not a multiple of the block size, I/B decision,
+update scatter order).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from qsvc_b200 import yuv
+from qsvc_b200.mctf import level_schedule
+
+pytestmark = pytest.mark.gpu
+
+#        X    Y   GOPs TRLs bs  sr  a  uf    flat
+CASES = [
+    (352, 288, 1, 5, 16, 4, 0, 0.0, 0),    # cfg1 geometry; sr reaches 32 (heap alias at a=0)
+    (128, 96, 1, 4, 16, 8, 2, 0.25, 0),    # quarter-pel: size-field read + border pollution
+    (128, 96, 1, 3, 16, 16, 1, 0.3, 0),    # half-pel, non-dyadic update factor
+    (128, 120, 1, 4, 8, 32, 0, 0.0, 0),    # odd pyramid sizes, sr 32/64/128: carried reference[0]
+    (128, 72, 2, 5, 16, 4, 2, 0.25, 0),    # height % block_size != 0: chained prediction tail
+    (128, 96, 2, 3, 16, 4, 0, 0.25, 2),    # IBIB frame types
+    (96, 64, 1, 3, 16, 6, 1, 0.25, 0),     # search range that is not a power of two
+    (80, 48, 1, 3, 16, 16, 2, 0.25, 0),    # border larger than the picture
+    (176, 144, 2, 3, 32, 4, 1, 0.5, 3),    # X % bs != 0 (uncovered columns)
+]
+
+
+def clip_for(X, Y, GOPs, TRLs, sr, flat, seed=7):
+    frames = GOPs * 2 ** (TRLs - 1) + 1
+    return yuv.synthetic_clip(X, Y, frames, seed, max_shift=min(48, 3 * sr), flat_every=flat)
+
+
+@pytest.mark.parametrize("X,Y,GOPs,TRLs,bs,sr,a,uf,flat", CASES)
+def test_tools_match_oracle(ctx, X, Y, GOPs, TRLs, bs, sr, a, uf, flat):
+    """Each tool on its own, levels chained through the oracle's outputs."""
+    low = clip_for(X, Y, GOPs, TRLs, sr, flat)
+    for s in level_schedule(GOPs, TRLs, bs, sr, block_size_min=bs):
+        even, odd = low[0::2], low[1::2]
+        b, r = s["block_size"], s["search_range"]
+        mv_o = orc.motion_estimate(even, odd, X, Y, b, r, a)
+        mv_g = ctx.motion_estimate(even, odd, X, Y, b, r, a)
+        assert np.array_equal(mv_g, mv_o), f"motion_{s['t']}: {(mv_g != mv_o).sum()} components differ"
+        high_o, types_o, mvf_o, pred_o, rc = orc.decorrelate(even, odd, mv_o, X, Y, b, r, a)
+        assert rc == 0
+        high_g, types_g, mvf_g, pred_g = ctx.decorrelate(even, odd, mv_o, X, Y, b, r, a,
+                                                         want_prediction=True)
+        assert types_g == types_o
+        assert np.array_equal(pred_g, pred_o), f"prediction_{s['t']}: {(pred_g != pred_o).sum()} samples differ"
+        assert np.array_equal(high_g, high_o), f"high_{s['t']}: {(high_g != high_o).sum()} samples differ"
+        assert np.array_equal(mvf_g, mvf_o)
+        low_o = orc.update(even, high_o, mvf_o, types_o, X, Y, b, uf)
+        low_g = ctx.update(even, high_o, mvf_o, types_o, X, Y, b, uf)
+        assert np.array_equal(low_g, low_o), f"low_{s['t']}: {(low_g != low_o).sum()} samples differ"
+        # inverse tools on the same level
+        even_o = orc.update(low_o, high_o, mvf_o, types_o, X, Y, b, uf, inverse=True)
+        even_g = ctx.un_update(low_o, high_o, mvf_o, types_o, X, Y, b, uf)
+        assert np.array_equal(even_g, even_o)
+        odd_o, _ = orc.correlate(even_o, high_o, mvf_o, types_o, X, Y, b, r, a)
+        odd_g, _ = ctx.correlate(even_o, high_o, mvf_o, types_o, X, Y, b, r, a)
+        assert np.array_equal(odd_g, odd_o)
+        low = low_o
+
+
+@pytest.mark.parametrize("X,Y,GOPs,TRLs,bs,sr,a,uf,flat", CASES[:6])
+def test_resident_analyze_synthesize_match_oracle(ctx, X, Y, GOPs, TRLs, bs, sr, a, uf, flat):
+    """Whole-sequence analysis and synthesis with frames resident in HBM."""
+    clip = clip_for(X, Y, GOPs, TRLs, sr, flat, seed=11)
+    ref = orc.analyze(clip, X, Y, TRLs, bs, sr, a, uf, block_size_min=bs)
+    got = ctx.analyze(clip, X, Y, GOPs, TRLs, bs, sr, a, uf, block_size_min=bs)
+    for t in range(1, TRLs):
+        for name in ("motion", "motion_filtered", "high", "low"):
+            assert np.array_equal(got[f"{name}_{t}"], ref[f"{name}_{t}"]), f"{name}_{t}"
+        assert got[f"frame_types_{t}"] == ref[f"frame_types_{t}"]
+    # synthesis from the analysis outputs (motion_filtered_t plays motion_t)
+    sub = {f"low_{TRLs-1}": ref[f"low_{TRLs-1}"]}
+    low = ref[f"low_{TRLs-1}"]
+    sched = level_schedule(GOPs, TRLs, bs, sr, block_size_min=bs)
+    for s in reversed(sched):
+        t = s["t"]
+        sub[f"high_{t}"], sub[f"motion_{t}"] = ref[f"high_{t}"], ref[f"motion_filtered_{t}"]
+        sub[f"frame_types_{t}"] = ref[f"frame_types_{t}"]
+        even = orc.update(low, sub[f"high_{t}"], sub[f"motion_{t}"], sub[f"frame_types_{t}"], X, Y,
+                          bs, uf, inverse=True)
+        odd, _ = orc.correlate(even, sub[f"high_{t}"], sub[f"motion_{t}"], sub[f"frame_types_{t}"],
+                               X, Y, bs, s["search_range"], a)
+        low = np.empty((2 * odd.shape[0] + 1, even.shape[1]), np.uint8)
+        low[0::2], low[1::2] = even, odd
+    rec = ctx.synthesize(sub, X, Y, GOPs, TRLs, bs, sr, a, uf)
+    assert np.array_equal(rec, low)
+
+
+def test_first_pair_flag_for_gop_shards(ctx):
+    """A later GOP shard must start from the carried (non-restored) reference[0]
+    when the pyramid is not perfectly reconstructing."""
+    X, Y, bs, sr = 128, 120, 8, 64
+    clip = yuv.synthetic_clip(X, Y, 9, 5, max_shift=40)
+    even, odd = clip[0::2], clip[1::2]
+    full = orc.motion_estimate(even, odd, X, Y, bs, sr, 0)
+    part = ctx.motion_estimate(even[2:], odd[2:], X, Y, bs, sr, 0, first_pair_is_global_first=False)
+    assert np.array_equal(part, full[2:])
+    part_fresh = ctx.motion_estimate(even[2:], odd[2:], X, Y, bs, sr, 0)
+    assert np.array_equal(part_fresh, orc.motion_estimate(even[2:], odd[2:], X, Y, bs, sr, 0))
+
+
+def test_domain_error_on_large_vectors(ctx):
+    """always_B=0 with |mv| > 127 is undefined behaviour in the reference; the
+    library must refuse loudly instead of inventing a result."""
+    from qsvc_b200._lib import QsvcError, QSVC_EDOMAIN
+    X, Y, bs = 64, 48, 16
+    clip = yuv.synthetic_clip(X, Y, 3, 1)
+    mv = np.zeros((1, 4, Y // bs, X // bs), np.int16)
+    mv[0, 0, 0, 0] = 200
+    with pytest.raises(QsvcError) as e:
+        ctx.decorrelate(clip[0::2], clip[1::2], mv, X, Y, bs, 64, 0, always_B=0)
+    assert e.value.code == QSVC_EDOMAIN
+    high, types, mvo, _ = ctx.decorrelate(clip[0::2], clip[1::2], mv, X, Y, bs, 64, 0, always_B=1)
+    ref = orc.decorrelate(clip[0::2], clip[1::2], mv, X, Y, bs, 64, 0, always_B=1)
+    assert np.array_equal(high, ref[0]) and types == ref[1] == b"B"
