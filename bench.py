@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the MCTF analysis hot path on B200.
+
+Metric (BASELINE.json): 1080p MCTF analysis frames/s (+ ME SAD Gops/s).
+A "step" is one full temporal analysis (all TRLs-1 levels: split ->
+motion_estimate -> decorrelate -> update) of one synthetic clip per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                  [--workload cfg3|cfg2|cfg1|cfg4]
+
+N > 1: launched under torchrun, one rank per GPU; whole GOPs are sharded (each
+rank analyses its own clip of the named shape: weak scaling, no data-path
+collective); NCCL is used only for the barrier and the max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: X, Y, GOPs, TRLs(reference flag), block, search range, subpixel, always_B
+    "cfg1": dict(X=352, Y=288, GOPs=2, TRLs=5, bs=16, sr=4, a=0, always_B=0,
+                 desc="CIF 352x288, 33 frames, GOP 16, block 16, search 4, integer-pel"),
+    "cfg2": dict(X=704, Y=576, GOPs=4, TRLs=5, bs=16, sr=8, a=1, always_B=0,
+                 desc="4CIF 704x576, 65 frames, GOP 16, block 16, search 8, half-pel"),
+    "cfg3": dict(X=1920, Y=1080, GOPs=4, TRLs=6, bs=16, sr=16, a=2, always_B=1,
+                 desc="1080p 1920x1080, 129 frames, GOP 32, block 16, search 16, quarter-pel"),
+    "cfg4": dict(X=3840, Y=2160, GOPs=8, TRLs=6, bs=16, sr=16, a=0, always_B=1,
+                 desc="2160p 3840x2160, 257 frames, GOP 32, block 16, search 16, integer-pel"),
+}
+SEEDS = {"cfg1": 1, "cfg2": 11, "cfg3": 2, "cfg4": 13}
+
+
+def n_frames(w):
+    return w["GOPs"] * 2 ** (w["TRLs"] - 1) + 1
+
+
+def desp(x, l):
+    for _ in range(l):
+        x = (x + 1) // 2
+    return x
+
+
+def sad_ops_total(w):
+    """18 * [sum_l bs^2 * blocks(l) + sum_subpel (bs<<l)^2 * blocks] per pair."""
+    import math
+    BY, BX = w["Y"] // w["bs"], w["X"] // w["bs"]
+    pictures, sr, total = n_frames(w), w["sr"], 0.0
+    for _ in range(1, w["TRLs"]):
+        L = max(0, int(round(math.log2(sr))) - 1)
+        per_pair = sum(w["bs"] ** 2 * desp(BY, l) * desp(BX, l) for l in range(L + 1))
+        per_pair += sum((w["bs"] << l) ** 2 * BY * BX for l in range(1, w["a"] + 1))
+        total += 18.0 * per_pair * (pictures // 2)
+        pictures = (pictures + 1) // 2
+        sr = min(2 * sr, 128)
+    return total
+
+
+def mc_bytes_total(w):
+    """every input frame of a level read once, every output frame
+    written once (high + low), plus the motion fields read and written."""
+    fb = w["X"] * w["Y"] * 3 // 2
+    BY, BX = w["Y"] // w["bs"], w["X"] // w["bs"]
+    pictures, total = n_frames(w), 0
+    for _ in range(1, w["TRLs"]):
+        pairs = pictures // 2
+        total += fb * (pictures + pairs + pairs + 1) + 16 * BY * BX * pairs
+        pictures = (pictures + 1) // 2
+    return total
+
+
+# ------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for name, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------- reference (CPU) arm
+
+def cpu_reference_sample(w, procs, pairs_per_proc=1):
+    """Times the reference's own CPU tools (oracle/_ref, unmodified) on a bounded
+    sample of the workload: `procs` independent chains, each `pairs_per_proc`
+    frame pair(s) of the workload's shape at temporal level 1 (split,
+    motion_estimate, decorrelate, update), run concurrently on the host cores.
+    The reference's cost is linear in the number of pairs, so
+    frames/s for the whole clip = frames / (pairs_total * seconds_per_pair / procs).
+    Upper levels use larger search ranges and cost more per pair, so this
+    flatters the CPU."""
+    from oracle import run_ref
+    from qsvc_b200 import yuv
+    if not run_ref.build():
+        return None
+    X, Y = w["X"], w["Y"]
+    frames = 2 * pairs_per_proc + 1
+    clip = yuv.synthetic_clip(X, Y, frames, 99, max_shift=min(48, 3 * w["sr"]))
+    tmp = tempfile.mkdtemp(prefix="qsvc_ref_")
+    dirs = []
+    for p in range(procs):
+        d = os.path.join(tmp, f"p{p}")
+        os.makedirs(d)
+        yuv.write_frames(os.path.join(d, "low_0"), clip)
+        dirs.append(d)
+    errs = []
+
+    def chain(d):
+        try:
+            run_ref.analyze_step(d, 1, frames, X, Y, w["bs"], w["sr"], w["a"], 0.0, w["always_B"])
+        except Exception as e:  # noqa: BLE001
+            errs.append(str(e))
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=chain, args=(d,)) for d in dirs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    subprocess.call(["rm", "-rf", tmp])
+    if errs:
+        raise RuntimeError("reference chain failed: " + errs[0])
+    pairs_total = sum(s // 2 for s in _pictures_per_level(w))
+    sec_per_pair = dt / (procs * pairs_per_proc)
+    fps = n_frames(w) / (pairs_total * sec_per_pair)
+    return dict(value=fps, seconds=dt, sec_per_pair_per_core=dt / pairs_per_proc, procs=procs,
+                sample=f"{procs} concurrent chains x {pairs_per_proc} pair(s) of {X}x{Y} at level 1 "
+                       f"(sr={w['sr']}, a={w['a']}, bs={w['bs']}), {dt:.1f} s wall; extrapolated "
+                       f"linearly to the clip's {pairs_total} pairs")
+
+
+def _pictures_per_level(w):
+    out, p = [], n_frames(w)
+    for _ in range(1, w["TRLs"]):
+        out.append(p)
+        p = (p + 1) // 2
+    return out
+
+
+# ----------------------------------------------------------------------- main
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wname = args.workload or "cfg3"
+    w = WORKLOADS[wname]
+    frames = n_frames(w)
+    cfg = {"workload": f"{wname}: {w['desc']} (reference flags --TRLs={w['TRLs']} --GOPs={w['GOPs']}"
+                       f" --update_factor=0 --always_B={w['always_B']})",
+           "frames_per_gpu": frames, "sharding": "whole GOPs per GPU, no collective",
+           "l2": f"inputs {frames * w['X'] * w['Y'] * 3 // 2 / 1e6:.0f} MB per step exceed the 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        procs = min(os.cpu_count() or 1, 32)
+        r = cpu_reference_sample(w, procs)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+            return 0
+        # --steps/--warmup: the sample is one bounded pass; repeating it K times would
+        # only repeat the same CPU work, so K is honoured as min(K, 1) passes.
+        line = {"metric": "1080p MCTF analysis frames/s" if wname == "cfg3" else f"{wname} MCTF analysis frames/s",
+                "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": frames / r["value"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+                "data": "synthetic", "config": cfg, "impl": "reference",
+                "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": procs,
+                                 "kind": "reference", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from qsvc_b200 import yuv
+    from qsvc_b200.mctf import Context, level_schedule
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (qsvc_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # one clip per rank (different seed per rank: independent GOP shards)
+    clip = yuv.synthetic_clip(w["X"], w["Y"], frames, SEEDS[wname] + 1000 * rank,
+                              max_shift=min(48, 3 * w["sr"]))
+    pinned = torch.empty(clip.shape, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[...] = clip
+    clip_pinned = pinned.numpy()
+
+    ctx = Context(local_rank)
+    kw = dict(TRLs=w["TRLs"], block_size=w["bs"], search_range=w["sr"], subpixel_accuracy=w["a"],
+              update_factor=0.0, always_B=w["always_B"], block_size_min=w["bs"])
+    sched = level_schedule(w["GOPs"], w["TRLs"], w["bs"], w["sr"], w["bs"])
+
+    # ---- device-resident throughput: inputs already in HBM when the timed region starts
+    ctx.resident_load(clip_pinned, w["X"], w["Y"])
+    for _ in range(max(args.warmup, 3)):
+        ctx.resident_analyze(**kw)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = ctx.launches
+    ctx.profile_enable(True)
+    ctx.timer_start()
+    for _ in range(args.steps):
+        ctx.resident_analyze(**kw)
+    ms = ctx.timer_stop()
+    barrier()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    clocks = sampler.stop()
+    launches = ctx.launches - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * frames / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers (H2D + analysis + D2H)
+    fb = clip.shape[1]
+    outs = {}
+    h2d = clip.nbytes
+    d2h = 0
+    for s in sched:
+        n, b = s["pairs"], s["block_size"]
+        d2h += n * fb + 2 * n * 8 * (w["Y"] // b) * (w["X"] // b) + n
+        if s["t"] == w["TRLs"] - 1:
+            d2h += (n + 1) * fb
+
+    def e2e_step():
+        ctx.resident_load(clip_pinned, w["X"], w["Y"])
+        ctx.resident_analyze(**kw)
+        for s in sched:
+            want = ("high", "motion", "motion_filtered", "frame_types") + (
+                ("low",) if s["t"] == w["TRLs"] - 1 else ())
+            outs[s["t"]] = ctx.resident_fetch(s["t"], s["pairs"], s["block_size"], want)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * frames * args.steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- rooflines
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+    u8_peak, i32_peak = ctx.int_peak()
+    steps = args.steps
+    cls_ms = {k: v[0] / steps for k, v in prof.items()}
+    cls_n = {k: v[1] // steps for k, v in prof.items()}
+    sad = sad_ops_total(w)
+    search_ms = cls_ms["search"]
+    me_ms = cls_ms["search"] + cls_ms["dwt_rows"] + cls_ms["dwt_cols"]  # upper bound: includes MC's DWT
+    mc_ms = cls_ms["predict"] + cls_ms["residue"] + cls_ms["update"]
+    dominant = max(cls_ms, key=cls_ms.get)
+    rooflines = {
+        "me_search": {"bound": "int-sad", "achieved": sad / (search_ms * 1e-3) / 1e9 if search_ms else None,
+                      "peak": u8_peak / 1e9, "peak_i32": i32_peak / 1e9, "unit": "G SAD-op/s",
+                      "frac": (sad / (search_ms * 1e-3)) / u8_peak if search_ms else None,
+                      "note": "peak = measured __vsadu4 issue rate x4 (qsvc_int_peak); algorithmic SAD-ops of SURVEY 8(d)"},
+        "mc_path": {"bound": "hbm", "achieved": mc_bytes_total(w) / (ms_per_step * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s",
+                    "frac": mc_bytes_total(w) / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                    "note": "algorithmic frame+motion bytes of all levels / whole step time"},
+    }
+    # the dominant kernel class of the step, against the bound that applies to it
+    share = cls_ms[dominant] / max(1e-9, sum(cls_ms.values()))
+    if dominant == "search":
+        roof = {"bound": "int-sad", "kernel": "k_search", "achieved": rooflines["me_search"]["achieved"],
+                "peak": u8_peak / 1e9, "unit": "G SAD-op/s", "frac": rooflines["me_search"]["frac"],
+                "traffic": None, "share_of_step": share}
+    else:
+        # DWT / predict / image kernels stream int16 planes: report them against HBM using
+        # the step's algorithmic bytes attributed to that class
+        alg = mc_bytes_total(w)
+        ach = alg / (cls_ms[dominant] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "share_of_step": share,
+                "peak_source": hbm_src}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            r = cpu_reference_sample(w, min(os.cpu_count() or 1, 32))
+            if r:
+                cpu = {"value": r["value"], "unit": "frames/s", "cores": r["procs"],
+                       "kind": "reference", "sample": r["sample"]}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
+                   "sample": f"failed: {e}"}
+
+    line = {
+        "metric": "1080p MCTF analysis frames/s" if wname == "cfg3" else f"{wname} MCTF analysis frames/s",
+        "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": cfg, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "roofline": roof, "rooflines": rooflines,
+        "me_sad_gops": sad / (ms_per_step * 1e-3) / 1e9,
+        "kernel_ms_per_step": cls_ms, "kernel_launches_per_step": cls_n,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -46,6 +46,9 @@ SIGNATURES = {
     "qsvc_timer_start": (_i, [C.c_void_p]),
     "qsvc_timer_stop": (_i, [C.c_void_p, C.POINTER(C.c_float)]),
     "qsvc_synchronize": (_i, [C.c_void_p]),
+    "qsvc_profile_enable": (_i, [C.c_void_p, _i]),
+    "qsvc_profile_read": (_i, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong), _i]),
+    "qsvc_int_peak": (_i, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qsvc_motion_estimate": (_i, [C.c_void_p, u8p, u8p, _i, _i, _i, _i, _i, _i, _i, _i, i16p]),
     "qsvc_decorrelate": (_i, [C.c_void_p, u8p, u8p, i16p, _i, _i, _i, _i, _i, _i, _i, _i, u8p,
                               C.c_void_p, i16p, u8p]),

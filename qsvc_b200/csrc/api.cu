@@ -65,6 +65,7 @@ struct qsvc_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   long long launches = 0;
+  Profiler prof;
   std::vector<PoolBlock> pool;
   size_t me_budget = (size_t)40 << 30;  // bytes of HBM for the ME image planes of one chunk
   // resident sequence
@@ -73,7 +74,7 @@ struct qsvc_ctx {
   std::vector<LevelResult> levels;  // index t (0 unused)
   double sad_ops = 0;
   float search_ms = 0, total_ms = 0;
-  Launch L() { return Launch{stream, &launches}; }
+  Launch L() { return Launch{stream, &launches, &prof}; }
 };
 
 static int pool_alloc(qsvc_ctx *c, size_t bytes, void **out) {
@@ -620,6 +621,61 @@ int qsvc_timer_stop(qsvc_ctx *c, float *ms) {
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaEventSynchronize(c->ev1));
   CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return QSVC_OK;
+}
+// Measured issue rate of the SAD instructions: SAD operations per second with
+// packed bytes (__vsadu4) and with 32-bit lanes (__sad), best of 5.
+int qsvc_int_peak(qsvc_ctx *c, double *u8_sad_ops_per_s, double *i32_sad_ops_per_s) {
+  if (!c) return fail(QSVC_EINVAL, "null context");
+  CU(cudaSetDevice(c->device));
+  const int blocks = 148 * 8, iters = 4096;
+  Scratch s(c);
+  unsigned *d_out;
+  TRY(s.get((size_t)blocks * 256 * sizeof(unsigned), (void **)&d_out));
+  for (int packed = 1; packed >= 0; packed--) {
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+      CU(cudaEventRecord(c->ev0, c->stream));
+      int e = run_int_peak(c->stream, d_out, blocks, iters, packed != 0);
+      if (e) return fail(QSVC_ECUDA, "int peak launch: %s", cudaGetErrorString((cudaError_t)e));
+      c->launches++;
+      CU(cudaEventRecord(c->ev1, c->stream));
+      CU(cudaEventSynchronize(c->ev1));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+      double ops = (double)blocks * 256 * iters * 8 * (packed ? 4 : 1);
+      if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    if (packed && u8_sad_ops_per_s) *u8_sad_ops_per_s = best;
+    if (!packed && i32_sad_ops_per_s) *i32_sad_ops_per_s = best;
+  }
+  return QSVC_OK;
+}
+int qsvc_profile_enable(qsvc_ctx *c, int on) {
+  if (!c) return fail(QSVC_EINVAL, "null context");
+  c->prof.enabled = on != 0;
+  c->prof.n = 0;
+  return QSVC_OK;
+}
+// Sums the per-launch event pairs recorded since the last call, per kernel class.
+int qsvc_profile_read(qsvc_ctx *c, float *ms, long long *launches, int n_classes) {
+  if (!c) return fail(QSVC_EINVAL, "null context");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < n_classes; k++) {
+    if (ms) ms[k] = 0.f;
+    if (launches) launches[k] = 0;
+  }
+  for (int i = 0; i < c->prof.n; i++) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, c->prof.recs[i].a, c->prof.recs[i].b));
+    int k = c->prof.recs[i].cls;
+    if (k < n_classes) {
+      if (ms) ms[k] += t;
+      if (launches) launches[k]++;
+    }
+  }
+  c->prof.n = 0;
   return QSVC_OK;
 }
 int qsvc_synchronize(qsvc_ctx *c) {

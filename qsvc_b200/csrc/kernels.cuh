@@ -2,9 +2,37 @@
 #pragma once
 #include "common.cuh"
 
+// Kernel classes for the per-class device timers (qsvc_profile_*).
+enum {
+  KC_IMG = 0,     // frame load/store, border fill, size fields, copies
+  KC_DWT_ROWS,    // 5/3 row passes
+  KC_DWT_COLS,    // 5/3 column passes
+  KC_SEARCH,      // block search (SAD)
+  KC_PREDICT,     // motion-compensated prediction (+ clip)
+  KC_RESIDUE,     // residue / reconstruction / histograms
+  KC_UPDATE,      // update lifting step
+  KC_COUNT
+};
+
+struct Profiler {
+  bool enabled = false;
+  struct Rec { cudaEvent_t a, b; int cls; };
+  Rec *recs = nullptr;
+  int n = 0, cap = 0;
+};
+
 struct Launch {
   cudaStream_t stream;
   long long *counter;  // number of kernels launched (host side)
+  Profiler *prof;
+};
+
+// RAII: brackets one kernel launch with two events when profiling is enabled.
+struct ProfScope {
+  const Launch &L;
+  int idx;
+  ProfScope(const Launch &l, int cls);
+  ~ProfScope();
 };
 
 // ---- image preparation (kernels_img.cu) ----
@@ -42,6 +70,7 @@ struct SearchParams {
   int mode, lim;
 };
 void launch_search(const Launch &L, const SearchParams &q, int npairs);
+int run_int_peak(cudaStream_t stream, unsigned *d_out, int blocks, int iters, bool packed);
 
 // ---- motion compensation (kernels_mc.cu) ----
 struct PredictParams {

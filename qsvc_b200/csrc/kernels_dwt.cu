@@ -61,6 +61,7 @@ int dwt_init_attributes() {
 static void launch_rows(const Launch &L, Plane p, int slot0, int nslots, int ny, int nx, bool synth) {
   dim3 grid(ny < 2048 ? ny : 2048, 1, nslots);
   size_t smem = (size_t)nx * sizeof(short);
+  ProfScope ps_(L, KC_DWT_ROWS);
   if (synth)
     k_dwt_rows<true><<<grid, 256, smem, L.stream>>>(p, slot0, ny, nx);
   else
@@ -75,6 +76,7 @@ static void launch_cols(const Launch &L, Plane p, int slot0, int nslots, int ny,
   while (cw_log2 > 3 && ((nx + (1 << cw_log2) - 1) >> cw_log2) * nslots < 296) cw_log2--;
   dim3 grid((nx + (1 << cw_log2) - 1) >> cw_log2, 1, nslots);
   size_t smem = ((size_t)ny << cw_log2) * sizeof(short);
+  ProfScope ps_(L, KC_DWT_COLS);
   if (synth)
     k_dwt_cols<true><<<grid, 256, smem, L.stream>>>(p, slot0, ny, nx, cw_log2);
   else

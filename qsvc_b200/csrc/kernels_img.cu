@@ -4,7 +4,30 @@
 // texture.cpp:55-113 (fill_border, 8 regions), texture.cpp:34-46 (alloc).
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 #define COUNT(L) (++*(L).counter)
+
+ProfScope::ProfScope(const Launch &l, int cls) : L(l), idx(-1) {
+  Profiler *p = L.prof;
+  if (!p || !p->enabled) return;
+  if (p->n == p->cap) {
+    int ncap = p->cap ? p->cap * 2 : 4096;
+    p->recs = (Profiler::Rec *)realloc(p->recs, sizeof(Profiler::Rec) * ncap);
+    for (int i = p->cap; i < ncap; i++) {
+      cudaEventCreate(&p->recs[i].a);
+      cudaEventCreate(&p->recs[i].b);
+    }
+    p->cap = ncap;
+  }
+  idx = p->n++;
+  p->recs[idx].cls = cls;
+  cudaEventRecord(p->recs[idx].a, L.stream);
+}
+
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(L.prof->recs[idx].b, L.stream);
+}
 
 __global__ void k_load_u8(Plane dst, int slot0, const uint8_t *__restrict__ src,
                           long long frame_stride, long long comp_off, int f0, int fstep, int h,
@@ -23,6 +46,7 @@ void launch_load_u8(const Launch &L, Plane dst, int slot0, int nslots, const uin
                     long long frame_stride, long long comp_off, int f0, int fstep, int h, int w) {
   if (nslots <= 0 || h <= 0 || w <= 0) return;
   dim3 grid((w + 255) / 256, h < 1024 ? h : 1024, nslots);
+  ProfScope ps_(L, KC_IMG);
   k_load_u8<<<grid, 256, 0, L.stream>>>(dst, slot0, src, frame_stride, comp_off, f0, fstep, h, w);
   COUNT(L);
 }
@@ -43,6 +67,7 @@ void launch_store_u8(const Launch &L, Plane src, int slot0, int nslots, uint8_t 
                      long long frame_stride, long long comp_off, int f0, int fstep, int h, int w) {
   if (nslots <= 0 || h <= 0 || w <= 0) return;
   dim3 grid((w + 255) / 256, h < 1024 ? h : 1024, nslots);
+  ProfScope ps_(L, KC_IMG);
   k_store_u8<<<grid, 256, 0, L.stream>>>(src, slot0, dst, frame_stride, comp_off, f0, fstep, h, w);
   COUNT(L);
 }
@@ -63,6 +88,7 @@ __global__ void k_size_fields(Plane p, int slot0, int rows) {
 void launch_size_fields(const Launch &L, Plane p, int slot0, int nslots, int rows) {
   if (nslots <= 0) return;
   dim3 grid((rows + 127) / 128, nslots);
+  ProfScope ps_(L, KC_IMG);
   k_size_fields<<<grid, 128, 0, L.stream>>>(p, slot0, rows);
   COUNT(L);
 }
@@ -104,6 +130,7 @@ void launch_fill_border(const Launch &L, Plane p, int slot0, int nslots, int Y, 
     int h = (region >= 4 && region <= 5) ? Y : b;
     int w = (region == 2 || region == 7) ? X : b;
     dim3 grid((w + 127) / 128, h < 512 ? h : 512, nslots);
+    ProfScope ps_(L, KC_IMG);
     k_fill_region<<<grid, 128, 0, L.stream>>>(p, slot0, region, Y, X, b);
     COUNT(L);
   }

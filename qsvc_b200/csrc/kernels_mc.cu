@@ -35,6 +35,7 @@ void launch_predict(const Launch &L, const PredictParams &q) {
   int cy = q.BY * q.bsa, cx = q.BX * q.bsa;
   if (cy <= 0 || cx <= 0) return;
   dim3 grid((cx + 1023) / 1024, cy < 2048 ? cy : 2048, 3);
+  ProfScope ps_(L, KC_PREDICT);
   k_predict<<<grid, 256, 0, L.stream>>>(q);
   COUNT(L);
 }
@@ -58,6 +59,7 @@ __global__ void k_clip_uncovered(Plane pred, int Ya, int Xa, int cy, int cx) {
 void launch_clip_uncovered(const Launch &L, Plane pred, int Ya, int Xa, int cy, int cx) {
   if (cy >= Ya && cx >= Xa) return;
   dim3 grid(8, Ya < 1024 ? Ya : 1024, 3);
+  ProfScope ps_(L, KC_PREDICT);
   k_clip_uncovered<<<grid, 256, 0, L.stream>>>(pred, Ya, Xa, cy, cx);
   COUNT(L);
 }
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(256) k_residue(ResidueParams q) {
 
 void launch_residue(const Launch &L, const ResidueParams &q) {
   dim3 grid((q.X + 1023) / 1024, q.Y < 296 ? q.Y : 296, 3);
+  ProfScope ps_(L, KC_RESIDUE);
   k_residue<<<grid, 256, 0, L.stream>>>(q);
   COUNT(L);
 }
@@ -130,6 +133,7 @@ __global__ void k_mv_hist(const short *__restrict__ mv, int n, int *hist) {
 void launch_mv_hist(const Launch &L, const short *mv, int n, int *hist) {
   if (n <= 0) return;
   int blocks = (n + 255) / 256;
+  ProfScope ps_(L, KC_RESIDUE);
   k_mv_hist<<<blocks < 64 ? blocks : 64, 256, 0, L.stream>>>(mv, n, hist);
   COUNT(L);
 }
@@ -153,6 +157,7 @@ void launch_copy_bytes(const Launch &L, void *dst, const void *src, size_t n) {
   size_t blocks = (n / 16 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope ps_(L, KC_IMG);
   k_copy_bytes<<<(int)blocks, 256, 0, L.stream>>>((uint8_t *)dst, (const uint8_t *)src, n);
   COUNT(L);
 }
@@ -168,6 +173,7 @@ __global__ void k_load_residue(Plane dst, int slot, const uint8_t *__restrict__ 
 
 void launch_load_residue(const Launch &L, Plane dst, int slot, const uint8_t *src, int h, int w) {
   dim3 grid((w + 255) / 256, h < 1024 ? h : 1024);
+  ProfScope ps_(L, KC_IMG);
   k_load_residue<<<grid, 256, 0, L.stream>>>(dst, slot, src, h, w);
   COUNT(L);
 }
@@ -256,6 +262,7 @@ __global__ void __launch_bounds__(256) k_update(UpdateParams q) {
 
 void launch_update(const Launch &L, const UpdateParams &q) {
   dim3 grid((q.X + 15) / 16, (q.Y + 15) / 16, 3);
+  ProfScope ps_(L, KC_UPDATE);
   k_update<<<grid, 256, 0, L.stream>>>(q);
   COUNT(L);
 }

@@ -119,6 +119,40 @@ void launch_search(const Launch &L, const SearchParams &q, int npairs) {
     s_attr = smem;
   }
   dim3 grid(q.nbx, q.nby, npairs);
+  ProfScope ps_(L, KC_SEARCH);
   k_search<<<grid, 128, smem, L.stream>>>(q);
   COUNT(L);
+}
+
+// ---- integer-SAD peak microbenchmark (the ME roofline denominator) ----
+// Register-resident loops of the two SAD instructions the search kernels use:
+// __vsadu4 (VABSDIFF4.U8.ACC, 4 SAD-ops per instruction) and __sad (VABSDIFF,
+// 1 SAD-op).  Eight independent accumulators per thread hide the ALU latency.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) k_int_peak(unsigned *out, int iters, unsigned seed) {
+  unsigned a[8], acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    a[k] = (threadIdx.x + 1) * 0x01030507u * (k + 1) + seed;
+    acc[k] = 0;
+  }
+  unsigned b = blockIdx.x * 0x9e3779b9u + seed;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      acc[k] = PACKED ? __vsadu4(a[k], b) + acc[k] : __sad((int)a[k], (int)b, acc[k]);
+    b += 0x01010101u;
+  }
+  unsigned r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r += acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+int run_int_peak(cudaStream_t stream, unsigned *d_out, int blocks, int iters, bool packed) {
+  if (packed)
+    k_int_peak<true><<<blocks, 256, 0, stream>>>(d_out, iters, 12345u);
+  else
+    k_int_peak<false><<<blocks, 256, 0, stream>>>(d_out, iters, 12345u);
+  return (int)cudaGetLastError();
 }

@@ -100,6 +100,25 @@ class Context:
     def synchronize(self):
         check(self._L.qsvc_synchronize(self._h))
 
+    KERNEL_CLASSES = ("image", "dwt_rows", "dwt_cols", "search", "predict", "residue", "update")
+
+    def profile_enable(self, on=True):
+        check(self._L.qsvc_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """{class: (device ms, launches)} since the previous read."""
+        n = len(self.KERNEL_CLASSES)
+        ms = (C.c_float * n)()
+        cnt = (C.c_longlong * n)()
+        check(self._L.qsvc_profile_read(self._h, ms, cnt, n))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
+
+    def int_peak(self):
+        """Measured SAD-op/s of this GPU: (packed u8 __vsadu4, 32-bit __sad)."""
+        a, b = C.c_double(), C.c_double()
+        check(self._L.qsvc_int_peak(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # ---- per-tool calls (host buffers in, host buffers out)
     def motion_estimate(self, even, odd, X, Y, block_size=32, search_range=4, subpixel_accuracy=0,
                         border_size=0, first_pair_is_global_first=True):
