@@ -492,7 +492,9 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
     uint8_t *dst = out + (long long)k * out_stride;
     bool upd_next = k >= 1 && types[k - 1] == 'B';
     bool upd_prev = k < n_pairs && types[k] == 'B';
-    if (!(upd_next || upd_prev) || BY == 0 || BX == 0) {
+    // update_factor == 0: every contribution is aux + (+-0) with aux already in
+    // [0,255], so the scatter is the identity (analyze.py's default)
+    if (!(upd_next || upd_prev) || BY == 0 || BX == 0 || uf == 0.0f) {
       // chroma up (zero-high synthesis) and down (analysis) are exact inverses
       launch_copy_bytes(Lh, dst, frame, (size_t)fb);
       continue;

@@ -1,0 +1,368 @@
+"""Flag-compatible command-line front-ends of the reference's MCTF tools.
+
+    mctf <tool> --flag=value ...        (bin/mctf, same contract as mctf.sh:35-39)
+    python -m qsvc_b200.tools <tool> ...
+
+Tools: split merge motion_estimate decorrelate correlate update un_update
+       analyze_step analyze synthesize_step synthesize
+Flag names, short forms and defaults follow the reference's getopt_long tables
+(motion_estimate.cpp:500-530, decorrelate.cpp:209-251, update.cpp:170-205,
+split.cpp:50-71) and MCTF_parser.py; unambiguous prefixes are accepted like
+getopt_long does (synthesize_step.py:135-137 relies on --even= --low= --odd=).
+Files are read from / written to the current directory.  Exit codes: 0 on
+success, 1 for --help and for motion_estimate when the motion file already
+exists (motion_estimate.cpp:659-682), 134 (abort) when a file cannot be opened.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from .. import yuv
+from ..mctf import Context, SEARCH_RANGE_MAX, gop_size, level_schedule, merge, split
+
+RED, OFF = "\033[1;31m", "\033[0m"
+
+
+def _error(msg: str):
+    sys.stderr.write(f"{RED}{msg}{OFF}")
+
+
+def _abort(tool: str, msg: str):
+    _error(f"{tool}: {msg} ... aborting!\n")
+    sys.exit(134)
+
+
+class _Parser(argparse.ArgumentParser):
+    def __init__(self, tool, **kw):
+        super().__init__(prog=tool, add_help=False, allow_abbrev=True, **kw)
+        self.tool = tool
+        self.add_argument("--help", "-?", action="store_true")
+
+    def opt(self, long, short, default, typ=str):
+        names = [f"--{long}"] + ([f"-{short}"] if short else [])
+        self.add_argument(*names, dest=long, default=default, type=typ)
+
+    def parse(self, argv):
+        args, _unknown = self.parse_known_args(argv)
+        if args.help:
+            self.print_usage()
+            sys.exit(1)
+        return args
+
+    def error(self, message):  # unknown/ambiguous flags: the reference tools print and go on
+        _error(f"{self.tool}: {message}\n")
+        sys.exit(134)
+
+
+def _read_frames(tool, fn, X, Y, count):
+    if not os.path.exists(fn):
+        _abort(tool, f'unable to read "{fn}"')
+    return yuv.read_frames(fn, X, Y, count)
+
+
+def _ctx():
+    return Context(int(os.environ.get("QSVC_DEVICE", "0")))
+
+
+# ------------------------------------------------------------------- tools
+
+def t_split(argv, inverse=False):
+    tool = "merge" if inverse else "split"
+    p = _Parser(tool)
+    p.opt("even_fn", "e", "even")
+    p.opt("low_fn", "l", "low")
+    p.opt("odd_fn", "o", "odd")
+    p.opt("pictures", "p", 9, int)
+    p.opt("pixels_in_x", "x", 352, int)
+    p.opt("pixels_in_y", "y", 288, int)
+    a = p.parse(argv)
+    n = a.pictures // 2
+    if not inverse:
+        low = _read_frames(tool, a.low_fn, a.pixels_in_x, a.pixels_in_y, 2 * n + 1)
+        even, odd = split(low)
+        yuv.write_frames(a.even_fn, even)
+        yuv.write_frames(a.odd_fn, odd)
+    else:
+        even = _read_frames(tool, a.even_fn, a.pixels_in_x, a.pixels_in_y, n + 1)
+        odd = _read_frames(tool, a.odd_fn, a.pixels_in_x, a.pixels_in_y, n)
+        yuv.write_frames(a.low_fn, merge(even, odd))
+    return 0
+
+
+def t_motion_estimate(argv):
+    tool = "motion_estimate"
+    p = _Parser(tool)
+    p.opt("block_size", "b", 32, int)
+    p.opt("border_size", "d", 0, int)
+    p.opt("even_fn", "e", "even")
+    p.opt("imotion_fn", "i", "imotion")  # opened but never read by the reference (:825)
+    p.opt("motion_fn", "m", "motion")
+    p.opt("odd_fn", "o", "odd")
+    p.opt("pictures", "p", 9, int)
+    p.opt("pixels_in_x", "x", 352, int)
+    p.opt("pixels_in_y", "y", 288, int)
+    p.opt("search_range", "s", 4, int)
+    p.opt("subpixel_accuracy", "a", 0, int)
+    a = p.parse(argv)
+    if os.path.exists(a.motion_fn):
+        return 1  # "reusing motion information": exit(1) without computing (:659-682)
+    n = a.pictures // 2
+    open(a.motion_fn, "wb").close()
+    even = _read_frames(tool, a.even_fn, a.pixels_in_x, a.pixels_in_y, n + 1)
+    odd = _read_frames(tool, a.odd_fn, a.pixels_in_x, a.pixels_in_y, n)
+    with _ctx() as c:
+        mv = c.motion_estimate(even, odd, a.pixels_in_x, a.pixels_in_y, a.block_size,
+                               a.search_range, a.subpixel_accuracy, a.border_size)
+    yuv.write_motion(a.motion_fn, mv)
+    return 0
+
+
+def t_decorrelate(argv, inverse=False):
+    tool = "correlate" if inverse else "decorrelate"
+    p = _Parser(tool)
+    p.opt("block_overlaping", "v", 0, int)
+    p.opt("block_size", "b", 16, int)
+    p.opt("even_fn", "e", "even")
+    p.opt("frame_types_fn", "f", "frame_types")
+    p.opt("high_fn", "h", "high")
+    p.opt("motion_in_fn", "i", "motion_in")
+    if not inverse:
+        p.opt("motion_out_fn", "t", "motion_out")
+    p.opt("odd_fn", "o", "odd")
+    p.opt("pictures", "p", 33, int)
+    p.opt("pixels_in_x", "x", 352, int)
+    p.opt("pixels_in_y", "y", 288, int)
+    p.opt("search_range", "s", 4, int)
+    p.opt("subpixel_accuracy", "a", 0, int)
+    p.opt("always_B", "B", 0, int)
+    a = p.parse(argv)
+    X, Y, n = a.pixels_in_x, a.pixels_in_y, a.pictures // 2
+    even = _read_frames(tool, a.even_fn, X, Y, n + 1)
+    if not os.path.exists(a.motion_in_fn):
+        _abort(tool, f'unable to read "{a.motion_in_fn}"')
+    mv = yuv.read_motion(a.motion_in_fn, X, Y, a.block_size, n)
+    with _ctx() as c:
+        if not inverse:
+            odd = _read_frames(tool, a.odd_fn, X, Y, n)
+            high, types, mvo, pred = c.decorrelate(even, odd, mv, X, Y, a.block_size,
+                                                   a.search_range, a.subpixel_accuracy,
+                                                   a.block_overlaping, a.always_B,
+                                                   want_prediction=True)
+            yuv.write_frames(a.high_fn, high)
+            open(a.frame_types_fn, "wb").write(types)
+            yuv.write_motion(a.motion_out_fn, mvo)
+        else:
+            high = _read_frames(tool, a.high_fn, X, Y, n)
+            if not os.path.exists(a.frame_types_fn):
+                _abort(tool, f'unable to read "{a.frame_types_fn}"')
+            types = open(a.frame_types_fn, "rb").read()[:n]
+            odd, pred = c.correlate(even, high, mv, types, X, Y, a.block_size, a.search_range,
+                                    a.subpixel_accuracy, a.block_overlaping, want_prediction=True)
+            yuv.write_frames(a.odd_fn, odd)
+    yuv.write_frames(f"prediction_{a.even_fn}", pred)  # decorrelate.cpp:454-472
+    return 0
+
+
+def t_update(argv, inverse=False):
+    tool = "un_update" if inverse else "update"
+    p = _Parser(tool)
+    p.opt("block_size", "b", 16, int)
+    p.opt("even_fn", "e", "even")
+    p.opt("frame_types_fn", "f", "frame_types")
+    p.opt("high_fn", "h", "high")
+    p.opt("low_fn", "l", "low")
+    p.opt("motion_fn", "m", "motion")
+    p.opt("pictures", None, 33, int)  # long form only (update.cpp:209)
+    p.opt("pixels_in_x", "x", 352, int)
+    p.opt("pixels_in_y", "y", 288, int)
+    p.opt("subpixel_accuracy", "a", 0, int)  # parsed, unused (update.cpp)
+    p.opt("update_factor", "u", 0.25, float)
+    a = p.parse(argv)
+    X, Y, n = a.pixels_in_x, a.pixels_in_y, a.pictures // 2
+    src, dst = (a.low_fn, a.even_fn) if inverse else (a.even_fn, a.low_fn)
+    frames = _read_frames(tool, src, X, Y, n + 1)
+    high = _read_frames(tool, a.high_fn, X, Y, n)
+    for fn in (a.motion_fn, a.frame_types_fn):
+        if not os.path.exists(fn):
+            _abort(tool, f'unable to read "{fn}"')
+    mv = yuv.read_motion(a.motion_fn, X, Y, a.block_size, n)
+    types = open(a.frame_types_fn, "rb").read()[:n]
+    with _ctx() as c:
+        out = c.update(frames, high, mv, types, X, Y, a.block_size,
+                       float(np.float32(a.update_factor)), inverse=inverse)
+    yuv.write_frames(dst, out)
+    return 0
+
+
+# ----------------------------------------------------------------- drivers
+
+def _driver_parser(tool, lists=False):
+    p = _Parser(tool)
+    s = str if lists else int
+    p.opt("GOPs", None, 1, int)
+    p.opt("TRLs", None, 4, int)
+    p.opt("always_B", None, 0, int)
+    p.opt("block_overlaping", None, 0, int)
+    p.opt("block_size", None, None, s)
+    p.opt("block_size_min", None, None, int)
+    p.opt("border_size", None, 0, int)
+    p.opt("pictures", None, None, int)
+    p.opt("pixels_in_x", None, "352" if lists else 352, s)
+    p.opt("pixels_in_y", None, "288" if lists else 288, s)
+    p.opt("search_range", None, 4, int)
+    p.opt("subpixel_accuracy", None, "0" if lists else 0, s)
+    p.opt("temporal_subband", None, 1, int)
+    p.opt("update_factor", None, None, float)
+    return p
+
+
+def _default_bs(X, Y):  # analyze.py:79-83 (evaluated on the default 352x288: always 32)
+    return 32
+
+
+def t_analyze(argv):
+    """analyze.py:107-153, fused: frames stay resident in HBM across levels."""
+    a = _driver_parser("analyze").parse(argv)
+    X, Y = a.pixels_in_x, a.pixels_in_y
+    bs = a.block_size if a.block_size is not None else _default_bs(X, Y)
+    bs_min = a.block_size_min if a.block_size_min is not None else 32
+    uf = 0.0 if a.update_factor is None else a.update_factor  # analyze.py default 0
+    pictures = a.GOPs * gop_size(a.TRLs) + 1
+    low0 = _read_frames("analyze", "low_0", X, Y, pictures)
+    with _ctx() as c:
+        out = c.analyze(low0, X, Y, a.GOPs, a.TRLs, bs, a.search_range, a.subpixel_accuracy, uf,
+                        a.always_B, a.block_overlaping, a.border_size, bs_min)
+    low = low0
+    for s in level_schedule(a.GOPs, a.TRLs, bs, a.search_range, bs_min):
+        t = s["t"]
+        even, odd = split(low)
+        yuv.write_frames(f"even_{t}", even)
+        yuv.write_frames(f"odd_{t}", odd)
+        yuv.write_motion(f"motion_{t}", out[f"motion_{t}"])
+        yuv.write_motion(f"motion_filtered_{t}", out[f"motion_filtered_{t}"])
+        open(f"frame_types_{t}", "wb").write(out[f"frame_types_{t}"])
+        yuv.write_frames(f"high_{t}", out[f"high_{t}"])
+        yuv.write_frames(f"low_{t}", out[f"low_{t}"])
+        low = out[f"low_{t}"]
+    return 0
+
+
+def t_analyze_step(argv):
+    """analyze_step.py:115-232: split, motion_estimate, decorrelate, update."""
+    a = _driver_parser("analyze_step").parse(argv)
+    X, Y, t = a.pixels_in_x, a.pixels_in_y, a.temporal_subband
+    bs = a.block_size if a.block_size is not None else _default_bs(X, Y)
+    uf = 0.0 if a.update_factor is None else a.update_factor
+    pictures = a.pictures if a.pictures is not None else 9
+    common = [f"--pictures={pictures}", f"--pixels_in_x={X}", f"--pixels_in_y={Y}"]
+    rc = t_split([f"--even_fn=even_{t}", f"--low_fn=low_{t-1}", f"--odd_fn=odd_{t}"] + common)
+    rc = rc or t_motion_estimate([f"--block_size={bs}", f"--border_size={a.border_size}",
+                                  f"--even_fn=even_{t}", f"--imotion_fn=imotion_{t}",
+                                  f"--motion_fn=motion_{t}", f"--odd_fn=odd_{t}",
+                                  f"--search_range={a.search_range}",
+                                  f"--subpixel_accuracy={a.subpixel_accuracy}"] + common)
+    rc = rc or t_decorrelate([f"--block_overlaping={a.block_overlaping}", f"--block_size={bs}",
+                              f"--even_fn=even_{t}", f"--frame_types_fn=frame_types_{t}",
+                              f"--high_fn=high_{t}", f"--motion_in_fn=motion_{t}",
+                              f"--motion_out_fn=motion_filtered_{t}", f"--odd_fn=odd_{t}",
+                              f"--search_range={a.search_range}",
+                              f"--subpixel_accuracy={a.subpixel_accuracy}",
+                              f"--always_B={a.always_B}"] + common)
+    rc = rc or t_update([f"--block_size={bs}", f"--even_fn=even_{t}",
+                         f"--frame_types_fn=frame_types_{t}", f"--high_fn=high_{t}",
+                         f"--low_fn=low_{t}", f"--motion_fn=motion_filtered_{t}",
+                         f"--subpixel_accuracy={a.subpixel_accuracy}",
+                         f"--update_factor={uf}"] + common)
+    return -1 & 0xFF if rc else 0  # the reference drivers turn any failure into sys.exit(-1)
+
+
+def _per_level(value: str, index: int, typ=int):
+    parts = str(value).split(",")
+    return typ(parts[index] if index < len(parts) else parts[-1])
+
+
+def t_synthesize(argv):
+    """synthesize.py:95-153.  block_size / pixels_in_x / pixels_in_y /
+    subpixel_accuracy are comma lists indexed per temporal level
+    (:127-133); this build requires them to be constant over the levels
+    (spatially scalable synthesis is SURVEY 8f)."""
+    a = _driver_parser("synthesize", lists=True).parse(argv)
+    T = a.TRLs
+    bs_list = a.block_size if a.block_size is not None else "16,16,16,16"
+    uf = 0.25 if a.update_factor is None else a.update_factor  # synthesize.py default 1/4
+    geo = set()
+    for t in range(1, T):
+        geo.add((_per_level(bs_list, (T - 1) - t), _per_level(a.pixels_in_x, T - t),
+                 _per_level(a.pixels_in_y, T - t), _per_level(a.subpixel_accuracy, T - t)))
+    if len(geo) != 1:
+        _error("synthesize: per-level geometry lists must be constant in this build\n")
+        return 255
+    bs, X, Y, acc = geo.pop()
+    sub = {}
+    for s in level_schedule(a.GOPs, T, bs, a.search_range, bs):
+        t, n = s["t"], s["pairs"]
+        sub[f"high_{t}"] = _read_frames("synthesize", f"high_{t}", X, Y, n)
+        if not os.path.exists(f"motion_{t}") or not os.path.exists(f"frame_types_{t}"):
+            _abort("synthesize", f'unable to read "motion_{t}"/"frame_types_{t}"')
+        sub[f"motion_{t}"] = yuv.read_motion(f"motion_{t}", X, Y, bs, n)
+        sub[f"frame_types_{t}"] = open(f"frame_types_{t}", "rb").read()[:n]
+        if t == T - 1:
+            sub[f"low_{t}"] = _read_frames("synthesize", f"low_{t}", X, Y, n + 1)
+    with _ctx() as c:
+        low0 = c.synthesize(sub, X, Y, a.GOPs, T, bs, a.search_range, acc, uf, a.block_overlaping)
+    yuv.write_frames("low_0", low0)
+    return 0
+
+
+def t_synthesize_step(argv):
+    """synthesize_step.py:84-143: un_update, correlate, merge."""
+    a = _driver_parser("synthesize_step").parse(argv)
+    X, Y, t = a.pixels_in_x, a.pixels_in_y, a.temporal_subband
+    bs = a.block_size if a.block_size is not None else 16
+    uf = 0.25 if a.update_factor is None else a.update_factor
+    pictures = a.pictures if a.pictures is not None else 33
+    common = [f"--pictures={pictures}", f"--pixels_in_x={X}", f"--pixels_in_y={Y}"]
+    rc = t_update([f"--block_size={bs}", f"--even_fn=even_{t}", f"--frame_types_fn=frame_types_{t}",
+                   f"--high_fn=high_{t}", f"--low_fn=low_{t}", f"--motion_fn=motion_{t}",
+                   f"--subpixel_accuracy={a.subpixel_accuracy}", f"--update_factor={uf}"] + common,
+                  inverse=True)
+    rc = rc or t_decorrelate([f"--block_overlaping={a.block_overlaping}", f"--block_size={bs}",
+                              f"--even_fn=even_{t}", f"--frame_types_fn=frame_types_{t}",
+                              f"--high_fn=high_{t}", f"--motion_in_fn=motion_{t}",
+                              f"--odd_fn=odd_{t}", f"--search_range={a.search_range}",
+                              f"--subpixel_accuracy={a.subpixel_accuracy}"] + common, inverse=True)
+    rc = rc or t_split([f"--even={f'even_{t}'}", f"--low=low_{t-1}", f"--odd=odd_{t}"] + common,
+                       inverse=True)
+    return 255 if rc else 0
+
+
+TOOLS = {
+    "split": t_split,
+    "merge": lambda argv: t_split(argv, inverse=True),
+    "motion_estimate": t_motion_estimate,
+    "decorrelate": t_decorrelate,
+    "correlate": lambda argv: t_decorrelate(argv, inverse=True),
+    "update": t_update,
+    "un_update": lambda argv: t_update(argv, inverse=True),
+    "analyze": t_analyze,
+    "analyze_step": t_analyze_step,
+    "synthesize": t_synthesize,
+    "synthesize_step": t_synthesize_step,
+}
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv or argv[0] not in TOOLS:
+        sys.stderr.write("usage: mctf <" + "|".join(TOOLS) + "> [--flag=value ...]\n")
+        return 1
+    from .._lib import QsvcError
+    try:
+        return int(TOOLS[argv[0]](argv[1:]) or 0)
+    except QsvcError as e:
+        _error(f"{argv[0]}: {e}\n")
+        return 2
