@@ -22,7 +22,7 @@ CASES = {
     "ib_types_a0":   (64, 48, 2, 3, 16, 4, 0, 0.25, 0, 2, 21),   # IBIB frame types, update 1/4
     "quarter_pel":   (64, 48, 1, 4, 16, 8, 2, 0.3, 0, 0, 22),    # border pollution, size-field reads
     "ragged_height": (64, 40, 2, 4, 16, 4, 1, 0.0, 0, 0, 23),    # Y % bs != 0: chained tail rows
-    "odd_pyramid":   (64, 60, 1, 4, 8, 32, 0, 0.0, 1, 0, 24),    # non-invertible pyramid descent
+    "odd_pyramid":   (64, 60, 2, 3, 8, 32, 0, 0.0, 1, 0, 24),    # non-invertible pyramid descent
 }
 
 
