@@ -54,15 +54,21 @@ int qsvc_timer_stop(qsvc_ctx *ctx, float *elapsed_ms);
 int qsvc_synchronize(qsvc_ctx *ctx);
 /* Per-kernel-class device timers (CUDA event pairs around every launch while
  * enabled).  Classes: 0 image load/store/border, 1 DWT rows, 2 DWT columns,
- * 3 block search, 4 predict, 5 residue/reconstruct, 6 update.  read() waits for
+ * 3 block search, 4 predict, 5 residue/reconstruct, 6 update, 7 sub-pixel search
+ * exact path.  read() waits for
  * the stream, sums what was recorded since the previous read and resets. */
-#define QSVC_KERNEL_CLASSES 7
+#define QSVC_KERNEL_CLASSES 8
 int qsvc_profile_enable(qsvc_ctx *ctx, int on);
 int qsvc_profile_read(qsvc_ctx *ctx, float *ms_per_class, long long *launches_per_class,
                       int n_classes);
 /* Measured SAD-instruction issue rate of this GPU (the ME roofline denominator):
  * SAD operations per second with packed bytes (__vsadu4) and 32-bit lanes (__sad). */
 int qsvc_int_peak(qsvc_ctx *ctx, double *u8_sad_ops_per_s, double *i32_sad_ops_per_s);
+/* Motion-estimation implementation: 0 automatic (fused sub-pixel path when the
+ * geometry allows it, default; also env QSVC_ME_MODE), 1 literal path that
+ * materialises the up-sampled images like the reference, 2 fused or fail.  All
+ * modes produce identical motion fields. */
+int qsvc_set_me_mode(qsvc_ctx *ctx, int mode);
 
 /* Replaces `motion_estimate` main(), reference motion_estimate.cpp:490-912
  * (search: :70-184, pyramid driver: :260-413).

@@ -67,6 +67,7 @@ struct qsvc_ctx {
   long long launches = 0;
   Profiler prof;
   std::vector<PoolBlock> pool;
+  int me_mode = 0;  // 0: automatic, 1: literal (materialised) path only, 2: fused path required
   size_t me_budget = (size_t)40 << 30;  // bytes of HBM for the ME image planes of one chunk
   // resident sequence
   uint8_t *low0 = nullptr;
@@ -223,6 +224,155 @@ static double me_sad_ops(int BY, int BX, int bs, int bd, int L, int a) {
   return 18.0 * ops;
 }
 
+// ---- fused ME path (a in {1,2}): compact pyramid planes + u8 interpolated planes
+// + packed-byte sub-pixel search (kernels_subpel.cu).  Same results as the literal
+// path below; chosen automatically when the geometry allows it.
+static bool me_fused_ok(int X, int Y, int bs, int bd, int sr, int a) {
+  if (a < 1 || a > 2 || bd != 0) return false;
+  for (int l = 1; l <= a; l++)
+    if (!subpel_supported(bs << l)) return false;
+  const int B = sr + bd;
+  if (B > X || B > Y) return false;                 // second synthesis must see zero high bands
+  if (Y + B + 2 > ((Y - B) << a)) return false;     // over-pixel search must stay clear of the
+  if (X % 4 != 0) return false;                     //   un-shifted rows; word-aligned block columns
+  return true;
+}
+
+static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_stride,
+                          const uint8_t *odd, long long odd_stride, int n_pairs, int X, int Y,
+                          int bs, int sr, int a, int L, bool pr, int first_global, short *mv_out) {
+  const int BY = Y / bs, BX = X / bs;
+  const int B = sr, Bc = B + 2;
+  const long long field = 4LL * BY * BX;
+  const int n_search = 1 + L + a;
+  Launch Lh = c->L();
+  // per-slot footprints
+  const int S = (X + 2 * Bc + 7) & ~7;
+  const size_t slot_shorts = (size_t)(Y + 2 * Bc + 1) * S;
+  int pitch[3];
+  size_t vbytes[3], vtotal = 0;
+  for (int l = 0; l <= a; l++) {
+    pitch[l] = (((X << l) + 15) & ~15) + 16;
+    vbytes[l] = (size_t)pitch[l] * ((Y << l) + 2);
+    vtotal += vbytes[l];
+  }
+  const size_t per_slot = slot_shorts * sizeof(short) + vtotal;
+  const int per_pair_slots = pr ? 2 : 3;
+  long long max_pairs = (long long)(c->me_budget / per_slot - 1) / per_pair_slots;
+  if (max_pairs < 1) max_pairs = 1;
+
+  for (int i0 = 0; i0 < n_pairs; i0 += (int)max_pairs) {
+    const int m = (int)std::min<long long>(max_pairs, n_pairs - i0);
+    Scratch s(c);
+    const int n_copy = pr ? 0 : m - 1;
+    const int nslots = 2 * m + 1 + n_copy;
+    short *raw;
+    TRY(s.get(slot_shorts * nslots * sizeof(short), (void **)&raw));
+    Plane img;
+    img.base = raw;
+    img.slot_stride = (long long)slot_shorts;
+    img.S = S;
+    img.y_dim = Y + 2 * Bc;  // every row pointer is "shifted": plain bordered image
+    img.x_dim = X;
+    img.b = Bc;
+    uint8_t *v[3] = {nullptr, nullptr, nullptr};
+    for (int l = 0; l <= a; l++) TRY(s.get(vbytes[l] * nslots, (void **)&v[l]));
+    short *mv_tmp;
+    int *d_slots, *d_flags, *d_slow;
+    TRY(s.get((size_t)m * field * sizeof(short), (void **)&mv_tmp));
+    TRY(s.get((size_t)m * 3 * sizeof(int), (void **)&d_slots));
+    TRY(s.get((size_t)(nslots + 1) * sizeof(int), (void **)&d_flags));
+    TRY(s.get(((size_t)m * BY * BX + 1) * sizeof(int), (void **)&d_slow));
+    std::vector<int> slots(3 * m);
+    for (int i = 0; i < m; i++) {
+      slots[3 * i] = (!pr && i >= 1) ? 2 * m + i : i;
+      slots[3 * i + 1] = i + 1;
+      slots[3 * i + 2] = m + 1 + i;
+    }
+    CU(cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(raw, 0, slot_shorts * nslots * sizeof(short), c->stream));
+    CU(cudaMemsetAsync(d_flags, 0, (size_t)(nslots + 1) * sizeof(int), c->stream));
+    launch_load_u8(Lh, img, 0, m + 1, even, even_stride, 0, i0, 1, Y, X);
+    launch_load_u8(Lh, img, m + 1, m, odd, odd_stride, 0, i0, 1, Y, X);
+    launch_fill_border(Lh, img, 0, m + 1, Y, X, B);
+    if (n_copy > 0) {
+      launch_load_u8(Lh, img, 2 * m + 1, n_copy, even, even_stride, 0, i0 + 1, 1, Y, X);
+      launch_fill_border(Lh, img, 2 * m + 1, n_copy, Y, X, B);
+    }
+    if (!pr) {
+      // carried reference[0]: one pass of the non-invertible pyramid (the sub-pixel
+      // synthesis/analysis pair of the reference is an exact identity and is skipped)
+      auto used_state = [&](int slot0, int n) {
+        if (n <= 0) return;
+        dwt_analyze(Lh, img, slot0, n, Y, X, L);
+        for (int l = L - 1; l >= 0; --l) dwt_synthesize(Lh, img, slot0, n, desp(Y, l), desp(X, l), 1);
+      };
+      if (!(first_global && i0 == 0)) used_state(0, 1);
+      used_state(2 * m + 1, n_copy);
+    }
+    short *bufs[2] = {mv_out + (long long)i0 * field, mv_tmp};
+    int j = 0;
+    auto run_search = [&](int mode, int nby, int nbx, int lim) {
+      SearchParams q;
+      q.img = img;
+      q.slots = d_slots;
+      q.mv_out = bufs[(j + n_search - 1) & 1];
+      q.mv_in = bufs[(j + n_search) & 1];
+      q.BY = BY;
+      q.BX = BX;
+      q.nby = nby;
+      q.nbx = nbx;
+      q.bs = bs;
+      q.bd = 0;
+      q.mode = mode;
+      q.lim = lim;
+      launch_search(Lh, q, m);
+      j++;
+    };
+    dwt_analyze(Lh, img, 0, nslots, Y, X, L);
+    run_search(ME_INIT, desp(BY, L), desp(BX, L), 0);
+    for (int l = L - 1; l >= 0; --l) {
+      dwt_synthesize(Lh, img, 0, nslots, desp(Y, l), desp(X, l), 1);
+      run_search(ME_DESCEND, desp(BY, l), desp(BX, l), sr);
+    }
+    // byte planes of the level-0 interiors and their zero-high-band interpolations
+    launch_plane_to_u8(Lh, img, 0, nslots, Y, X, v[0], (long long)vbytes[0], pitch[0], d_flags);
+    for (int l = 1; l <= a; l++)
+      launch_upsample2x(Lh, v[l - 1], Y << (l - 1), X << (l - 1), pitch[l - 1], (long long)vbytes[l - 1],
+                        v[l], pitch[l], (long long)vbytes[l], nslots);
+    for (int l = 1; l <= a; l++) {
+      CU(cudaMemsetAsync(d_slow, 0, sizeof(int), c->stream));
+      SubpelParams q;
+      q.b0 = img;
+      q.slots = d_slots;
+      q.v = v[l];
+      q.v_slot_stride = (long long)vbytes[l];
+      q.v_pitch = pitch[l];
+      q.slot_flags = d_flags;
+      q.mv_out = bufs[(j + n_search - 1) & 1];
+      q.mv_in = bufs[(j + n_search) & 1];
+      q.BY = BY;
+      q.BX = BX;
+      q.l = l;
+      q.Y = Y;
+      q.X = X;
+      q.B = B;
+      q.Bc = Bc;
+      q.Ya = Y << a;
+      q.Ba = B << a;
+      q.size_field = (unsigned long long)heap_row_shorts(X << a, B << a) * 2ull | 1ull;
+      q.lim = sr << a;
+      q.slow_count = d_slow;
+      q.slow_list = d_slow + 1;
+      launch_subpel(Lh, q, bs << l, m);
+      j++;
+    }
+    CU(cudaGetLastError());
+    c->sad_ops += me_sad_ops(BY, BX, bs, 0, L, a) * m;
+  }
+  return QSVC_OK;
+}
+
 // even frame k at even + k*even_stride, odd frame i at odd + i*odd_stride (device).
 static int me_level(qsvc_ctx *c, const uint8_t *even, long long even_stride, const uint8_t *odd,
                     long long odd_stride, int n_pairs, int X, int Y, int bs, int bd, int sr, int a,
@@ -242,6 +392,11 @@ static int me_level(qsvc_ctx *c, const uint8_t *even, long long even_stride, con
   bool pr = true;
   for (int l = 0; l < L; l++)
     if ((Y >> l) != desp(Y, l) || (X >> l) != desp(X, l)) pr = false;
+
+  if (c->me_mode != 1 && me_fused_ok(X, Y, bs, bd, sr, a))
+    return me_level_fused(c, even, even_stride, odd, odd_stride, n_pairs, X, Y, bs, sr, a, L, pr,
+                          first_global, mv_out);
+  if (c->me_mode == 2) return fail(QSVC_EINVAL, "fused ME path requested but not applicable");
 
   const long long field = 4LL * BY * BX;
   const int n_search = 1 + L + a;
@@ -582,6 +737,7 @@ qsvc_ctx *qsvc_create(int device) {
     delete c;
     return nullptr;
   }
+  if (const char *e = getenv("QSVC_ME_MODE")) c->me_mode = atoi(e);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->me_budget = std::min<size_t>((size_t)64 << 30, free_b / 3);
   return c;
@@ -651,6 +807,11 @@ int qsvc_int_peak(qsvc_ctx *c, double *u8_sad_ops_per_s, double *i32_sad_ops_per
     if (packed && u8_sad_ops_per_s) *u8_sad_ops_per_s = best;
     if (!packed && i32_sad_ops_per_s) *i32_sad_ops_per_s = best;
   }
+  return QSVC_OK;
+}
+int qsvc_set_me_mode(qsvc_ctx *c, int mode) {
+  if (!c || mode < 0 || mode > 2) return fail(QSVC_EINVAL, "bad me_mode");
+  c->me_mode = mode;
   return QSVC_OK;
 }
 int qsvc_profile_enable(qsvc_ctx *c, int on) {

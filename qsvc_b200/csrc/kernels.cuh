@@ -11,6 +11,7 @@ enum {
   KC_PREDICT,     // motion-compensated prediction (+ clip)
   KC_RESIDUE,     // residue / reconstruction / histograms
   KC_UPDATE,      // update lifting step
+  KC_SEARCH_EXACT,  // sub-pixel search, exact int16 path for polluted / edge blocks
   KC_COUNT
 };
 
@@ -70,6 +71,33 @@ struct SearchParams {
   int mode, lim;
 };
 void launch_search(const Launch &L, const SearchParams &q, int npairs);
+// sub-pixel search levels without materialised up-sampled images (kernels_subpel.cu)
+struct SubpelParams {
+  Plane b0;            // compact level-0 buffers after the over-pixel descent
+  const int *slots;    // per pair: R0 slot, R1 slot, P slot
+  const uint8_t *v;    // V_l planes (u8, one per slot) of this level
+  long long v_slot_stride;
+  int v_pitch;
+  const int *slot_flags;  // nonzero: the slot's level-0 interior does not fit in bytes
+  const short *mv_in;
+  short *mv_out;
+  int BY, BX;
+  int l;               // sub-pixel level, 1 or 2
+  int Y, X;            // level-0 picture size
+  int B, Bc;           // fill border (search_range + border_size), compact plane border
+  int Ya, Ba;          // rows / border of the reference's allocation (size-field rows)
+  unsigned long long size_field;
+  int lim;             // vector clamp, search_range << a
+  int *slow_count;
+  int *slow_list;
+};
+bool subpel_supported(int W);
+void launch_subpel(const Launch &L, const SubpelParams &q, int W, int npairs);
+void launch_plane_to_u8(const Launch &L, Plane src, int slot0, int nslots, int Y, int X,
+                        uint8_t *dst, long long dst_slot_stride, int pitch, int *flags);
+void launch_upsample2x(const Launch &L, const uint8_t *in, int n, int m, int pitch_in,
+                       long long in_slot_stride, uint8_t *out, int pitch_out,
+                       long long out_slot_stride, int nslots);
 int run_int_peak(cudaStream_t stream, unsigned *d_out, int blocks, int iters, bool packed);
 
 // ---- motion compensation (kernels_mc.cu) ----

@@ -1,0 +1,468 @@
+// kernels_subpel.cu -- sub-pixel levels of the motion search without
+// materialising the 2^a-times up-sampled int16 images.
+//
+// Reference semantics (motion_estimate.cpp:361-407): for l = 1..a the three
+// images are synthesised one more 5/3 level in place (high bands = whatever the
+// buffer holds there: zeros, plus the fill_border replicas that the un-shifted
+// fill_border call left inside the first high-band rows/columns), vectors are
+// doubled and clamped, and every block is refined by +-1 at block size bs<<l.
+//
+// Here:
+//  * B0 = the level-0 buffer after the over-pixel descent lives in a compact
+//    bordered int16 plane (interior + fill ring + zeros);
+//  * V_l = up^l(u8(B0 interior)) are dense u8 planes made by k_upsample2x: the
+//    exact zero-high-band synthesis for byte data (s[2i] = l[i],
+//    s[2i+1] = (l[i] + l[i+1]) >> 1, last = l[last]; columns first, then rows);
+//  * a block whose windows lie in the region where B_l == V_l (away from the
+//    polluted top/left strips, inside the picture, all samples bytes) takes the
+//    FAST path: windows are copied as aligned 32-bit words and the nine SADs per
+//    direction are accumulated with __vsadu4 (VABSDIFF4.U8.ACC, 4 SAD-ops/instr);
+//  * every other block is queued and handled by the EXACT path, which rebuilds
+//    the int16 windows from B0 with the literal synthesis formulas (including
+//    the high-band reads) and accumulates with __sad.
+#include "kernels.cuh"
+
+#define COUNT(L) (++*(L).counter)
+
+__constant__ int c_cand9[9][2] = {{-1, -1}, {-1, 1}, {1, -1}, {1, 1}, {-1, 0},
+                                  {1, 0},   {0, 1},  {0, -1}, {0, 0}};
+
+// ------------------------------------------------------------ u8 planes
+
+__global__ void __launch_bounds__(256) k_plane_to_u8(Plane src, int slot0, int Y, int X,
+                                                     uint8_t *dst, long long dst_slot_stride,
+                                                     int pitch, int *flags) {
+  const int s = blockIdx.z;
+  int bad = 0;
+  for (int y = blockIdx.y; y < Y; y += gridDim.y) {
+    const short *row = src.row(slot0 + s, y);
+    uint8_t *drow = dst + (long long)s * dst_slot_stride + (long long)y * pitch;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < X; x += gridDim.x * blockDim.x) {
+      int v = row[x];
+      bad |= (unsigned)v > 255u;
+      drow[x] = (uint8_t)v;
+    }
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&flags[s], 1);
+}
+
+void launch_plane_to_u8(const Launch &L, Plane src, int slot0, int nslots, int Y, int X,
+                        uint8_t *dst, long long dst_slot_stride, int pitch, int *flags) {
+  if (nslots <= 0) return;
+  dim3 grid((X + 1023) / 1024, Y < 512 ? Y : 512, nslots);
+  ProfScope ps_(L, KC_IMG);
+  k_plane_to_u8<<<grid, 256, 0, L.stream>>>(src, slot0, Y, X, dst, dst_slot_stride, pitch, flags);
+  COUNT(L);
+}
+
+// out (2n x 2m) = rows(cols(in (n x m))) of the zero-high-band 5/3 synthesis on bytes
+// (5_3.cpp:81-94 with h = 0, dwt2d.cpp:139-172: columns first, then rows).
+// One thread: 4 input pixels of input rows i and i+1 -> 8 output pixels of rows 2i, 2i+1.
+__global__ void __launch_bounds__(256) k_upsample2x(const uint8_t *__restrict__ in, int n, int m,
+                                                    int pitch_in, long long in_slot_stride,
+                                                    uint8_t *__restrict__ out, int pitch_out,
+                                                    long long out_slot_stride) {
+  const int s = blockIdx.z;
+  const uint8_t *src = in + (long long)s * in_slot_stride;
+  uint8_t *dst = out + (long long)s * out_slot_stride;
+  const int mw = (m + 3) >> 2;
+  for (int i = blockIdx.y; i < n; i += gridDim.y) {
+    const uint8_t *r0 = src + (long long)i * pitch_in;
+    const uint8_t *r1 = src + (long long)(i + 1 < n ? i + 1 : i) * pitch_in;  // last odd row = last row
+    uint8_t *o0 = dst + (long long)(2 * i) * pitch_out;
+    uint8_t *o1 = o0 + pitch_out;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < mw; w += gridDim.x * blockDim.x) {
+      const int j = w << 2;
+      unsigned a = *reinterpret_cast<const unsigned *>(r0 + j);
+      unsigned b = *reinterpret_cast<const unsigned *>(r1 + j);
+      // next pixel to the right (replicated at the right edge: last odd column = last column)
+      int jn = j + 4 < m ? j + 4 : m - 1;
+      unsigned an = r0[jn], bn = r1[jn];
+      if (j + 4 > m) {  // partial word at the right edge: replicate the last valid pixel
+        int last = m - 1 - j;
+        unsigned la = (a >> (8 * last)) & 0xff, lb = (b >> (8 * last)) & 0xff;
+        for (int k = last + 1; k < 4; k++) {
+          a = (a & ~(0xffu << (8 * k))) | (la << (8 * k));
+          b = (b & ~(0xffu << (8 * k))) | (lb << (8 * k));
+        }
+        an = la;
+        bn = lb;
+      }
+      unsigned t0 = a;                 // column pass, even output row
+      unsigned t1 = __vhaddu4(a, b);   // column pass, odd output row: floor((a + b) / 2)
+      unsigned t0n = an, t1n = (an + bn) >> 1;
+      // row pass: out[2j] = t[j], out[2j+1] = floor((t[j] + t[j+1]) / 2)
+      unsigned s0 = __funnelshift_r(t0, t0n, 8), s1 = __funnelshift_r(t1, t1n, 8);
+      unsigned h0 = __vhaddu4(t0, s0), h1 = __vhaddu4(t1, s1);
+      uint2 q0, q1;
+      q0.x = __byte_perm(t0, h0, 0x5140);
+      q0.y = __byte_perm(t0, h0, 0x7362);
+      q1.x = __byte_perm(t1, h1, 0x5140);
+      q1.y = __byte_perm(t1, h1, 0x7362);
+      *reinterpret_cast<uint2 *>(o0 + 2 * j) = q0;
+      *reinterpret_cast<uint2 *>(o1 + 2 * j) = q1;
+    }
+  }
+}
+
+void launch_upsample2x(const Launch &L, const uint8_t *in, int n, int m, int pitch_in,
+                       long long in_slot_stride, uint8_t *out, int pitch_out,
+                       long long out_slot_stride, int nslots) {
+  if (nslots <= 0) return;
+  int mw = (m + 3) / 4;
+  dim3 grid((mw + 255) / 256, n < 1024 ? n : 1024, nslots);
+  ProfScope ps_(L, KC_IMG);
+  k_upsample2x<<<grid, 256, 0, L.stream>>>(in, n, m, pitch_in, in_slot_stride, out, pitch_out,
+                                           out_slot_stride);
+  COUNT(L);
+}
+
+// ------------------------------------------------------------- fast path
+
+__device__ __forceinline__ void subpel_centre(const SubpelParams &q, int pair, int by, int bx,
+                                              short c[4]) {
+  const long long plane = (long long)q.BY * q.BX;
+  const short *mvi = q.mv_in + (long long)pair * 4 * plane;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    short v = mvi[k * plane + (long long)by * q.BX + bx];
+    v = (short)(v * 2);
+    if (v > q.lim) v = (short)q.lim;
+    if (v < -q.lim) v = (short)(-q.lim);
+    c[k] = v;
+  }
+}
+
+__device__ __forceinline__ void subpel_store(const SubpelParams &q, int pair, int by, int bx,
+                                             const short c[4], const int *err /*[2][9]*/) {
+  const long long plane = (long long)q.BY * q.BX;
+  short *mvo = q.mv_out + (long long)pair * 4 * plane;
+  for (int d = 0; d < 2; d++) {
+    int best = 0, min_error = 0;
+    for (int k = 0; k < 9; k++) {
+      int e = err[d * 9 + k];
+      if (k == 0 || e <= min_error) {
+        min_error = e;
+        best = k;
+      }
+    }
+    int sgn = d ? -1 : 1;
+    long long dst = (long long)by * q.BX + bx;
+    mvo[(2 * d) * plane + dst] = (short)(c[2 * d] + sgn * c_cand9[best][1]);
+    mvo[(2 * d + 1) * plane + dst] = (short)(c[2 * d + 1] + sgn * c_cand9[best][0]);
+  }
+}
+
+// W = block size at this level (bs << l), W in {16, 32, 64}.  Thread t owns the
+// 32-bit word column j = t % (W/4) of RPT consecutive block rows.
+template <int W>
+__global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_fast(SubpelParams q) {
+  constexpr int WPR = W / 4;       // P words per row
+  constexpr int RPT = 8;           // rows per thread
+  constexpr int NT = WPR * (W / RPT);
+  constexpr int PS = WPR + 2;      // smem row strides in words (8*stride % 32 == 16)
+  constexpr int RWORDS = WPR + 2;  // aligned words covering W + 2 bytes at any alignment
+  constexpr int RS = RWORDS + ((RWORDS % 4 == 2) ? 0 : ((6 - RWORDS % 4) % 4));
+  __shared__ unsigned sP[W * PS];
+  __shared__ unsigned sR[2][(W + 2) * RS];
+  __shared__ int s_err[NT / 32 > 0 ? NT / 32 : 1][18];
+  __shared__ int s_fin[18];
+
+  const int bx = blockIdx.x, by = blockIdx.y, pair = blockIdx.z;
+  const int l = q.l;
+  const int Yl = q.Y << l, Xl = q.X << l;
+  short c[4];
+  subpel_centre(q, pair, by, bx, c);
+  const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
+  const int py0 = by * W, px0 = bx * W;
+  const int wy[2] = {py0 + c[MV_PREV_Y] - 1, py0 + c[MV_NEXT_Y] - 1};
+  const int wx[2] = {px0 + c[MV_PREV_X] - 1, px0 + c[MV_NEXT_X] - 1};
+  // B_l == V_l on [clean, dim) x [clean, dim): outside the rows/columns reached by the
+  // fill_border replicas that sit in the first high-band rows/columns of level 1
+  const int clean = (2 * q.B + 2) << (l - 1);
+  bool fast = !(q.slot_flags[r0s] | q.slot_flags[r1s] | q.slot_flags[ps]);
+#pragma unroll
+  for (int d = 0; d < 2; d++)
+    fast = fast && wy[d] >= clean && wx[d] >= clean && wy[d] + W + 2 <= Yl && wx[d] + W + 2 <= Xl;
+  if (!fast) {
+    if (threadIdx.x == 0) {
+      int idx = atomicAdd(q.slow_count, 1);
+      q.slow_list[idx] = (pair * q.BY + by) * q.BX + bx;
+    }
+    return;
+  }
+
+  const uint8_t *vP = q.v + (long long)ps * q.v_slot_stride;
+  for (int i = threadIdx.x; i < W * WPR; i += NT) {
+    int y = i / WPR, w = i % WPR;
+    sP[y * PS + w] = *reinterpret_cast<const unsigned *>(vP + (long long)(py0 + y) * q.v_pitch + px0 + 4 * w);
+  }
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+    const uint8_t *vR = q.v + (long long)(d ? r1s : r0s) * q.v_slot_stride;
+    const int xa = wx[d] & ~3;
+    for (int i = threadIdx.x; i < (W + 2) * RWORDS; i += NT) {
+      int y = i / RWORDS, w = i % RWORDS;
+      sR[d][y * RS + w] =
+          *reinterpret_cast<const unsigned *>(vR + (long long)(wy[d] + y) * q.v_pitch + xa + 4 * w);
+    }
+  }
+  __syncthreads();
+
+  const int j = threadIdx.x % WPR, g = threadIdx.x / WPR;
+  unsigned p[RPT];
+#pragma unroll
+  for (int r = 0; r < RPT; r++) p[r] = sP[(g * RPT + r) * PS + j];
+  constexpr int DY[9] = {-1, -1, 1, 1, -1, 1, 0, 0, 0};
+  constexpr int DX[9] = {-1, 1, -1, 1, 0, 0, 1, -1, 0};
+  unsigned acc[18];
+#pragma unroll
+  for (int k = 0; k < 18; k++) acc[k] = 0;
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+    // window column of candidate dx for P byte 0 of word j: (wx & 3) + 1 + sgn*dx + 4j
+    const int sgn = d ? -1 : 1;
+    const int base = (wx[d] & 3) + 1;
+    const int o_m = base - 1, o_0 = base, o_p = base + 1;  // window byte offsets for shift -1, 0, +1
+    const unsigned *R = sR[d] + (g * RPT) * RS + j;
+#pragma unroll
+    for (int rr = 0; rr < RPT + 2; rr++) {
+      const unsigned *rw = R + rr * RS;
+      unsigned w0 = rw[0], w1 = rw[1], w2 = rw[2];
+      // shifted words for x offsets -1, 0, +1 (window coordinates)
+      unsigned sh[3];
+      {
+        int o = o_m;
+        sh[0] = __funnelshift_r(o < 4 ? w0 : w1, o < 4 ? w1 : w2, 8 * (o & 3));
+        o = o_0;
+        sh[1] = __funnelshift_r(o < 4 ? w0 : w1, o < 4 ? w1 : w2, 8 * (o & 3));
+        o = o_p;
+        sh[2] = __funnelshift_r(o < 4 ? w0 : w1, o < 4 ? w1 : w2, 8 * (o & 3));
+      }
+      // window row rr pairs with P row r = rr - 1 - wdy for window shifts wdy in {-1,0,1}
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        const int wdy = sgn * DY[k], wdx = sgn * DX[k];
+        const int r = rr - 1 - wdy;
+        if (r >= 0 && r < RPT) acc[d * 9 + k] = __vsadu4(p[r], sh[wdx + 1]) + acc[d * 9 + k];
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 18; k++) {
+    unsigned v = __reduce_add_sync(0xffffffffu, acc[k]);
+    if (lane == 0) s_err[warp][k] = (int)v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 18) {
+    int e = 0;
+    for (int w = 0; w < (NT + 31) / 32; w++) e += s_err[w][threadIdx.x];
+    s_fin[threadIdx.x] = e;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
+}
+
+// ------------------------------------------------------------ exact path
+
+struct B0View {
+  Plane p;
+  int Y, X, B, Bc;       // picture, fill border, compact border
+  int Ya, Ba;            // alloc geometry of the reference's buffer (rows)
+  unsigned long long size_field;
+};
+
+// Cell of the reference's level-0 buffer at logical (y, x): the compact plane where
+// it is materialised, else zero (never-written fresh heap), except the malloc size
+// field seen at x in [-4, 0) of the rows whose pointer is not shifted (A.3).
+__device__ __forceinline__ int b0_cell(const B0View &v, int slot, int y, int x) {
+  if (y >= -v.Bc && y < v.Y + v.Bc && x >= -v.Bc && x < v.X + v.Bc) return v.p.row(slot, y)[x];
+  if (x < 0 && x >= -4 && y >= v.Ya - v.Ba && y < v.Ya + v.Ba)
+    return (short)((v.size_field >> (16 * (x + 4))) & 0xffff);
+  return 0;
+}
+// High-band cell (row >= Y or column >= X inside the level-1 domain): zero beyond the
+// fill_border replicas.
+__device__ __forceinline__ int b0_high(const B0View &v, int slot, int y, int x) {
+  if (y >= v.Y + v.B || x >= v.X + v.B) return 0;
+  return v.p.row(slot, y)[x];
+}
+
+// Column pass of the level-1 synthesis (5_3.cpp:81-94 on column xp of [0,2Y) x [0,2X)).
+__device__ int t1_even(const B0View &v, int slot, int i, int xp) {
+  int low = xp < v.X ? (int)v.p.row(slot, i)[xp] : b0_high(v, slot, i, xp);
+  int h = (i == 0) ? b0_high(v, slot, v.Y, xp) / 2
+                   : (b0_high(v, slot, v.Y + i, xp) + b0_high(v, slot, v.Y + i - 1, xp)) / 4;
+  return (short)(low - h);
+}
+__device__ int t1_cell(const B0View &v, int slot, int y, int xp) {
+  int i = y >> 1;
+  if (!(y & 1)) return t1_even(v, slot, i, xp);
+  int e0 = t1_even(v, slot, i, xp);
+  int h = b0_high(v, slot, v.Y + i, xp);
+  if (i < v.Y - 1) return (short)(h + (e0 + t1_even(v, slot, i + 1, xp)) / 2);
+  return (short)(h + e0);
+}
+// Level-1 image cell inside [0,2Y) x [0,2X) (row pass on top of the column pass).
+__device__ int b1_even(const B0View &v, int slot, int y, int j) {
+  int h = (j == 0) ? t1_cell(v, slot, y, v.X) / 2
+                   : (t1_cell(v, slot, y, v.X + j) + t1_cell(v, slot, y, v.X + j - 1)) / 4;
+  return (short)(t1_cell(v, slot, y, j) - h);
+}
+__device__ int b1_inside(const B0View &v, int slot, int y, int x) {
+  int j = x >> 1;
+  if (!(x & 1)) return b1_even(v, slot, y, j);
+  int e0 = b1_even(v, slot, y, j);
+  int h = t1_cell(v, slot, y, v.X + j);
+  if (j < v.X - 1) return (short)(h + (e0 + b1_even(v, slot, y, j + 1)) / 2);
+  return (short)(h + e0);
+}
+__device__ __forceinline__ int b1_cell(const B0View &v, int slot, int y, int x) {
+  if (y >= 0 && y < 2 * v.Y && x >= 0 && x < 2 * v.X) return b1_inside(v, slot, y, x);
+  return b0_cell(v, slot, y, x);
+}
+
+// Fills dst (h x w, row stride w) with the level-l window whose top-left is (y0, x0).
+// Level 2 is built from a level-1 window staged in `tmp` (high bands of the second
+// synthesis are zero because B <= min(X, Y): checked on the host).
+__device__ void gen_window(const B0View &v, int slot, int l, int y0, int x0, int h, int w,
+                           short *dst, short *tmp, int nthreads) {
+  if (l == 1) {
+    for (int i = threadIdx.x; i < h * w; i += nthreads)
+      dst[i] = (short)b1_cell(v, slot, y0 + i / w, x0 + i % w);
+    return;
+  }
+  // level-1 window covering rows [y0>>1, ((y0+h-1)>>1)+1], same for columns (floor division)
+  const int ty0 = y0 >> 1, tx0 = x0 >> 1;
+  const int th = ((y0 + h - 1) >> 1) - ty0 + 2, tw = ((x0 + w - 1) >> 1) - tx0 + 2;
+  const int Y2 = 4 * v.Y, X2 = 4 * v.X, Y1 = 2 * v.Y, X1 = 2 * v.X;
+  for (int i = threadIdx.x; i < th * tw; i += nthreads) {
+    int y = ty0 + i / tw, x = tx0 + i % tw;
+    tmp[i] = (y >= 0 && y < Y1 && x >= 0 && x < X1) ? (short)b1_inside(v, slot, y, x) : (short)0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < h * w; i += nthreads) {
+    int y = y0 + i / w, x = x0 + i % w;
+    int val;
+    if (y >= 0 && y < Y2 && x >= 0 && x < X2) {
+      // column pass (zero high band): T(y, xp) for xp = x>>1 and (x>>1)+1
+      auto T = [&](int yy, int xp) -> int {
+        const short *col = tmp + (xp - tx0);
+        int i0 = yy >> 1;
+        int a = col[(i0 - ty0) * tw];
+        if (!(yy & 1)) return a;
+        if (yy == Y2 - 1) return a;
+        return (short)((a + col[(i0 + 1 - ty0) * tw]) / 2);
+      };
+      int j0 = x >> 1;
+      int a = T(y, j0);
+      if (!(x & 1) || x == X2 - 1)
+        val = a;
+      else
+        val = (short)((a + T(y, j0 + 1)) / 2);
+    } else {
+      val = b0_cell(v, slot, y, x);
+    }
+    dst[i] = (short)val;
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) k_subpel_exact(SubpelParams q, B0View v) {
+  constexpr int RW = W + 2;
+  extern __shared__ short sm[];
+  short *Ps = sm;
+  short *Rs0 = Ps + W * W;
+  short *Rs1 = Rs0 + RW * RW;
+  short *tmp = Rs1 + RW * RW;  // (W/2 + 3)^2 level-1 staging
+  __shared__ int s_part[8][18];
+  __shared__ int s_fin[18];
+  const int total = *q.slow_count;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int id = q.slow_list[item];
+    const int bx = id % q.BX, by = (id / q.BX) % q.BY, pair = id / (q.BX * q.BY);
+    short c[4];
+    subpel_centre(q, pair, by, bx, c);
+    const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
+    const int py0 = by * W, px0 = bx * W;
+    gen_window(v, ps, q.l, py0, px0, W, W, Ps, tmp, blockDim.x);
+    __syncthreads();
+    gen_window(v, r0s, q.l, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, RW, RW, Rs0, tmp, blockDim.x);
+    __syncthreads();
+    gen_window(v, r1s, q.l, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, RW, RW, Rs1, tmp, blockDim.x);
+    __syncthreads();
+    unsigned acc[18];
+#pragma unroll
+    for (int k = 0; k < 18; k++) acc[k] = 0;
+    for (int i = threadIdx.x; i < W * W; i += blockDim.x) {
+      int y = i / W, x = i % W;
+      int p = Ps[i];
+      const short *a = Rs0 + (y + 1) * RW + x + 1;
+      const short *b = Rs1 + (y + 1) * RW + x + 1;
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        int off = c_cand9[k][0] * RW + c_cand9[k][1];
+        acc[k] = __sad(p, (int)a[off], acc[k]);
+        acc[9 + k] = __sad(p, (int)b[-off], acc[9 + k]);
+      }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 18; k++) {
+      unsigned s = __reduce_add_sync(0xffffffffu, acc[k]);
+      if (lane == 0) s_part[warp][k] = (int)s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 18) {
+      int e = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) e += s_part[w][threadIdx.x];
+      s_fin[threadIdx.x] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
+    __syncthreads();
+  }
+}
+
+template <int W>
+static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) {
+  constexpr int NT = (W / 4) * (W / 8);
+  dim3 grid(q.BX, q.BY, npairs);
+  {
+    ProfScope ps_(L, KC_SEARCH);
+    k_subpel_fast<W><<<grid, NT, 0, L.stream>>>(q);
+    COUNT(L);
+  }
+  B0View v;
+  v.p = q.b0;
+  v.Y = q.Y;
+  v.X = q.X;
+  v.B = q.B;
+  v.Bc = q.Bc;
+  v.Ya = q.Ya;
+  v.Ba = q.Ba;
+  v.size_field = q.size_field;
+  const int RW = W + 2, TW = W / 2 + 4;
+  size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW + (size_t)TW * TW) * sizeof(short);
+  static size_t s_attr = 0;
+  if (smem > 48 * 1024 && smem > s_attr) {
+    cudaFuncSetAttribute(k_subpel_exact<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    s_attr = smem;
+  }
+  {
+    ProfScope ps_(L, KC_SEARCH_EXACT);
+    k_subpel_exact<W><<<148 * 4, 256, smem, L.stream>>>(q, v);
+    COUNT(L);
+  }
+}
+
+bool subpel_supported(int W) { return W == 32 || W == 64; }
+
+void launch_subpel(const Launch &L, const SubpelParams &q, int W, int npairs) {
+  if (npairs <= 0) return;
+  if (W == 32)
+    launch_subpel_w<32>(L, q, npairs);
+  else
+    launch_subpel_w<64>(L, q, npairs);
+}

@@ -100,7 +100,12 @@ class Context:
     def synchronize(self):
         check(self._L.qsvc_synchronize(self._h))
 
-    KERNEL_CLASSES = ("image", "dwt_rows", "dwt_cols", "search", "predict", "residue", "update")
+    KERNEL_CLASSES = ("image", "dwt_rows", "dwt_cols", "search", "predict", "residue", "update",
+                      "search_exact")
+
+    def set_me_mode(self, mode: int):
+        """0 automatic, 1 literal (materialised) ME path, 2 fused ME path or fail."""
+        check(self._L.qsvc_set_me_mode(self._h, mode))
 
     def profile_enable(self, on=True):
         check(self._L.qsvc_profile_enable(self._h, 1 if on else 0))

@@ -26,6 +26,8 @@ CASES = [
     (96, 64, 1, 3, 16, 6, 1, 0.25, 0),     # search range that is not a power of two
     (80, 48, 1, 3, 16, 16, 2, 0.25, 0),    # border larger than the picture
     (176, 144, 2, 3, 32, 4, 1, 0.5, 3),    # X % bs != 0 (uncovered columns)
+    (352, 288, 1, 3, 16, 8, 2, 0.0, 0),    # CIF quarter-pel: mostly fast-path blocks in the fused ME
+    (320, 192, 1, 4, 16, 16, 1, 0.0, 0),   # half-pel, sr up to 64
 ]
 
 
@@ -91,6 +93,30 @@ def test_resident_analyze_synthesize_match_oracle(ctx, X, Y, GOPs, TRLs, bs, sr,
         low[0::2], low[1::2] = even, odd
     rec = ctx.synthesize(sub, X, Y, GOPs, TRLs, bs, sr, a, uf)
     assert np.array_equal(rec, low)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("X,Y,GOPs,TRLs,bs,sr,a,uf,flat", [c for c in CASES if c[6] in (1, 2) and c[4] << c[6] <= 64])
+def test_me_literal_and_fused_paths_agree_with_oracle(ctx, mode, X, Y, GOPs, TRLs, bs, sr, a, uf, flat):
+    """mode 1: literal path (materialised up-sampled images); mode 2: fused sub-pixel
+    path (u8 planes + packed-byte SAD + exact generator for polluted/edge blocks)."""
+    from qsvc_b200._lib import QsvcError
+    low = clip_for(X, Y, GOPs, TRLs, sr, flat, seed=13)
+    ctx.set_me_mode(mode)
+    try:
+        for s in level_schedule(GOPs, TRLs, bs, sr, block_size_min=bs):
+            even, odd = low[0::2], low[1::2]
+            mv_o = orc.motion_estimate(even, odd, X, Y, bs, s["search_range"], a)
+            try:
+                mv_g = ctx.motion_estimate(even, odd, X, Y, bs, s["search_range"], a)
+            except QsvcError:
+                assert mode == 2  # geometry outside the fused path's domain: refused, not wrong
+                continue
+            bad = np.argwhere(mv_g != mv_o)
+            assert bad.size == 0, f"motion_{s['t']}: {len(bad)} components differ, first {bad[:5].tolist()}"
+            low = even
+    finally:
+        ctx.set_me_mode(0)
 
 
 def test_first_pair_flag_for_gop_shards(ctx):
