@@ -278,10 +278,12 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     uint8_t *v[3] = {nullptr, nullptr, nullptr};
     for (int l = 0; l <= a; l++) TRY(s.get(vbytes[l] * nslots, (void **)&v[l]));
     short *mv_tmp;
-    int *d_slots, *d_flags, *d_slow;
+    int *d_slots, *d_slow;
+    uint8_t *d_flags;
+    const int tiles_x = (X + 15) / 16, tiles_per_slot = tiles_x * ((Y + 15) / 16);
     TRY(s.get((size_t)m * field * sizeof(short), (void **)&mv_tmp));
     TRY(s.get((size_t)m * 3 * sizeof(int), (void **)&d_slots));
-    TRY(s.get((size_t)(nslots + 1) * sizeof(int), (void **)&d_flags));
+    TRY(s.get((size_t)nslots * tiles_per_slot + 16, (void **)&d_flags));
     TRY(s.get(((size_t)m * BY * BX + 1) * sizeof(int), (void **)&d_slow));
     std::vector<int> slots(3 * m);
     for (int i = 0; i < m; i++) {
@@ -291,7 +293,7 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     }
     CU(cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(raw, 0, slot_shorts * nslots * sizeof(short), c->stream));
-    CU(cudaMemsetAsync(d_flags, 0, (size_t)(nslots + 1) * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(d_flags, 0, (size_t)nslots * tiles_per_slot + 16, c->stream));
     launch_load_u8(Lh, img, 0, m + 1, even, even_stride, 0, i0, 1, Y, X);
     launch_load_u8(Lh, img, m + 1, m, odd, odd_stride, 0, i0, 1, Y, X);
     launch_fill_border(Lh, img, 0, m + 1, Y, X, B);
@@ -336,7 +338,8 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       run_search(ME_DESCEND, desp(BY, l), desp(BX, l), sr);
     }
     // byte planes of the level-0 interiors and their zero-high-band interpolations
-    launch_plane_to_u8(Lh, img, 0, nslots, Y, X, v[0], (long long)vbytes[0], pitch[0], d_flags);
+    launch_plane_to_u8(Lh, img, 0, nslots, Y, X, v[0], (long long)vbytes[0], pitch[0], d_flags, tiles_x,
+                       tiles_per_slot);
     for (int l = 1; l <= a; l++)
       launch_upsample2x(Lh, v[l - 1], Y << (l - 1), X << (l - 1), pitch[l - 1], (long long)vbytes[l - 1],
                         v[l], pitch[l], (long long)vbytes[l], nslots);
@@ -348,7 +351,9 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       q.v = v[l];
       q.v_slot_stride = (long long)vbytes[l];
       q.v_pitch = pitch[l];
-      q.slot_flags = d_flags;
+      q.tile_bad = d_flags;
+      q.tiles_x = tiles_x;
+      q.tiles_per_slot = tiles_per_slot;
       q.mv_out = bufs[(j + n_search - 1) & 1];
       q.mv_in = bufs[(j + n_search) & 1];
       q.BY = BY;

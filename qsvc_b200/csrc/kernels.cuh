@@ -78,7 +78,8 @@ struct SubpelParams {
   const uint8_t *v;    // V_l planes (u8, one per slot) of this level
   long long v_slot_stride;
   int v_pitch;
-  const int *slot_flags;  // nonzero: the slot's level-0 interior does not fit in bytes
+  const uint8_t *tile_bad;  // per slot, per 16x16 level-0 tile: holds a sample outside [0,255]
+  int tiles_x, tiles_per_slot;
   const short *mv_in;
   short *mv_out;
   int BY, BX;
@@ -94,7 +95,8 @@ struct SubpelParams {
 bool subpel_supported(int W);
 void launch_subpel(const Launch &L, const SubpelParams &q, int W, int npairs);
 void launch_plane_to_u8(const Launch &L, Plane src, int slot0, int nslots, int Y, int X,
-                        uint8_t *dst, long long dst_slot_stride, int pitch, int *flags);
+                        uint8_t *dst, long long dst_slot_stride, int pitch, uint8_t *tile_bad,
+                        int tiles_x, int tiles_per_slot);
 void launch_upsample2x(const Launch &L, const uint8_t *in, int n, int m, int pitch_in,
                        long long in_slot_stride, uint8_t *out, int pitch_out,
                        long long out_slot_stride, int nslots);

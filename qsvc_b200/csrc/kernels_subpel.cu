@@ -31,27 +31,29 @@ __constant__ int c_cand9[9][2] = {{-1, -1}, {-1, 1}, {1, -1}, {1, 1}, {-1, 0},
 
 __global__ void __launch_bounds__(256) k_plane_to_u8(Plane src, int slot0, int Y, int X,
                                                      uint8_t *dst, long long dst_slot_stride,
-                                                     int pitch, int *flags) {
+                                                     int pitch, uint8_t *tile_bad, int tiles_x,
+                                                     int tiles_per_slot) {
+  // tile_bad[slot][y >> 4][x >> 4] != 0: that 16x16 tile holds a sample outside [0,255]
   const int s = blockIdx.z;
-  int bad = 0;
   for (int y = blockIdx.y; y < Y; y += gridDim.y) {
     const short *row = src.row(slot0 + s, y);
     uint8_t *drow = dst + (long long)s * dst_slot_stride + (long long)y * pitch;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < X; x += gridDim.x * blockDim.x) {
       int v = row[x];
-      bad |= (unsigned)v > 255u;
+      if ((unsigned)v > 255u) tile_bad[(long long)s * tiles_per_slot + (y >> 4) * tiles_x + (x >> 4)] = 1;
       drow[x] = (uint8_t)v;
     }
   }
-  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&flags[s], 1);
 }
 
 void launch_plane_to_u8(const Launch &L, Plane src, int slot0, int nslots, int Y, int X,
-                        uint8_t *dst, long long dst_slot_stride, int pitch, int *flags) {
+                        uint8_t *dst, long long dst_slot_stride, int pitch, uint8_t *tile_bad,
+                        int tiles_x, int tiles_per_slot) {
   if (nslots <= 0) return;
   dim3 grid((X + 1023) / 1024, Y < 512 ? Y : 512, nslots);
   ProfScope ps_(L, KC_IMG);
-  k_plane_to_u8<<<grid, 256, 0, L.stream>>>(src, slot0, Y, X, dst, dst_slot_stride, pitch, flags);
+  k_plane_to_u8<<<grid, 256, 0, L.stream>>>(src, slot0, Y, X, dst, dst_slot_stride, pitch, tile_bad,
+                                            tiles_x, tiles_per_slot);
   COUNT(L);
 }
 
@@ -180,10 +182,27 @@ __global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_fast(SubpelParams 
   // B_l == V_l on [clean, dim) x [clean, dim): outside the rows/columns reached by the
   // fill_border replicas that sit in the first high-band rows/columns of level 1
   const int clean = (2 * q.B + 2) << (l - 1);
-  bool fast = !(q.slot_flags[r0s] | q.slot_flags[r1s] | q.slot_flags[ps]);
+  bool fast = true;
 #pragma unroll
   for (int d = 0; d < 2; d++)
     fast = fast && wy[d] >= clean && wx[d] >= clean && wy[d] + W + 2 <= Yl && wx[d] + W + 2 <= Xl;
+  if (fast) {
+    // every level-0 pixel under the three windows must be a byte (non-invertible
+    // pyramids leave a few out-of-range samples near the picture edges)
+    int bad = 0;
+    for (int img = 0; img < 3; img++) {
+      const int slot = img == 0 ? r0s : (img == 1 ? r1s : ps);
+      const int y0 = img == 2 ? py0 : wy[img], x0 = img == 2 ? px0 : wx[img];
+      const int span = img == 2 ? W : W + 2;
+      const int ty0 = (y0 >> l) >> 4, ty1 = min((((y0 + span - 1) >> l) + 1), q.Y - 1) >> 4;
+      const int tx0 = (x0 >> l) >> 4, tx1 = min((((x0 + span - 1) >> l) + 1), q.X - 1) >> 4;
+      const int nty = ty1 - ty0 + 1, ntx = tx1 - tx0 + 1;
+      const uint8_t *map = q.tile_bad + (long long)slot * q.tiles_per_slot;
+      for (int i = threadIdx.x; i < nty * ntx; i += NT)
+        bad |= map[(ty0 + i / ntx) * q.tiles_x + tx0 + i % ntx];
+    }
+    fast = !__syncthreads_or(bad);
+  }
   if (!fast) {
     if (threadIdx.x == 0) {
       int idx = atomicAdd(q.slow_count, 1);
@@ -312,6 +331,18 @@ __device__ int b1_even(const B0View &v, int slot, int y, int j) {
 }
 __device__ int b1_inside(const B0View &v, int slot, int y, int x) {
   int j = x >> 1;
+  if (y >= 2 * v.B + 2 && x >= 2 * v.B + 2) {
+    // every high-band sample this cell depends on is zero: plain bilinear x2
+    // (5_3.cpp:81-94 with h = 0; columns first, then rows)
+    const int i = y >> 1;
+    const short *r0 = v.p.row(slot, i);
+    const short *r1 = v.p.row(slot, i + 1 < v.Y ? i + 1 : i);
+    const int jn = j + 1 < v.X ? j + 1 : j;
+    int t0 = (y & 1) ? (short)((r0[j] + r1[j]) / 2) : r0[j];
+    if (!(x & 1)) return t0;
+    int t1 = (y & 1) ? (short)((r0[jn] + r1[jn]) / 2) : r0[jn];
+    return (short)((t0 + t1) / 2);
+  }
   if (!(x & 1)) return b1_even(v, slot, y, j);
   int e0 = b1_even(v, slot, y, j);
   int h = t1_cell(v, slot, y, v.X + j);
@@ -323,24 +354,66 @@ __device__ __forceinline__ int b1_cell(const B0View &v, int slot, int y, int x) 
   return b0_cell(v, slot, y, x);
 }
 
+// Level-1 window (h x w at (y0, x0)) into dst.  The column-pass samples T(y, j)
+// (low columns) and T(y, X + j) (high columns) that the row pass needs are staged
+// in TL / TH first, so every level-0 cell is read a bounded number of times.
+__device__ void gen_level1(const B0View &v, int slot, int y0, int x0, int h, int w, short *dst,
+                           short *TL, short *TH, int nthreads) {
+  const int Y1 = 2 * v.Y, X1 = 2 * v.X;
+  const int ya = max(y0, 0), yb = min(y0 + h, Y1);
+  const int xa = max(x0, 0), xb = min(x0 + w, X1);
+  int j0 = 0, nj = 0, hj0 = 0, nh = 0;
+  if (ya < yb && xa < xb) {
+    j0 = xa >> 1;
+    const int j1 = min(((xb - 1) >> 1) + 1, v.X - 1);
+    nj = j1 - j0 + 1;
+    hj0 = max(j0 - 1, 0);
+    nh = j1 - hj0 + 1;
+    const int rows = yb - ya;
+    for (int i = threadIdx.x; i < rows * nj; i += nthreads)
+      TL[i] = (short)t1_cell(v, slot, ya + i / nj, j0 + i % nj);
+    for (int i = threadIdx.x; i < rows * nh; i += nthreads)
+      TH[i] = (short)t1_cell(v, slot, ya + i / nh, v.X + hj0 + i % nh);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < h * w; i += nthreads) {
+    const int y = y0 + i / w, x = x0 + i % w;
+    int val;
+    if (y >= 0 && y < Y1 && x >= 0 && x < X1) {
+      const short *tl = TL + (y - ya) * nj - j0;
+      const short *th = TH + (y - ya) * nh - hj0;
+      auto even = [&](int jj) -> int {
+        int hh = (jj == 0) ? th[0] / 2 : (th[jj] + th[jj - 1]) / 4;
+        return (short)(tl[jj] - hh);
+      };
+      const int j = x >> 1;
+      if (!(x & 1)) {
+        val = even(j);
+      } else {
+        int e0 = even(j);
+        val = (j < v.X - 1) ? (short)(th[j] + (e0 + even(j + 1)) / 2) : (short)(th[j] + e0);
+      }
+    } else {
+      val = b0_cell(v, slot, y, x);
+    }
+    dst[i] = (short)val;
+  }
+}
+
 // Fills dst (h x w, row stride w) with the level-l window whose top-left is (y0, x0).
 // Level 2 is built from a level-1 window staged in `tmp` (high bands of the second
 // synthesis are zero because B <= min(X, Y): checked on the host).
 __device__ void gen_window(const B0View &v, int slot, int l, int y0, int x0, int h, int w,
-                           short *dst, short *tmp, int nthreads) {
+                           short *dst, short *tmp, short *TL, short *TH, int nthreads) {
   if (l == 1) {
-    for (int i = threadIdx.x; i < h * w; i += nthreads)
-      dst[i] = (short)b1_cell(v, slot, y0 + i / w, x0 + i % w);
+    gen_level1(v, slot, y0, x0, h, w, dst, TL, TH, nthreads);
     return;
   }
   // level-1 window covering rows [y0>>1, ((y0+h-1)>>1)+1], same for columns (floor division)
   const int ty0 = y0 >> 1, tx0 = x0 >> 1;
   const int th = ((y0 + h - 1) >> 1) - ty0 + 2, tw = ((x0 + w - 1) >> 1) - tx0 + 2;
-  const int Y2 = 4 * v.Y, X2 = 4 * v.X, Y1 = 2 * v.Y, X1 = 2 * v.X;
-  for (int i = threadIdx.x; i < th * tw; i += nthreads) {
-    int y = ty0 + i / tw, x = tx0 + i % tw;
-    tmp[i] = (y >= 0 && y < Y1 && x >= 0 && x < X1) ? (short)b1_inside(v, slot, y, x) : (short)0;
-  }
+  const int Y2 = 4 * v.Y, X2 = 4 * v.X;
+  gen_level1(v, slot, ty0, tx0, th, tw, tmp, TL, TH, nthreads);
   __syncthreads();
   for (int i = threadIdx.x; i < h * w; i += nthreads) {
     int y = y0 + i / w, x = x0 + i % w;
@@ -375,7 +448,9 @@ __global__ void __launch_bounds__(256) k_subpel_exact(SubpelParams q, B0View v) 
   short *Ps = sm;
   short *Rs0 = Ps + W * W;
   short *Rs1 = Rs0 + RW * RW;
-  short *tmp = Rs1 + RW * RW;  // (W/2 + 3)^2 level-1 staging
+  short *tmp = Rs1 + RW * RW;  // (W/2 + 4)^2 level-1 staging
+  short *TL = tmp + (W / 2 + 4) * (W / 2 + 4);
+  short *TH = TL + (W + 2) * (W / 2 + 4);
   __shared__ int s_part[8][18];
   __shared__ int s_fin[18];
   const int total = *q.slow_count;
@@ -386,11 +461,11 @@ __global__ void __launch_bounds__(256) k_subpel_exact(SubpelParams q, B0View v) 
     subpel_centre(q, pair, by, bx, c);
     const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
     const int py0 = by * W, px0 = bx * W;
-    gen_window(v, ps, q.l, py0, px0, W, W, Ps, tmp, blockDim.x);
+    gen_window(v, ps, q.l, py0, px0, W, W, Ps, tmp, TL, TH, blockDim.x);
     __syncthreads();
-    gen_window(v, r0s, q.l, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, RW, RW, Rs0, tmp, blockDim.x);
+    gen_window(v, r0s, q.l, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, RW, RW, Rs0, tmp, TL, TH, blockDim.x);
     __syncthreads();
-    gen_window(v, r1s, q.l, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, RW, RW, Rs1, tmp, blockDim.x);
+    gen_window(v, r1s, q.l, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, RW, RW, Rs1, tmp, TL, TH, blockDim.x);
     __syncthreads();
     unsigned acc[18];
 #pragma unroll
@@ -444,7 +519,7 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
   v.Ba = q.Ba;
   v.size_field = q.size_field;
   const int RW = W + 2, TW = W / 2 + 4;
-  size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW + (size_t)TW * TW) * sizeof(short);
+  size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW + (size_t)TW * TW + 2 * (size_t)RW * TW) * sizeof(short);
   static size_t s_attr = 0;
   if (smem > 48 * 1024 && smem > s_attr) {
     cudaFuncSetAttribute(k_subpel_exact<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
