@@ -69,6 +69,9 @@ int qsvc_int_peak(qsvc_ctx *ctx, double *u8_sad_ops_per_s, double *i32_sad_ops_p
  * materialises the up-sampled images like the reference, 2 fused or fail.  All
  * modes produce identical motion fields. */
 int qsvc_set_me_mode(qsvc_ctx *ctx, int mode);
+/* Same for decorrelate / correlate (env QSVC_MC_MODE): 1 literal path with materialised
+ * int16 planes, 2 byte-plane fused path or fail, 0 automatic. */
+int qsvc_set_mc_mode(qsvc_ctx *ctx, int mode);
 
 /* Replaces `motion_estimate` main(), reference motion_estimate.cpp:490-912
  * (search: :70-184, pyramid driver: :260-413).

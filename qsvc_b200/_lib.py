@@ -47,6 +47,7 @@ SIGNATURES = {
     "qsvc_timer_stop": (_i, [C.c_void_p, C.POINTER(C.c_float)]),
     "qsvc_synchronize": (_i, [C.c_void_p]),
     "qsvc_set_me_mode": (_i, [C.c_void_p, _i]),
+    "qsvc_set_mc_mode": (_i, [C.c_void_p, _i]),
     "qsvc_profile_enable": (_i, [C.c_void_p, _i]),
     "qsvc_profile_read": (_i, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong), _i]),
     "qsvc_int_peak": (_i, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

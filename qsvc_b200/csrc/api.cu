@@ -67,6 +67,7 @@ struct qsvc_ctx {
   long long launches = 0;
   Profiler prof;
   std::vector<PoolBlock> pool;
+  int mc_mode = 0;  // same three values for the decorrelate / correlate path
   int me_mode = 0;  // 0: automatic, 1: literal (materialised) path only, 2: fused path required
   size_t me_budget = (size_t)40 << 30;  // bytes of HBM for the ME image planes of one chunk
   // resident sequence
@@ -526,6 +527,8 @@ static void prepare_reference(qsvc_ctx *c, Plane ref, int slot_set, const uint8_
   for (int s = 1; s <= a; s++) dwt_synthesize(Lh, ref, s0, 3, Y << s, X << s, 1);
 }
 
+#include "mc_fused.inc"
+
 // analysis != 0: decorrelate (in = odd frames, out = high frames);
 // analysis == 0: correlate   (in = high frames, out = odd frames, types given).
 static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long even_stride,
@@ -543,10 +546,8 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
   const int ba = (4 * sr + ov) << a;
   Launch Lh = c->L();
   Scratch s(c);
-  PlaneAlloc ref, pred;
-  TRY(alloc_dense_planes(s, 6, Ya, Xa, &ref));
-  TRY(alloc_dense_planes(s, 3, Ya, Xa, &pred));
-  CU(cudaMemsetAsync(pred.raw, 0, pred.bytes, c->stream));
+  const bool fused = c->mc_mode != 1 && mc_fused_ok(X, Y, bs, ov, a);
+  if (c->mc_mode == 2 && !fused) return fail(QSVC_EINVAL, "fused MC path requested but not applicable");
   int *d_hist = nullptr;
   const int HS = 1024;  // per pair: 256 predicted, 256 residue, 257 motion (+pad)
   const bool need_hist = analysis && !always_B;
@@ -556,6 +557,17 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
   }
   const int padh = heap_row_shorts(Xa, ba) - (Xa + 2 * ba);
 
+  if (fused) {
+    TRY(mc_fused_core(c, analysis, even, even_stride, in, in_stride, mv_in, n_pairs, X, Y, bs, sr, a,
+                      types_in, out, out_stride, prediction_out, need_hist ? d_hist : nullptr, HS));
+    if (need_hist)
+      for (int i = 0; i < n_pairs; i++)
+        launch_mv_hist(Lh, mv_in + (long long)i * field, (int)field, d_hist + (long long)i * HS + 512);
+  } else {
+  PlaneAlloc ref, pred;
+  TRY(alloc_dense_planes(s, 6, Ya, Xa, &ref));
+  TRY(alloc_dense_planes(s, 3, Ya, Xa, &pred));
+  CU(cudaMemsetAsync(pred.raw, 0, pred.bytes, c->stream));
   if (n_pairs > 0) prepare_reference(c, ref.p, 0, even, X, Y, a);
   for (int i = 0; i < n_pairs; i++) {
     prepare_reference(c, ref.p, (i + 1) & 1, even + (long long)(i + 1) * even_stride, X, Y, a);
@@ -589,6 +601,7 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
     r.is_I = (!analysis && types_in[i] == 'I') ? 1 : 0;
     launch_residue(Lh, r);
     if (need_hist) launch_mv_hist(Lh, mv, (int)field, d_hist + (long long)i * HS + 512);
+  }
   }
   CU(cudaGetLastError());
   if (!analysis) return QSVC_OK;
@@ -743,6 +756,7 @@ qsvc_ctx *qsvc_create(int device) {
     return nullptr;
   }
   if (const char *e = getenv("QSVC_ME_MODE")) c->me_mode = atoi(e);
+  if (const char *e = getenv("QSVC_MC_MODE")) c->mc_mode = atoi(e);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->me_budget = std::min<size_t>((size_t)64 << 30, free_b / 3);
   return c;
@@ -812,6 +826,11 @@ int qsvc_int_peak(qsvc_ctx *c, double *u8_sad_ops_per_s, double *i32_sad_ops_per
     if (packed && u8_sad_ops_per_s) *u8_sad_ops_per_s = best;
     if (!packed && i32_sad_ops_per_s) *i32_sad_ops_per_s = best;
   }
+  return QSVC_OK;
+}
+int qsvc_set_mc_mode(qsvc_ctx *c, int mode) {
+  if (!c || mode < 0 || mode > 2) return fail(QSVC_EINVAL, "bad mc_mode");
+  c->mc_mode = mode;
   return QSVC_OK;
 }
 int qsvc_set_me_mode(qsvc_ctx *c, int mode) {

@@ -143,3 +143,39 @@ struct UpdateParams {
 void launch_update(const Launch &L, const UpdateParams &q);
 // residue plane: top-left h x w = high - 128 (rest untouched)
 void launch_load_residue(const Launch &L, Plane dst, int slot, const uint8_t *src, int h, int w);
+
+// ---- byte-plane motion compensation (kernels_mcfused.cu) ----
+struct PredU8Params {
+  const uint8_t *v;          // V_a planes, [even frame][component], (Ya + 2) x v_pitch each
+  long long v_plane_stride;  // bytes between consecutive planes
+  int v_pitch;
+  uint8_t *p;                // P_a planes out, [pair][component]
+  long long p_plane_stride;
+  int p_pitch;
+  const short *mv;           // fields of the pairs
+  int f0;                    // V frame index of pair 0's reference[0]
+  int BY, BX, bsa, Ya, Xa, ba, padh;
+};
+void launch_predict_u8(const Launch &L, const PredU8Params &q, int npairs);
+
+struct LLParams {
+  const uint8_t *p;          // P_a planes, [pair][component]
+  long long p_plane_stride;
+  int p_pitch;
+  const uint8_t *in;         // analysis: odd frames; synthesis: high frames (I420, per pair)
+  long long in_stride;
+  uint8_t *out;              // analysis: high frames ('B' variant); synthesis: odd frames
+  long long out_stride;
+  uint8_t *prediction;       // nullable: prediction_<even> side output, frame stride pred_stride
+  long long pred_stride;
+  int *hist;                 // nullable: per pair [0,256) predicted luma, [256,512) residue + 128
+  int hist_stride;
+  const char *types;         // synthesis: frame types (device)
+  int X, Y, a, synth;
+  int smem_a;                // filled by the launcher
+};
+void launch_ll_residue(const Launch &L, LLParams q, int npairs);
+void launch_tail_state(const Launch &L, const uint8_t *P, long long plane_stride, int pitch,
+                       uint8_t *Pnext, int Ya, int Xa, int cy, int first_comp, int ncomp);
+void launch_copy_rows(const Launch &L, const uint8_t *src, uint8_t *dst, long long plane_stride,
+                      int pitch, int row0, int rows, int width);

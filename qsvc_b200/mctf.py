@@ -107,6 +107,10 @@ class Context:
         """0 automatic, 1 literal (materialised) ME path, 2 fused ME path or fail."""
         check(self._L.qsvc_set_me_mode(self._h, mode))
 
+    def set_mc_mode(self, mode: int):
+        """0 automatic, 1 literal decorrelate/correlate path, 2 byte-plane fused path or fail."""
+        check(self._L.qsvc_set_mc_mode(self._h, mode))
+
     def profile_enable(self, on=True):
         check(self._L.qsvc_profile_enable(self._h, 1 if on else 0))
 

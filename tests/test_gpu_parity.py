@@ -119,6 +119,38 @@ def test_me_literal_and_fused_paths_agree_with_oracle(ctx, mode, X, Y, GOPs, TRL
         ctx.set_me_mode(0)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("X,Y,GOPs,TRLs,bs,sr,a,uf,flat", CASES)
+def test_mc_literal_and_fused_paths_agree_with_oracle(ctx, mode, X, Y, GOPs, TRLs, bs, sr, a, uf, flat):
+    """decorrelate / correlate: mode 1 materialises int16 planes like the reference,
+    mode 2 runs on byte planes (k_predict_u8 + k_ll_residue + chained tail rows)."""
+    from qsvc_b200._lib import QsvcError
+    low = clip_for(X, Y, GOPs, TRLs, sr, flat, seed=17)
+    ctx.set_mc_mode(mode)
+    try:
+        for s in level_schedule(GOPs, TRLs, bs, sr, block_size_min=bs):
+            even, odd = low[0::2], low[1::2]
+            r = s["search_range"]
+            mv = orc.motion_estimate(even, odd, X, Y, bs, r, a)
+            high_o, types_o, mvf_o, pred_o, rc = orc.decorrelate(even, odd, mv, X, Y, bs, r, a)
+            try:
+                high_g, types_g, mvf_g, pred_g = ctx.decorrelate(even, odd, mv, X, Y, bs, r, a,
+                                                                 want_prediction=True)
+            except QsvcError:
+                assert mode == 2
+                continue
+            assert types_g == types_o
+            bad = np.argwhere(pred_g != pred_o)
+            assert bad.size == 0, f"prediction_{s['t']}: {len(bad)} differ, first {bad[:4].tolist()}"
+            assert np.array_equal(high_g, high_o) and np.array_equal(mvf_g, mvf_o)
+            odd_o, _ = orc.correlate(even, high_o, mvf_o, types_o, X, Y, bs, r, a)
+            odd_g, _ = ctx.correlate(even, high_o, mvf_o, types_o, X, Y, bs, r, a)
+            assert np.array_equal(odd_g, odd_o)
+            low = even
+    finally:
+        ctx.set_mc_mode(0)
+
+
 def test_first_pair_flag_for_gop_shards(ctx):
     """A later GOP shard must start from the carried (non-restored) reference[0]
     when the pyramid is not perfectly reconstructing."""
