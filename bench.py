@@ -289,16 +289,11 @@ def main():
     for s in sched:
         n, b = s["pairs"], s["block_size"]
         d2h += n * fb + 2 * n * 8 * (w["Y"] // b) * (w["X"] // b) + n
-        if s["t"] == w["TRLs"] - 1:
-            d2h += (n + 1) * fb
+        d2h += (n + 1) * fb
 
     def e2e_step():
-        ctx.resident_load(clip_pinned, w["X"], w["Y"])
-        ctx.resident_analyze(**kw)
-        for s in sched:
-            want = ("high", "motion", "motion_filtered", "frame_types") + (
-                ("low",) if s["t"] == w["TRLs"] - 1 else ())
-            outs[s["t"]] = ctx.resident_fetch(s["t"], s["pairs"], s["block_size"], want)
+        # the public API call: host clip in, host sub-bands out (pinned buffers reused)
+        outs.update(ctx.analyze(clip_pinned, w["X"], w["Y"], w["GOPs"], reuse_buffers=True, **kw))
 
     e2e_step()
     barrier()

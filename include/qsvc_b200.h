@@ -138,6 +138,22 @@ int qsvc_resident_fetch(qsvc_ctx *ctx, int level, uint8_t *high, int16_t *motion
  * search kernels and device milliseconds spent in them (summed over levels). */
 int qsvc_resident_stats(qsvc_ctx *ctx, double *sad_ops, float *search_ms, float *total_ms);
 
+/* analyze.py in one call with HOST buffers: uploads low_0, runs every level and
+ * copies each level's results back on a second stream while the next level
+ * computes.  outs has TRLs entries (outs[0] unused); NULL members are skipped.
+ * Use qsvc_host_alloc (pinned memory) for the buffers so that the copies overlap. */
+typedef struct qsvc_level_out {
+  uint8_t *high;
+  int16_t *motion;
+  int16_t *motion_filtered;
+  char *frame_types;
+  uint8_t *low;
+} qsvc_level_out;
+int qsvc_analyze(qsvc_ctx *ctx, const qsvc_analyze_params *params, const uint8_t *low0,
+                 int n_frames, const qsvc_level_out *outs);
+void *qsvc_host_alloc(size_t bytes);
+void qsvc_host_free(void *ptr);
+
 /* Inverse: un_update -> correlate -> merge per level from TRLs-1 down to 1
  * (synthesize.py:95-153, synthesize_step.py:84-143), frames resident in HBM.
  * Inputs are pushed per level with qsvc_resident_push, then synthesize runs and

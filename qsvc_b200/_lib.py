@@ -33,6 +33,12 @@ class AnalyzeParams(C.Structure):
 
 
 u8p, i16p, chp = C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.c_char_p
+
+
+class LevelOut(C.Structure):
+    _fields_ = [("high", u8p), ("motion", i16p), ("motion_filtered", i16p),
+                ("frame_types", C.c_void_p), ("low", u8p)]
+
 _i = C.c_int
 
 # name -> (restype, argtypes); every symbol include/qsvc_b200.h declares
@@ -60,6 +66,9 @@ SIGNATURES = {
                          u8p]),
     "qsvc_resident_load": (_i, [C.c_void_p, u8p, _i, _i, _i]),
     "qsvc_resident_analyze": (_i, [C.c_void_p, C.POINTER(AnalyzeParams)]),
+    "qsvc_analyze": (_i, [C.c_void_p, C.POINTER(AnalyzeParams), u8p, _i, C.POINTER(LevelOut)]),
+    "qsvc_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "qsvc_host_free": (None, [C.c_void_p]),
     "qsvc_resident_fetch": (_i, [C.c_void_p, _i, u8p, i16p, i16p, C.c_void_p, u8p]),
     "qsvc_resident_stats": (_i, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float)]),

@@ -62,7 +62,8 @@ struct LevelResult {
 
 struct qsvc_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  std::vector<cudaEvent_t> level_events;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   long long launches = 0;
   Profiler prof;
@@ -742,6 +743,7 @@ qsvc_ctx *qsvc_create(int device) {
   qsvc_ctx *c = new qsvc_ctx();
   c->device = device;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
       cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess) {
     fail(QSVC_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -782,6 +784,8 @@ void qsvc_destroy(qsvc_ctx *c) {
   cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->ev2);
   cudaEventDestroy(c->ev3);
+  for (auto e : c->level_events) cudaEventDestroy(e);
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1002,8 +1006,41 @@ int qsvc_resident_load(qsvc_ctx *c, const uint8_t *low0, int n_frames, int X, in
   return QSVC_OK;
 }
 
+static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_level_out *outs);
+
 int qsvc_resident_analyze(qsvc_ctx *c, const qsvc_analyze_params *p) {
   ENTER(c);
+  return analyze_levels(c, p, nullptr);
+}
+
+void *qsvc_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    fail(QSVC_ENOMEM, "cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+void qsvc_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+// analyze.py equivalent in one call with host buffers: upload, all levels, and each
+// level's results copied back on a second stream while the next level computes.
+int qsvc_analyze(qsvc_ctx *c, const qsvc_analyze_params *p, const uint8_t *low0, int n_frames,
+                 const qsvc_level_out *outs) {
+  ENTER(c);
+  if (!p || !low0 || !outs) return fail(QSVC_EINVAL, "bad arguments");
+  TRY(qsvc_resident_load(c, low0, n_frames, p->pixels_in_x, p->pixels_in_y));
+  TRY(analyze_levels(c, p, outs));
+  CU(cudaStreamSynchronize(c->copy_stream));
+  for (int t = 1; t < p->TRLs; t++)
+    if (outs[t].frame_types) memcpy(outs[t].frame_types, c->levels[t].types.data(), (size_t)c->levels[t].n_pairs);
+  return QSVC_OK;
+}
+
+static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_level_out *outs) {
   if (!p || !c->low0) return fail(QSVC_EINVAL, "no resident sequence");
   if (p->pixels_in_x != c->X || p->pixels_in_y != c->Y) return fail(QSVC_EINVAL, "geometry mismatch");
   const int X = c->X, Y = c->Y;
@@ -1039,6 +1076,24 @@ int qsvc_resident_analyze(qsvc_ctx *c, const qsvc_analyze_params *p) {
                  lv.motion_filtered, nullptr));
     TRY(update_level(c, 0, even, 2 * fb, lv.high, fb, lv.motion_filtered, lv.types.c_str(), n, X, Y,
                      bs, p->update_factor, lv.low, fb));
+    if (outs) {
+      // stream this level's results to the host behind the next level's compute
+      while ((int)c->level_events.size() <= t) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->level_events.push_back(e);
+      }
+      CU(cudaEventRecord(c->level_events[t], c->stream));
+      CU(cudaStreamWaitEvent(c->copy_stream, c->level_events[t], 0));
+      const qsvc_level_out &o = outs[t];
+      if (o.high) CU(cudaMemcpyAsync(o.high, lv.high, (size_t)fb * n, cudaMemcpyDeviceToHost, c->copy_stream));
+      if (o.motion)
+        CU(cudaMemcpyAsync(o.motion, lv.motion, (size_t)field * n * sizeof(short), cudaMemcpyDeviceToHost, c->copy_stream));
+      if (o.motion_filtered)
+        CU(cudaMemcpyAsync(o.motion_filtered, lv.motion_filtered, (size_t)field * n * sizeof(short),
+                           cudaMemcpyDeviceToHost, c->copy_stream));
+      if (o.low) CU(cudaMemcpyAsync(o.low, lv.low, (size_t)fb * (n + 1), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
     low = lv.low;
     pictures = (pictures + 1) / 2;
     sr = std::min(sr * 2, 128);       // analyze.py:144-147

@@ -38,20 +38,25 @@ __host__ __device__ __forceinline__ int iclamp(int v, int lo, int hi) {
 
 // ---- 5/3 integer lifting on a strided line (reference 5_3.cpp:39-115) ----
 // C `/` truncates toward zero; results are stored as short (wraps mod 2^16).
+// The truncating divisions by 2 and 4 are spelled as shift sequences: with a
+// plain `/` nvcc merges the /2 and /4 sites of different branches into one
+// division by a *variable* and calls its 16-bit division subroutine per sample.
+__host__ __device__ __forceinline__ int tdiv2(int x) { return (x + (int)((unsigned)x >> 31)) >> 1; }
+__host__ __device__ __forceinline__ int tdiv4(int x) { return (x + ((x >> 31) & 3)) >> 2; }
 
 // h[i] of an n-sample line s (analysis).
 __device__ __forceinline__ short l53_ana_h(const short *s, int st, int i, int n) {
   int half = n >> 1;
   if (!(n & 1) && i == half - 1) return (short)(s[(n - 1) * st] - s[(n - 2) * st]);
-  return (short)(s[(2 * i + 1) * st] - (s[(2 * i) * st] + s[(2 * i + 2) * st]) / 2);
+  return (short)(s[(2 * i + 1) * st] - tdiv2(s[(2 * i) * st] + s[(2 * i + 2) * st]));
 }
 // l[i] (analysis); i in [0, n - n/2).
 __device__ __forceinline__ short l53_ana_l(const short *s, int st, int i, int n) {
   int half = n >> 1;
-  if (i == 0) return (short)(s[0] + l53_ana_h(s, st, 0, n) / 2);
+  if (i == 0) return (short)(s[0] + tdiv2(l53_ana_h(s, st, 0, n)));
   if (i < half)
-    return (short)(s[(2 * i) * st] + (l53_ana_h(s, st, i, n) + l53_ana_h(s, st, i - 1, n)) / 4);
-  return (short)(s[(n - 1) * st] + l53_ana_h(s, st, half - 1, n) / 2);  // odd n tail
+    return (short)(s[(2 * i) * st] + tdiv4(l53_ana_h(s, st, i, n) + l53_ana_h(s, st, i - 1, n)));
+  return (short)(s[(n - 1) * st] + tdiv2(l53_ana_h(s, st, half - 1, n)));  // odd n tail
 }
 // Output sample j of the analysed line laid out [lows | highs].
 __device__ __forceinline__ short l53_ana_out(const short *s, int st, int j, int n) {
@@ -62,9 +67,9 @@ __device__ __forceinline__ short l53_ana_out(const short *s, int st, int j, int 
 // Synthesis: l = s (lows at 0), h at offset hoff = n - n/2.
 __device__ __forceinline__ short l53_syn_even(const short *l, const short *h, int st, int i, int n) {
   int half = n >> 1;
-  if (i == 0) return (short)(l[0] - h[0] / 2);
-  if (i < half) return (short)(l[i * st] - (h[i * st] + h[(i - 1) * st]) / 4);
-  return (short)(l[half * st] - h[(half - 1) * st] / 2);  // odd n tail
+  if (i == 0) return (short)(l[0] - tdiv2(h[0]));
+  if (i < half) return (short)(l[i * st] - tdiv4(h[i * st] + h[(i - 1) * st]));
+  return (short)(l[half * st] - tdiv2(h[(half - 1) * st]));  // odd n tail
 }
 // Output sample j of the synthesised line.
 __device__ __forceinline__ short l53_syn_out(const short *s, int st, int j, int n) {
@@ -76,7 +81,7 @@ __device__ __forceinline__ short l53_syn_out(const short *s, int st, int j, int 
   int e0 = l53_syn_even(l, h, st, i, n);
   if (!(n & 1) && i == half - 1) return (short)(h[i * st] + e0);
   int e1 = l53_syn_even(l, h, st, i + 1, n);
-  return (short)(h[i * st] + (e0 + e1) / 2);
+  return (short)(h[i * st] + tdiv2(e0 + e1));
 }
 
 // Value seen through data[y][x] of a bordered texture whose alloc and

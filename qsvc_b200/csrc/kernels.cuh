@@ -172,7 +172,7 @@ struct LLParams {
   int hist_stride;
   const char *types;         // synthesis: frame types (device)
   int X, Y, a, synth;
-  int smem_a;                // filled by the launcher
+  int smem_a, smem_b;        // filled by the launcher
 };
 void launch_ll_residue(const Launch &L, LLParams q, int npairs);
 void launch_tail_state(const Launch &L, const uint8_t *P, long long plane_stride, int pitch,

@@ -91,15 +91,36 @@ template <typename F>
 __device__ __forceinline__ int ll53(F S, int m, int n) {
   auto H = [&](int i) -> int {
     return (i == (n >> 1) - 1) ? (short)(S(n - 1) - S(n - 2))
-                               : (short)(S(2 * i + 1) - (S(2 * i) + S(2 * i + 2)) / 2);
+                               : (short)(S(2 * i + 1) - tdiv2(S(2 * i) + S(2 * i + 2)));
   };
-  if (m == 0) return (short)(S(0) + H(0) / 2);
-  return (short)(S(2 * m) + (H(m) + H(m - 1)) / 4);
+  if (m == 0) return (short)(S(0) + tdiv2(H(0)));
+  return (short)(S(2 * m) + tdiv4(H(m) + H(m - 1)));
 }
 template <typename F>
 __device__ __forceinline__ int hh53(F S, int i, int n) {
   return (i == (n >> 1) - 1) ? (short)(S(n - 1) - S(n - 2))
-                             : (short)(S(2 * i + 1) - (S(2 * i) + S(2 * i + 2)) / 2);
+                             : (short)(S(2 * i + 1) - tdiv2(S(2 * i) + S(2 * i + 2)));
+}
+
+// Flattened 2-D loop over h x w elements by 256 threads without a division per element.
+#define FOR_2D(r, c, h, w)                                                                  \
+  for (int i_ = threadIdx.x, r = i_ / (w), c = i_ - r * (w), dc_ = 256 % (w), dr_ = 256 / (w); \
+       i_ < (h) * (w); i_ += 256, c += dc_, r += dr_, r += (c >= (w)), c -= (c >= (w)) ? (w) : 0)
+
+// l[m] from a line reached through s[g * st] (g = global index minus `base`), line
+// length n.  Branch-free: out-of-line taps of the first / last sample are re-pointed at
+// valid cells and masked by selects.
+template <typename T>
+__device__ __forceinline__ int ll53_line(const T *s, int st, int base, int m, int n) {
+  const T *p = s + (2 * m - base) * st;
+  const bool last = (m == (n >> 1) - 1), first = (m == 0);
+  const int s0 = p[0], s1 = p[st];
+  const int s2 = p[last ? st : 2 * st];
+  const int sm1 = p[first ? 0 : -st], sm2 = p[first ? 0 : -2 * st];
+  const int hm = (short)(s1 - (last ? s0 : tdiv2(s0 + s2)));
+  const int hm1 = (short)(sm1 - tdiv2(sm2 + s0));
+  const int hs = first ? 2 * hm : hm + hm1;  // l[0] = s[0] + h[0]/2 == s[0] + (2 h[0])/4
+  return (short)(s0 + tdiv4(hs));
 }
 
 // Output tile [oy0,oy0+T) x [ox0,ox0+T) of the level-nlev LL band of one P_a plane,
@@ -131,41 +152,43 @@ __global__ void __launch_bounds__(256) k_ll_residue(LLParams q) {
   }
   short *A = reinterpret_cast<short *>(smraw);  // row-pass output
   short *B = A + q.smem_a;                      // column-pass output (level image)
+  uint8_t *U = reinterpret_cast<uint8_t *>(B + q.smem_b);  // level-0 byte tile
   const short *LL = nullptr;
   int ll_w = 0;
   if (nlev > 0) {
-    // level 0 -> 1 straight from the byte plane
+    // stage the level-0 byte tile with aligned 32-bit loads
+    const int xs = rx0[0] & ~3;
+    const int uw = (rx1[0] - xs + 3) >> 2;  // words per row
+    const int up = uw << 2;                 // byte pitch of U
+    {
+      const int h0 = ry1[0] - ry0[0];
+      unsigned *U4 = reinterpret_cast<unsigned *>(U);
+      FOR_2D(r, w, h0, uw)
+        U4[r * uw + w] = *reinterpret_cast<const unsigned *>(P + (long long)(ry0[0] + r) * q.p_pitch + xs + 4 * w);
+      __syncthreads();
+    }
+    // level 0 -> 1
     {
       const int h0 = ry1[0] - ry0[0], w1 = rx1[1] - rx0[1], h1 = ry1[1] - ry0[1];
       const int nx = q.X << q.a, ny = q.Y << q.a;
-      for (int i = threadIdx.x; i < h0 * w1; i += blockDim.x) {
-        const int r = i / w1, m = rx0[1] + i % w1;
-        const uint8_t *row = P + (long long)(ry0[0] + r) * q.p_pitch;
-        A[i] = (short)ll53([&](int g) { return (int)row[g]; }, m, nx);
-      }
+      const int mx0 = rx0[1], my0 = ry0[1];
+      FOR_2D(r, cc, h0, w1)
+        A[r * w1 + cc] = (short)ll53_line(U + r * up, 1, xs, mx0 + cc, nx);
       __syncthreads();
-      for (int i = threadIdx.x; i < h1 * w1; i += blockDim.x) {
-        const int m = ry0[1] + i / w1, col = i % w1;
-        const short *cp = A + col - ry0[0] * w1;
-        B[i] = (short)ll53([&](int g) { return (int)cp[g * w1]; }, m, ny);
-      }
+      FOR_2D(r, cc, h1, w1)
+        B[r * w1 + cc] = (short)ll53_line(A + cc, w1, ry0[0], my0 + r, ny);
       __syncthreads();
     }
     for (int k = 1; k < nlev; k++) {
       const int hk = ry1[k] - ry0[k], wk = rx1[k] - rx0[k];
       const int w1 = rx1[k + 1] - rx0[k + 1], h1 = ry1[k + 1] - ry0[k + 1];
       const int nx = (q.X << q.a) >> k, ny = (q.Y << q.a) >> k;
-      for (int i = threadIdx.x; i < hk * w1; i += blockDim.x) {
-        const int r = i / w1, m = rx0[k + 1] + i % w1;
-        const short *rp = B + r * wk - rx0[k];
-        A[i] = (short)ll53([&](int g) { return (int)rp[g]; }, m, nx);
-      }
+      const int mx0 = rx0[k + 1], my0 = ry0[k + 1], bx0 = rx0[k], by0 = ry0[k];
+      FOR_2D(r, cc, hk, w1)
+        A[r * w1 + cc] = (short)ll53_line(B + r * wk, 1, bx0, mx0 + cc, nx);
       __syncthreads();
-      for (int i = threadIdx.x; i < h1 * w1; i += blockDim.x) {
-        const int m = ry0[k + 1] + i / w1, col = i % w1;
-        const short *cp = A + col - ry0[k] * w1;
-        B[i] = (short)ll53([&](int g) { return (int)cp[g * w1]; }, m, ny);
-      }
+      FOR_2D(r, cc, h1, w1)
+        B[r * w1 + cc] = (short)ll53_line(A + cc, w1, by0, my0 + r, ny);
       __syncthreads();
     }
     LL = B;
@@ -178,15 +201,15 @@ __global__ void __launch_bounds__(256) k_ll_residue(LLParams q) {
   uint8_t *pout = q.prediction ? q.prediction + (long long)pair * q.pred_stride + coff : nullptr;
   const int is_I = q.synth && q.types[pair] == 'I';
   const int tw = ox1 - ox0, th = oy1 - oy0;
-  for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
-    const int y = oy0 + i / tw, x = ox0 + i % tw;
-    const int p = LL ? (int)LL[(y - oy0) * ll_w + (x - ox0)] : (int)P[(long long)y * q.p_pitch + x];
+  FOR_2D(r, cc, th, tw) {
+    const int y = oy0 + r, x = ox0 + cc;
+    const int p = LL ? (int)LL[r * ll_w + cc] : (int)P[(long long)y * q.p_pitch + x];
     const int s = in[(long long)y * OW + x];
     int o;
     if (!q.synth) {
-      int r = s - p;
-      r = r < -128 ? -128 : (r > 127 ? 127 : r);
-      o = r + 128;
+      int rr = s - p;
+      rr = rr < -128 ? -128 : (rr > 127 ? 127 : rr);
+      o = rr + 128;
       if (do_hist) {
         atomicAdd(&h_pred[s], 1);
         atomicAdd(&h_res[o], 1);
@@ -211,8 +234,8 @@ __global__ void __launch_bounds__(256) k_ll_residue(LLParams q) {
 }
 
 // shared-memory footprint (shorts) of the row-pass (A) and level (B) buffers
-static void ll_smem(int a, int *sa, int *sb) {
-  int A = 0, B = 0;
+static void ll_smem(int a, int *sa, int *sb, int *su) {
+  int A = 0, B = 0, U = 0;
   for (int c = 0; c < 2; c++) {
     int nlev = a + c;
     if (nlev == 0) continue;
@@ -220,6 +243,7 @@ static void ll_smem(int a, int *sa, int *sb) {
     int ext[4];
     ext[nlev] = T;
     for (int k = nlev; k > 0; k--) ext[k - 1] = 2 * ext[k] + 3;
+    U = U > ext[0] * (ext[0] + 8) ? U : ext[0] * (ext[0] + 8);
     for (int k = 0; k < nlev; k++) {
       A = A > ext[k] * ext[k + 1] ? A : ext[k] * ext[k + 1];
       B = B > ext[k + 1] * ext[k + 1] ? B : ext[k + 1] * ext[k + 1];
@@ -227,14 +251,16 @@ static void ll_smem(int a, int *sa, int *sb) {
   }
   *sa = (A + 7) & ~7;
   *sb = (B + 7) & ~7;
+  *su = (U + 15) & ~15;
 }
 
 void launch_ll_residue(const Launch &L, LLParams q, int npairs) {
   if (npairs <= 0) return;
-  int sa, sb;
-  ll_smem(q.a, &sa, &sb);
+  int sa, sb, su;
+  ll_smem(q.a, &sa, &sb, &su);
   q.smem_a = sa;
-  size_t smem = (size_t)(sa + sb) * sizeof(short);
+  q.smem_b = sb;
+  size_t smem = (size_t)(sa + sb) * sizeof(short) + (size_t)su;
   static size_t s_attr = 0;
   if (smem > 48 * 1024 && smem > s_attr) {
     cudaFuncSetAttribute(k_ll_residue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

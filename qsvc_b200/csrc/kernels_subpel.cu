@@ -111,7 +111,7 @@ void launch_upsample2x(const Launch &L, const uint8_t *in, int n, int m, int pit
                        long long in_slot_stride, uint8_t *out, int pitch_out,
                        long long out_slot_stride, int nslots) {
   if (nslots <= 0) return;
-  int mw = (m + 3) / 4;
+  int mw = (m + 3) >> 2;
   dim3 grid((mw + 255) / 256, n < 1024 ? n : 1024, nslots);
   ProfScope ps_(L, KC_IMG);
   k_upsample2x<<<grid, 256, 0, L.stream>>>(in, n, m, pitch_in, in_slot_stride, out, pitch_out,
@@ -311,8 +311,8 @@ __device__ __forceinline__ int b0_high(const B0View &v, int slot, int y, int x) 
 // Column pass of the level-1 synthesis (5_3.cpp:81-94 on column xp of [0,2Y) x [0,2X)).
 __device__ int t1_even(const B0View &v, int slot, int i, int xp) {
   int low = xp < v.X ? (int)v.p.row(slot, i)[xp] : b0_high(v, slot, i, xp);
-  int h = (i == 0) ? b0_high(v, slot, v.Y, xp) / 2
-                   : (b0_high(v, slot, v.Y + i, xp) + b0_high(v, slot, v.Y + i - 1, xp)) / 4;
+  int h = (i == 0) ? tdiv2(b0_high(v, slot, v.Y, xp))
+                   : tdiv4(b0_high(v, slot, v.Y + i, xp) + b0_high(v, slot, v.Y + i - 1, xp));
   return (short)(low - h);
 }
 __device__ int t1_cell(const B0View &v, int slot, int y, int xp) {
@@ -320,13 +320,13 @@ __device__ int t1_cell(const B0View &v, int slot, int y, int xp) {
   if (!(y & 1)) return t1_even(v, slot, i, xp);
   int e0 = t1_even(v, slot, i, xp);
   int h = b0_high(v, slot, v.Y + i, xp);
-  if (i < v.Y - 1) return (short)(h + (e0 + t1_even(v, slot, i + 1, xp)) / 2);
+  if (i < v.Y - 1) return (short)(h + tdiv2(e0 + t1_even(v, slot, i + 1, xp)));
   return (short)(h + e0);
 }
 // Level-1 image cell inside [0,2Y) x [0,2X) (row pass on top of the column pass).
 __device__ int b1_even(const B0View &v, int slot, int y, int j) {
-  int h = (j == 0) ? t1_cell(v, slot, y, v.X) / 2
-                   : (t1_cell(v, slot, y, v.X + j) + t1_cell(v, slot, y, v.X + j - 1)) / 4;
+  int h = (j == 0) ? tdiv2(t1_cell(v, slot, y, v.X))
+                   : tdiv4(t1_cell(v, slot, y, v.X + j) + t1_cell(v, slot, y, v.X + j - 1));
   return (short)(t1_cell(v, slot, y, j) - h);
 }
 __device__ int b1_inside(const B0View &v, int slot, int y, int x) {
@@ -338,15 +338,15 @@ __device__ int b1_inside(const B0View &v, int slot, int y, int x) {
     const short *r0 = v.p.row(slot, i);
     const short *r1 = v.p.row(slot, i + 1 < v.Y ? i + 1 : i);
     const int jn = j + 1 < v.X ? j + 1 : j;
-    int t0 = (y & 1) ? (short)((r0[j] + r1[j]) / 2) : r0[j];
+    int t0 = (y & 1) ? (short)(tdiv2(r0[j] + r1[j])) : r0[j];
     if (!(x & 1)) return t0;
-    int t1 = (y & 1) ? (short)((r0[jn] + r1[jn]) / 2) : r0[jn];
-    return (short)((t0 + t1) / 2);
+    int t1 = (y & 1) ? (short)(tdiv2(r0[jn] + r1[jn])) : r0[jn];
+    return (short)(tdiv2(t0 + t1));
   }
   if (!(x & 1)) return b1_even(v, slot, y, j);
   int e0 = b1_even(v, slot, y, j);
   int h = t1_cell(v, slot, y, v.X + j);
-  if (j < v.X - 1) return (short)(h + (e0 + b1_even(v, slot, y, j + 1)) / 2);
+  if (j < v.X - 1) return (short)(h + tdiv2(e0 + b1_even(v, slot, y, j + 1)));
   return (short)(h + e0);
 }
 __device__ __forceinline__ int b1_cell(const B0View &v, int slot, int y, int x) {
@@ -383,7 +383,7 @@ __device__ void gen_level1(const B0View &v, int slot, int y0, int x0, int h, int
       const short *tl = TL + (y - ya) * nj - j0;
       const short *th = TH + (y - ya) * nh - hj0;
       auto even = [&](int jj) -> int {
-        int hh = (jj == 0) ? th[0] / 2 : (th[jj] + th[jj - 1]) / 4;
+        int hh = (jj == 0) ? tdiv2(th[0]) : tdiv4(th[jj] + th[jj - 1]);
         return (short)(tl[jj] - hh);
       };
       const int j = x >> 1;
@@ -391,7 +391,7 @@ __device__ void gen_level1(const B0View &v, int slot, int y0, int x0, int h, int
         val = even(j);
       } else {
         int e0 = even(j);
-        val = (j < v.X - 1) ? (short)(th[j] + (e0 + even(j + 1)) / 2) : (short)(th[j] + e0);
+        val = (j < v.X - 1) ? (short)(th[j] + tdiv2(e0 + even(j + 1))) : (short)(th[j] + e0);
       }
     } else {
       val = b0_cell(v, slot, y, x);
@@ -426,14 +426,14 @@ __device__ void gen_window(const B0View &v, int slot, int l, int y0, int x0, int
         int a = col[(i0 - ty0) * tw];
         if (!(yy & 1)) return a;
         if (yy == Y2 - 1) return a;
-        return (short)((a + col[(i0 + 1 - ty0) * tw]) / 2);
+        return (short)(tdiv2(a + col[(i0 + 1 - ty0) * tw]));
       };
       int j0 = x >> 1;
       int a = T(y, j0);
       if (!(x & 1) || x == X2 - 1)
         val = a;
       else
-        val = (short)((a + T(y, j0 + 1)) / 2);
+        val = (short)(tdiv2(a + T(y, j0 + 1)));
     } else {
       val = b0_cell(v, slot, y, x);
     }

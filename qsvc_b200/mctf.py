@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AnalyzeParams, check
+from ._lib import AnalyzeParams, LevelOut, check
 from .yuv import frame_bytes
 
 SEARCH_RANGE_MAX = 128  # analyze.py:26
@@ -66,9 +66,15 @@ class Context:
         if not self._h:
             raise _lib.QsvcError(_lib.QSVC_ECUDA, _lib.last_error())
         self.device = device
+        self._pinned = []
+        self._out_cache = {}
 
     def close(self):
         if getattr(self, "_h", None):
+            self._out_cache = {}
+            for ptr in self._pinned:
+                self._L.qsvc_host_free(ptr)
+            self._pinned = []
             self._L.qsvc_destroy(self._h)
             self._h = None
 
@@ -233,24 +239,61 @@ class Context:
         return dict(high=high, motion=mv, motion_filtered=mvf, frame_types=types.raw[:n_pairs],
                     low=low)
 
+    def host_alloc(self, shape, dtype=np.uint8):
+        """numpy array in pinned host memory (freed with the context)."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = self._L.qsvc_host_alloc(max(nbytes, 1))
+        if not ptr:
+            raise _lib.QsvcError(_lib.QSVC_ENOMEM, _lib.last_error())
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
     def analyze(self, low0, X, Y, GOPs, TRLs, block_size=32, search_range=4, subpixel_accuracy=0,
                 update_factor=0.0, always_B=0, block_overlaping=0, border_size=0,
-                block_size_min=32, first_global=True):
-        """analyze.py equivalent on arrays: returns {file name: payload}."""
+                block_size_min=32, first_global=True, reuse_buffers=False):
+        """analyze.py equivalent on arrays: returns {file name: payload}.
+
+        One C-ABI call (qsvc_analyze): upload, every temporal level, and the download of
+        each level's results overlapped with the next level's compute.  With
+        reuse_buffers=True the returned arrays are views of pinned buffers owned by the
+        context and are overwritten by the next call with the same geometry."""
         low0 = np.ascontiguousarray(low0, np.uint8)
-        assert low0.shape[0] == GOPs * gop_size(TRLs) + 1
-        self.resident_load(low0, X, Y)
-        self.resident_analyze(TRLs, block_size, search_range, subpixel_accuracy, update_factor,
-                              always_B, block_overlaping, border_size, block_size_min, first_global)
-        out = {}
-        for s in level_schedule(GOPs, TRLs, block_size, search_range, block_size_min):
-            r = self.resident_fetch(s["t"], s["pairs"], s["block_size"])
+        assert low0.shape == (GOPs * gop_size(TRLs) + 1, frame_bytes(X, Y))
+        sched = level_schedule(GOPs, TRLs, block_size, search_range, block_size_min)
+        key = (X, Y, GOPs, TRLs, block_size, block_size_min)
+        bufs = self._out_cache.get(key)
+        if bufs is None:
+            bufs = {}
+            fb = frame_bytes(X, Y)
+            for s in sched:
+                t, n, b = s["t"], s["pairs"], s["block_size"]
+                bufs[f"high_{t}"] = self.host_alloc((n, fb))
+                bufs[f"motion_{t}"] = self.host_alloc((n, 4, Y // b, X // b), np.int16)
+                bufs[f"motion_filtered_{t}"] = self.host_alloc((n, 4, Y // b, X // b), np.int16)
+                bufs[f"low_{t}"] = self.host_alloc((n + 1, fb))
+            self._out_cache[key] = bufs
+        outs = (LevelOut * TRLs)()
+        types = {}
+        for s in sched:
             t = s["t"]
-            out[f"high_{t}"] = r["high"]
-            out[f"motion_{t}"] = r["motion"]
-            out[f"motion_filtered_{t}"] = r["motion_filtered"]
-            out[f"frame_types_{t}"] = r["frame_types"]
-            out[f"low_{t}"] = r["low"]
+            types[t] = C.create_string_buffer(max(s["pairs"], 1))
+            outs[t].high = _u8(bufs[f"high_{t}"])
+            outs[t].motion = _i16(bufs[f"motion_{t}"])
+            outs[t].motion_filtered = _i16(bufs[f"motion_filtered_{t}"])
+            outs[t].frame_types = C.cast(types[t], C.c_void_p)
+            outs[t].low = _u8(bufs[f"low_{t}"])
+        p = self._params(X, Y, TRLs, block_size, search_range, subpixel_accuracy, update_factor,
+                         always_B, block_overlaping, border_size, block_size_min, first_global)
+        check(self._L.qsvc_analyze(self._h, C.byref(p), _u8(low0), low0.shape[0], outs))
+        self._geom = (X, Y, low0.shape[0])
+        out = {}
+        for s in sched:
+            t = s["t"]
+            for name in ("high", "motion", "motion_filtered", "low"):
+                a = bufs[f"{name}_{t}"]
+                out[f"{name}_{t}"] = a if reuse_buffers else a.copy()
+            out[f"frame_types_{t}"] = types[t].raw[: s["pairs"]]
         return out
 
     def synthesize(self, subbands, X, Y, GOPs, TRLs, block_size=16, search_range=4,
