@@ -68,6 +68,7 @@ struct qsvc_ctx {
   long long launches = 0;
   Profiler prof;
   std::vector<PoolBlock> pool;
+  int tma_mode = 1;  // 0: plain loads in the sub-pixel fast path (env QSVC_TMA=0)
   int mc_mode = 0;  // same three values for the decorrelate / correlate path
   int me_mode = 0;  // 0: automatic, 1: literal (materialised) path only, 2: fused path required
   size_t me_budget = (size_t)40 << 30;  // bytes of HBM for the ME image planes of one chunk
@@ -371,6 +372,11 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       q.lim = sr << a;
       q.slow_count = d_slow;
       q.slow_list = d_slow + 1;
+      q.v_rows_per_slot = (int)(vbytes[l] / pitch[l]);
+      q.use_tma = (c->tma_mode != 0 &&
+                   subpel_make_tensor_maps(v[l], pitch[l], (long long)q.v_rows_per_slot * nslots, bs << l, q.tm_p, q.tm_r))
+                      ? 1
+                      : 0;
       launch_subpel(Lh, q, bs << l, m);
       j++;
     }
@@ -759,6 +765,7 @@ qsvc_ctx *qsvc_create(int device) {
   }
   if (const char *e = getenv("QSVC_ME_MODE")) c->me_mode = atoi(e);
   if (const char *e = getenv("QSVC_MC_MODE")) c->mc_mode = atoi(e);
+  if (const char *e = getenv("QSVC_TMA")) c->tma_mode = atoi(e);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->me_budget = std::min<size_t>((size_t)64 << 30, free_b / 3);
   return c;
@@ -832,6 +839,7 @@ int qsvc_int_peak(qsvc_ctx *c, double *u8_sad_ops_per_s, double *i32_sad_ops_per
   }
   return QSVC_OK;
 }
+int qsvc_debug_tma_timeouts(void) { return subpel_tma_timeouts(); }
 int qsvc_set_mc_mode(qsvc_ctx *c, int mode) {
   if (!c || mode < 0 || mode > 2) return fail(QSVC_EINVAL, "bad mc_mode");
   c->mc_mode = mode;

@@ -91,8 +91,15 @@ struct SubpelParams {
   int lim;             // vector clamp, search_range << a
   int *slow_count;
   int *slow_list;
+  int v_rows_per_slot;   // v_slot_stride / v_pitch
+  int use_tma;           // tm_p / tm_r hold valid CUtensorMap objects
+  alignas(64) unsigned char tm_p[128];
+  alignas(64) unsigned char tm_r[128];
 };
+bool subpel_make_tensor_maps(const uint8_t *v, int pitch, long long total_rows, int W, void *tm_p,
+                             void *tm_r);
 bool subpel_supported(int W);
+int subpel_tma_timeouts();
 void launch_subpel(const Launch &L, const SubpelParams &q, int W, int npairs);
 void launch_plane_to_u8(const Launch &L, Plane src, int slot0, int nslots, int Y, int X,
                         uint8_t *dst, long long dst_slot_stride, int pitch, uint8_t *tile_bad,

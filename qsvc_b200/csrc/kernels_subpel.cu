@@ -20,6 +20,8 @@
 //  * every other block is queued and handled by the EXACT path, which rebuilds
 //    the int16 windows from B0 with the literal synthesis formulas (including
 //    the high-band reads) and accumulates with __sad.
+#include <cuda.h>
+
 #include "kernels.cuh"
 
 #define COUNT(L) (++*(L).counter)
@@ -283,6 +285,185 @@ __global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_fast(SubpelParams 
   if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
 }
 
+__device__ int g_tma_timeouts = 0;
+int subpel_tma_timeouts() {
+  int v = -1;
+  cudaMemcpyFromSymbol(&v, g_tma_timeouts, sizeof(int));
+  return v;
+}
+
+// ---- fast path, TMA variant ----
+// The predicted block and the two (W+2)-row windows are fetched by three
+// cp.async.bulk.tensor.2d loads (UTMALDG) at element coordinates, so the windows
+// arrive already aligned to their first column: the three horizontal shifts are
+// byte offsets 0/1/2 of two adjacent words.  Half of the threads take PREV, the
+// other half NEXT; each thread owns one 32-bit word column of 16 block rows and
+// accumulates the nine window shifts with VABSDIFF4.U8.ACC.
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, void *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int W>
+__global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_tma(SubpelParams q,
+                                                                const __grid_constant__ CUtensorMap tmP,
+                                                                const __grid_constant__ CUtensorMap tmR) {
+  constexpr int WPR = W / 4;            // P words per row
+  constexpr int RPT = 8;                // block rows per thread
+  constexpr int NT = WPR * (W / RPT);
+  constexpr int TP = (W + 32) / 4;      // TMA landing pitch in words (box inner dim W + 32 bytes)
+  constexpr int TBYTES = (W + 32) * (W + 2);
+  constexpr int TB = (TBYTES + 127) & ~127;
+  constexpr int RS = WPR + 2;           // re-aligned window pitch in words (8 * RS % 32 == 16)
+  constexpr int NWARP = (NT + 31) / 32;
+  __shared__ __align__(128) unsigned char sP[W * W];
+  __shared__ __align__(128) unsigned char sT[2][TB];
+  __shared__ unsigned sR[2][(W + 2) * RS];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ int s_err[NWARP][18];
+  __shared__ int s_fin[18];
+
+  const int bx = blockIdx.x, by = blockIdx.y, pair = blockIdx.z;
+  const int l = q.l;
+  const int Yl = q.Y << l, Xl = q.X << l;
+  short c[4];
+  subpel_centre(q, pair, by, bx, c);
+  const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
+  const int py0 = by * W, px0 = bx * W;
+  const int wy[2] = {py0 + c[MV_PREV_Y] - 1, py0 + c[MV_NEXT_Y] - 1};
+  const int wx[2] = {px0 + c[MV_PREV_X] - 1, px0 + c[MV_NEXT_X] - 1};
+  const int clean = (2 * q.B + 2) << (l - 1);
+  bool fast = true;
+#pragma unroll
+  for (int d = 0; d < 2; d++)
+    fast = fast && wy[d] >= clean && wx[d] >= clean && wy[d] + W + 2 <= Yl && wx[d] + W + 2 <= Xl;
+  if (fast) {
+    int bad = 0;
+    for (int img = 0; img < 3; img++) {
+      const int slot = img == 0 ? r0s : (img == 1 ? r1s : ps);
+      const int y0 = img == 2 ? py0 : wy[img], x0 = img == 2 ? px0 : wx[img];
+      const int span = img == 2 ? W : W + 2;
+      const int ty0 = (y0 >> l) >> 4, ty1 = min((((y0 + span - 1) >> l) + 1), q.Y - 1) >> 4;
+      const int tx0 = (x0 >> l) >> 4, tx1 = min((((x0 + span - 1) >> l) + 1), q.X - 1) >> 4;
+      const int nty = ty1 - ty0 + 1, ntx = tx1 - tx0 + 1;
+      const uint8_t *map = q.tile_bad + (long long)slot * q.tiles_per_slot;
+      for (int i = threadIdx.x; i < nty * ntx; i += NT)
+        bad |= map[(ty0 + i / ntx) * q.tiles_x + tx0 + i % ntx];
+    }
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    fast = !__syncthreads_or(bad);
+  }
+  if (!fast) {
+    if (threadIdx.x == 0) {
+      int idx = atomicAdd(q.slow_count, 1);
+      q.slow_list[idx] = (pair * q.BY + by) * q.BX + bx;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    // TMA needs 16-byte aligned inner coordinates: fetch from wx & ~15, W + 32 bytes wide
+    // (bytes beyond the plane pitch are zero-filled and never used)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)),
+                 "r"(W * W + 2 * TBYTES)
+                 : "memory");
+    tma_load_2d(sP, &tmP, px0, ps * q.v_rows_per_slot + py0, &bar);
+    tma_load_2d(sT[0], &tmR, wx[0] & ~15, r0s * q.v_rows_per_slot + wy[0], &bar);
+    tma_load_2d(sT[1], &tmR, wx[1] & ~15, r1s * q.v_rows_per_slot + wy[1], &bar);
+  }
+  {
+    unsigned done = 0;
+    const unsigned addr = smem_u32(&bar);
+    unsigned long long t0 = 0;
+    for (int spin = 0; !done; spin++) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(addr)
+          : "memory");
+      if (!done && (spin & 1023) == 1023) {  // never hang the GPU: give up after 50 ms
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 50000000ull) { atomicAdd(&g_tma_timeouts, 1); break; }
+      }
+    }
+  }
+  // re-align the windows so that window column 0 sits on a word boundary
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+    const unsigned *T4 = reinterpret_cast<const unsigned *>(sT[d]) + ((wx[d] & 15) >> 2);
+    const int sa = 8 * (wx[d] & 3);
+    for (int i = threadIdx.x; i < (W + 2) * (WPR + 1); i += NT) {
+      const int y = i / (WPR + 1), w = i % (WPR + 1);
+      sR[d][y * RS + w] = __funnelshift_r(T4[y * TP + w], T4[y * TP + w + 1], sa);
+    }
+  }
+  __syncthreads();
+
+  const int j = threadIdx.x % WPR, g = threadIdx.x / WPR;
+  unsigned p[RPT];
+  {
+    const unsigned *P4 = reinterpret_cast<const unsigned *>(sP) + (g * RPT) * WPR + j;
+#pragma unroll
+    for (int r = 0; r < RPT; r++) p[r] = P4[r * WPR];
+  }
+  unsigned acc[18];
+#pragma unroll
+  for (int k = 0; k < 18; k++) acc[k] = 0;
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+    const unsigned *R4 = sR[d] + (g * RPT) * RS + j;
+#pragma unroll
+    for (int rr = 0; rr < RPT + 2; rr++) {
+      const unsigned w0 = R4[rr * RS], w1 = R4[rr * RS + 1];
+      unsigned sh[3];
+      sh[0] = w0;                           // window column shift -1
+      sh[1] = __funnelshift_r(w0, w1, 8);   //                      0
+      sh[2] = __funnelshift_r(w0, w1, 16);  //                     +1
+#pragma unroll
+      for (int wdy = -1; wdy <= 1; wdy++) {
+        const int r = rr - 1 - wdy;  // block row paired with window row rr under vertical shift wdy
+        if (r >= 0 && r < RPT) {
+#pragma unroll
+          for (int wdx = -1; wdx <= 1; wdx++) {
+            const int a = d * 9 + (wdy + 1) * 3 + wdx + 1;
+            acc[a] = __vsadu4(p[r], sh[wdx + 1]) + acc[a];
+          }
+        }
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 18; k++) {
+    unsigned v = __reduce_add_sync(0xffffffffu, acc[k]);
+    if (lane == 0) s_err[warp][k] = (int)v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 18) {
+    // candidate k of direction dd tests the window shift sgn * (dy, dx)
+    constexpr int DY[9] = {-1, -1, 1, 1, -1, 1, 0, 0, 0};
+    constexpr int DX[9] = {-1, 1, -1, 1, 0, 0, 1, -1, 0};
+    const int dd = threadIdx.x / 9, k = threadIdx.x % 9;
+    const int sgn = dd ? -1 : 1;
+    const int slot = dd * 9 + (sgn * DY[k] + 1) * 3 + sgn * DX[k] + 1;
+    int e = 0;
+    for (int w = 0; w < NWARP; w++) e += s_err[w][slot];
+    s_fin[threadIdx.x] = e;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
+}
+
 // ------------------------------------------------------------ exact path
 
 struct B0View {
@@ -506,7 +687,11 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
   dim3 grid(q.BX, q.BY, npairs);
   {
     ProfScope ps_(L, KC_SEARCH);
-    k_subpel_fast<W><<<grid, NT, 0, L.stream>>>(q);
+    if (q.use_tma)
+      k_subpel_tma<W><<<grid, NT, 0, L.stream>>>(q, *reinterpret_cast<const CUtensorMap *>(q.tm_p),
+                                                       *reinterpret_cast<const CUtensorMap *>(q.tm_r));
+    else
+      k_subpel_fast<W><<<grid, NT, 0, L.stream>>>(q);
     COUNT(L);
   }
   B0View v;
@@ -540,4 +725,41 @@ void launch_subpel(const Launch &L, const SubpelParams &q, int W, int npairs) {
     launch_subpel_w<32>(L, q, npairs);
   else
     launch_subpel_w<64>(L, q, npairs);
+}
+
+// Tensor maps over the V_l planes of all slots seen as one tall 2-D u8 tensor
+// (pitch bytes wide, nslots * rows_per_slot rows): box W x W for the predicted block
+// and (W+32) x (W+2) for the windows (fetched from a 16-byte aligned column).  Encoded through the driver entry point so the
+// library does not link against libcuda.
+bool subpel_make_tensor_maps(const uint8_t *v, int pitch, long long total_rows, int W, void *tm_p,
+                             void *tm_r) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = (encode_fn)fn;
+    else
+      cudaGetLastError();
+  }
+  if (!encode) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)total_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+  cuuint32_t estr[2] = {1, 1};
+  cuuint32_t boxp[2] = {(cuuint32_t)W, (cuuint32_t)W};
+  cuuint32_t boxr[2] = {(cuuint32_t)(W + 32), (cuuint32_t)(W + 2)};
+  CUresult a = encode((CUtensorMap *)tm_p, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)v, gdim, gstride, boxp, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult b = encode((CUtensorMap *)tm_r, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)v, gdim, gstride, boxr, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return a == CUDA_SUCCESS && b == CUDA_SUCCESS;
 }

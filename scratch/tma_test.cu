@@ -1,0 +1,60 @@
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <vector>
+#include <stdlib.h>
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int BW, int BH>
+__global__ void k(const __grid_constant__ CUtensorMap tm, uint8_t *out, int x, int y, int mode) {
+  __shared__ __align__(128) unsigned char buf[BW * BH];
+  __shared__ __align__(8) unsigned long long bar;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (mode == 0) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    } else {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(BW * BH) : "memory");
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                   ::"r"(smem_u32(buf)), "l"(&tm), "r"(x), "r"(y), "r"(smem_u32(&bar)) : "memory");
+    }
+  }
+  unsigned done = 0; int spin = 0;
+  while (!done && spin < 100000) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    spin++;
+  }
+  for (int i = threadIdx.x; i < BW * BH; i += blockDim.x) out[i] = done ? buf[i] : 0xEE;
+}
+int main(int argc, char **argv) {
+  int bw = atoi(argv[1]), bh = atoi(argv[2]), cx = atoi(argv[3]), cy = atoi(argv[4]);
+  const int pitch = 1424, rows = 300;
+  std::vector<uint8_t> h(pitch * rows);
+  for (int i = 0; i < pitch * rows; i++) h[i] = (uint8_t)((i % pitch) * 7 + (i / pitch) * 13);
+  uint8_t *d, *o; cudaMalloc(&d, pitch * rows); cudaMalloc(&o, 80 * 66);
+  cudaMemcpy(d, h.data(), pitch * rows, cudaMemcpyHostToDevice);
+  void *fn = nullptr; cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  printf("entry %d %d %p\n", (int)e, (int)q, fn);
+  typedef CUresult (*enc_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  CUtensorMap tm;
+  cuuint64_t gdim[2] = {pitch, rows}; cuuint64_t gs[1] = {pitch}; cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh}; cuuint32_t es[2] = {1, 1};
+  CUresult r = ((enc_t)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, gdim, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  printf("encode %d\n", (int)r);
+  for (int mode = 0; mode < 2; mode++) {
+    if (bw == 80) k<80, 66><<<1, 128>>>(tm, o, cx, cy, mode); else k<64, 64><<<1, 128>>>(tm, o, cx, cy, mode);
+    e = cudaDeviceSynchronize();
+    printf("mode %d: %s\n", mode, cudaGetErrorString(e));
+    if (e != cudaSuccess) return 1;
+    std::vector<uint8_t> res(80 * 66); cudaMemcpy(res.data(), o, 80 * 66, cudaMemcpyDeviceToHost);
+    int bad = 0;
+    if (mode == 1) for (int yy = 0; yy < bh; yy++) for (int xx = 0; xx < bw; xx++) bad += res[yy * bw + xx] != h[(cy + yy) * pitch + cx + xx];
+    printf("  first bytes %d %d %d, mismatches %d\n", res[0], res[1], res[80], bad);
+  }
+  return 0;
+}
