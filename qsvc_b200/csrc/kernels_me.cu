@@ -109,8 +109,111 @@ __global__ void __launch_bounds__(128) k_search(SearchParams q) {
   }
 }
 
+// Specialisation for 16x16 blocks without block border (every shipped configuration):
+// one warp per block, four blocks per CTA.  Lane (y, xh) owns 8 pixels of block row y;
+// the predicted pixels stay in registers, the two 18x18 windows are staged per warp in
+// shared memory, candidate offsets are compile-time constants and the eighteen sums are
+// reduced with REDUX.
+__global__ void __launch_bounds__(128) k_search16(SearchParams q) {
+  constexpr int RP = 20;  // window row pitch in shorts
+  __shared__ __align__(8) short sR[4][2][18 * RP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bx = blockIdx.x * 4 + warp, by = blockIdx.y, pair = blockIdx.z;
+  if (bx >= q.nbx) return;
+  const long long plane = (long long)q.BY * q.BX;
+  const short *mvi = q.mv_in + (long long)pair * 4 * plane;
+  short *mvo = q.mv_out + (long long)pair * 4 * plane;
+  short c[4];
+  if (q.mode == ME_INIT) {
+    c[0] = c[1] = c[2] = c[3] = 0;
+  } else {
+    int src = (q.mode == ME_DESCEND) ? (by >> 1) * q.BX + (bx >> 1) : by * q.BX + bx;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      short v = mvi[k * plane + src];
+      v = (short)(v * 2);
+      if (v > q.lim) v = (short)q.lim;
+      if (v < -q.lim) v = (short)(-q.lim);
+      c[k] = v;
+    }
+  }
+  const int r0 = q.slots[3 * pair], r1 = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
+  const int luby = by * 16, lubx = bx * 16;
+  const int y = lane >> 1, xh = (lane & 1) * 8;
+  int p[8];
+  {
+    const short *row = q.img.row(ps, luby + y) + lubx + xh;
+#pragma unroll
+    for (int i = 0; i < 8; i++) p[i] = row[i];
+  }
+  if (lane < 18) {
+    const short *row0 = q.img.row(r0, luby + c[MV_PREV_Y] - 1 + lane) + lubx + c[MV_PREV_X] - 1;
+    const short *row1 = q.img.row(r1, luby + c[MV_NEXT_Y] - 1 + lane) + lubx + c[MV_NEXT_X] - 1;
+    short *d0 = sR[warp][0] + lane * RP, *d1 = sR[warp][1] + lane * RP;
+#pragma unroll
+    for (int i = 0; i < 18; i++) {
+      d0[i] = row0[i];
+      d1[i] = row1[i];
+    }
+  }
+  __syncwarp();
+  unsigned acc[18];  // [direction][window row shift 0..2][window column shift 0..2]
+#pragma unroll
+  for (int k = 0; k < 18; k++) acc[k] = 0;
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+#pragma unroll
+    for (int wr = 0; wr < 3; wr++) {
+      const short *a = sR[warp][d] + (y + wr) * RP + xh;
+      int v[10];
+#pragma unroll
+      for (int i = 0; i < 10; i++) v[i] = a[i];
+#pragma unroll
+      for (int wc = 0; wc < 3; wc++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[d * 9 + wr * 3 + wc] = __sad(p[i], v[i + wc], acc[d * 9 + wr * 3 + wc]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 18; k++) acc[k] = __reduce_add_sync(0xffffffffu, acc[k]);
+  if (lane < 2) {
+    constexpr int DY[9] = {-1, -1, 1, 1, -1, 1, 0, 0, 0};
+    constexpr int DX[9] = {-1, 1, -1, 1, 0, 0, 1, -1, 0};
+    const int d = lane, sgn = d ? -1 : 1;
+    int best = 0, min_error = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      // candidate k looks at window shift (1 + sgn*dy, 1 + sgn*dx)
+      int e0 = (int)acc[(1 + DY[k]) * 3 + 1 + DX[k]];        // PREV: centre + delta
+      int e1 = (int)acc[9 + (1 - DY[k]) * 3 + 1 - DX[k]];    // NEXT: centre - delta
+      int e = d ? e1 : e0;
+      if (k == 0 || e <= min_error) {
+        min_error = e;
+        best = k;
+      }
+    }
+    int by_best = DY[0], bx_best = DX[0];
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+      if (k == best) {
+        by_best = DY[k];
+        bx_best = DX[k];
+      }
+    long long dst = (long long)by * q.BX + bx;
+    mvo[(2 * d) * plane + dst] = (short)(c[2 * d] + sgn * bx_best);
+    mvo[(2 * d + 1) * plane + dst] = (short)(c[2 * d + 1] + sgn * by_best);
+  }
+}
+
 void launch_search(const Launch &L, const SearchParams &q, int npairs) {
   if (npairs <= 0 || q.nby <= 0 || q.nbx <= 0) return;
+  if (q.bs == 16 && q.bd == 0) {
+    dim3 grid((q.nbx + 3) / 4, q.nby, npairs);
+    ProfScope ps_(L, KC_SEARCH);
+    k_search16<<<grid, 128, 0, L.stream>>>(q);
+    COUNT(L);
+    return;
+  }
   int W = q.bs + 2 * q.bd, RW = W + 2;
   size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW) * sizeof(short);
   static size_t s_attr = 0;
