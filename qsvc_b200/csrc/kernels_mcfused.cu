@@ -103,9 +103,10 @@ __device__ __forceinline__ int hh53(F S, int i, int n) {
 }
 
 // Flattened 2-D loop over h x w elements by 256 threads without a division per element.
-#define FOR_2D(r, c, h, w)                                                                  \
-  for (int i_ = threadIdx.x, r = i_ / (w), c = i_ - r * (w), dc_ = 256 % (w), dr_ = 256 / (w); \
-       i_ < (h) * (w); i_ += 256, c += dc_, r += dr_, r += (c >= (w)), c -= (c >= (w)) ? (w) : 0)
+#define LL_NT 512
+#define FOR_2D(r, c, h, w)                                                                      \
+  for (int i_ = threadIdx.x, r = i_ / (w), c = i_ - r * (w), dc_ = LL_NT % (w), dr_ = LL_NT / (w); \
+       i_ < (h) * (w); i_ += LL_NT, c += dc_, r += dr_, r += (c >= (w)), c -= (c >= (w)) ? (w) : 0)
 
 // l[m] from a line reached through s[g * st] (g = global index minus `base`), line
 // length n.  Branch-free: out-of-line taps of the first / last sample are re-pointed at
@@ -123,10 +124,73 @@ __device__ __forceinline__ int ll53_line(const T *s, int st, int base, int m, in
   return (short)(s0 + tdiv4(hs));
 }
 
+// Sliding LL pass along one line: outputs l[m0 .. m0+cnt) of a line of n samples read
+// through src[(g - base) * sst] (g = global sample index) into dst[k * dst_st].  Each step
+// loads two new samples and reuses s[2m] and h[m-1] from the previous step.
+__device__ __forceinline__ void ll53_slide(const short *src, int sst, int base, int n, int m0, int cnt,
+                                           short *dst, int dst_st) {
+  if (cnt <= 0) return;
+  const int half = n >> 1;
+  const short *p = src + (2 * m0 - base) * sst;
+  int s0 = p[0];
+  int hprev = 0;
+  if (m0 > 0) hprev = (short)(p[-sst] - tdiv2(p[-2 * sst] + s0));
+  for (int k = 0; k < cnt; k++) {
+    const int m = m0 + k;
+    const int s1 = p[sst];
+    int hm, s2 = 0;
+    if (m == half - 1) {
+      hm = (short)(s1 - s0);
+    } else {
+      s2 = p[2 * sst];
+      hm = (short)(s1 - tdiv2(s0 + s2));
+    }
+    const int hs = (m == 0) ? 2 * hm : hm + hprev;
+    dst[k * dst_st] = (short)(s0 + tdiv4(hs));
+    hprev = hm;
+    s0 = s2;
+    p += 2 * sst;
+  }
+}
+
+// Level 0 -> 1 row pass on bytes: one thread produces the four outputs m = 4g+1 .. 4g+4
+// of one tile row from the 11 bytes [8g, 8g+11) held in three aligned words.
+__device__ __forceinline__ void ll53_row_u8x4(const unsigned *row_words, int xs, int nwords, int g,
+                                              int n, int mx0, int mx1, short *dst /* row, index m - mx0 */) {
+  const int half = n >> 1;
+  // word index of byte 8g inside the staged row (xs is a multiple of 8)
+  const int wi = (8 * g - xs) >> 2;
+  unsigned w[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    int idx = wi + k;
+    idx = idx < 0 ? 0 : (idx >= nwords ? nwords - 1 : idx);
+    w[k] = row_words[idx];
+  }
+  int s[11];
+#pragma unroll
+  for (int k = 0; k < 11; k++) s[k] = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
+  // h_rel[j] = h[4g + j], j = 0..4 (bytes are non-negative: /2 is a shift)
+  int h[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const int gi = 4 * g + j;
+    h[j] = (gi == half - 1) ? s[2 * j + 1] - s[2 * j] : s[2 * j + 1] - ((s[2 * j] + s[2 * j + 2]) >> 1);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int m = 4 * g + 1 + i;
+    if (m >= mx0 && m < mx1 && m > 0) {
+      const int hs = h[i + 1] + h[i];  // m >= 1 here: l[m] = s[2m] + (h[m] + h[m-1]) / 4
+      dst[m - mx0] = (short)(s[2 * i + 2] + tdiv4(hs));
+    }
+  }
+}
+
 // Output tile [oy0,oy0+T) x [ox0,ox0+T) of the level-nlev LL band of one P_a plane,
 // then residue (analysis) or reconstruction (synthesis) of that tile.
 // grid (ceil(X/32), ceil(Y/32), pairs * 3)
-__global__ void __launch_bounds__(256) k_ll_residue(LLParams q) {
+__global__ void __launch_bounds__(LL_NT) k_ll_residue(LLParams q) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ int h_pred[256], h_res[256];
   const int pair = blockIdx.z / 3, c = blockIdx.z % 3;
@@ -152,31 +216,40 @@ __global__ void __launch_bounds__(256) k_ll_residue(LLParams q) {
   }
   short *A = reinterpret_cast<short *>(smraw);  // row-pass output
   short *B = A + q.smem_a;                      // column-pass output (level image)
-  uint8_t *U = reinterpret_cast<uint8_t *>(B + q.smem_b);  // level-0 byte tile
   const short *LL = nullptr;
   int ll_w = 0;
   if (nlev > 0) {
-    // stage the level-0 byte tile with aligned 32-bit loads
-    const int xs = rx0[0] & ~3;
-    const int uw = (rx1[0] - xs + 3) >> 2;  // words per row
-    const int up = uw << 2;                 // byte pitch of U
-    {
-      const int h0 = ry1[0] - ry0[0];
-      unsigned *U4 = reinterpret_cast<unsigned *>(U);
-      FOR_2D(r, w, h0, uw)
-        U4[r * uw + w] = *reinterpret_cast<const unsigned *>(P + (long long)(ry0[0] + r) * q.p_pitch + xs + 4 * w);
-      __syncthreads();
-    }
+    // level-0 bytes are read straight from the plane (aligned 32-bit loads through L1)
+    const int xs = rx0[0] & ~7;
+    const int uw = (rx1[0] - xs + 3) >> 2;  // words per tile row
     // level 0 -> 1
     {
       const int h0 = ry1[0] - ry0[0], w1 = rx1[1] - rx0[1], h1 = ry1[1] - ry0[1];
       const int nx = q.X << q.a, ny = q.Y << q.a;
       const int mx0 = rx0[1], my0 = ry0[1];
-      FOR_2D(r, cc, h0, w1)
-        A[r * w1 + cc] = (short)ll53_line(U + r * up, 1, xs, mx0 + cc, nx);
+      {
+        // row pass: groups of four outputs m = 4g+1 .. 4g+4; m = 0 (first column of the
+        // picture) is outside every group and handled by the generic tap code
+        const int mx1 = rx1[1];
+        const int g_lo = (max(mx0, 1) - 1) >> 2, g_hi = (mx1 - 2) >> 2;
+        const int ng = g_hi - g_lo + 1;
+        FOR_2D(r, gg, h0, ng)
+          ll53_row_u8x4(reinterpret_cast<const unsigned *>(P + (long long)(ry0[0] + r) * q.p_pitch + xs), xs, uw,
+                        g_lo + gg, nx, mx0, mx1, A + r * w1);
+        if (mx0 == 0)
+          for (int r = threadIdx.x; r < h0; r += LL_NT)
+            A[r * w1] = (short)ll53_line(P + (long long)(ry0[0] + r) * q.p_pitch, 1, 0, 0, nx);
+      }
       __syncthreads();
-      FOR_2D(r, cc, h1, w1)
-        B[r * w1 + cc] = (short)ll53_line(A + cc, w1, ry0[0], my0 + r, ny);
+      {
+        // column pass: thread = (column, row segment), sliding down the column
+        const int nseg = max(1, LL_NT / w1), per = (h1 + nseg - 1) / nseg;
+        const int col = threadIdx.x % w1, seg = threadIdx.x / w1;
+        if (seg < nseg) {
+          const int k0 = seg * per, cnt = min(per, h1 - k0);
+          ll53_slide(A + col, w1, ry0[0], ny, my0 + k0, cnt, B + k0 * w1 + col, w1);
+        }
+      }
       __syncthreads();
     }
     for (int k = 1; k < nlev; k++) {
@@ -184,11 +257,24 @@ __global__ void __launch_bounds__(256) k_ll_residue(LLParams q) {
       const int w1 = rx1[k + 1] - rx0[k + 1], h1 = ry1[k + 1] - ry0[k + 1];
       const int nx = (q.X << q.a) >> k, ny = (q.Y << q.a) >> k;
       const int mx0 = rx0[k + 1], my0 = ry0[k + 1], bx0 = rx0[k], by0 = ry0[k];
-      FOR_2D(r, cc, hk, w1)
-        A[r * w1 + cc] = (short)ll53_line(B + r * wk, 1, bx0, mx0 + cc, nx);
+      {
+        // row pass: thread = (row, column segment), sliding along the row
+        const int nseg = max(1, LL_NT / hk), per = (w1 + nseg - 1) / nseg;
+        const int row = threadIdx.x % hk, seg = threadIdx.x / hk;
+        if (seg < nseg) {
+          const int k0 = seg * per, cnt = min(per, w1 - k0);
+          ll53_slide(B + row * wk, 1, bx0, nx, mx0 + k0, cnt, A + row * w1 + k0, 1);
+        }
+      }
       __syncthreads();
-      FOR_2D(r, cc, h1, w1)
-        B[r * w1 + cc] = (short)ll53_line(A + cc, w1, by0, my0 + r, ny);
+      {
+        const int nseg = max(1, LL_NT / w1), per = (h1 + nseg - 1) / nseg;
+        const int col = threadIdx.x % w1, seg = threadIdx.x / w1;
+        if (seg < nseg) {
+          const int k0 = seg * per, cnt = min(per, h1 - k0);
+          ll53_slide(A + col, w1, by0, ny, my0 + k0, cnt, B + k0 * w1 + col, w1);
+        }
+      }
       __syncthreads();
     }
     LL = B;
@@ -243,7 +329,7 @@ static void ll_smem(int a, int *sa, int *sb, int *su) {
     int ext[4];
     ext[nlev] = T;
     for (int k = nlev; k > 0; k--) ext[k - 1] = 2 * ext[k] + 3;
-    U = U > ext[0] * (ext[0] + 8) ? U : ext[0] * (ext[0] + 8);
+    U = U > ext[0] * (ext[0] + 12) ? U : ext[0] * (ext[0] + 12);
     for (int k = 0; k < nlev; k++) {
       A = A > ext[k] * ext[k + 1] ? A : ext[k] * ext[k + 1];
       B = B > ext[k + 1] * ext[k + 1] ? B : ext[k + 1] * ext[k + 1];
@@ -260,7 +346,8 @@ void launch_ll_residue(const Launch &L, LLParams q, int npairs) {
   ll_smem(q.a, &sa, &sb, &su);
   q.smem_a = sa;
   q.smem_b = sb;
-  size_t smem = (size_t)(sa + sb) * sizeof(short) + (size_t)su;
+  size_t smem = (size_t)(sa + sb) * sizeof(short);
+  (void)su;
   static size_t s_attr = 0;
   if (smem > 48 * 1024 && smem > s_attr) {
     cudaFuncSetAttribute(k_ll_residue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -268,7 +355,7 @@ void launch_ll_residue(const Launch &L, LLParams q, int npairs) {
   }
   dim3 grid((q.X + 31) / 32, (q.Y + 31) / 32, npairs * 3);
   ProfScope ps_(L, KC_RESIDUE);
-  k_ll_residue<<<grid, 256, smem, L.stream>>>(q);
+  k_ll_residue<<<grid, LL_NT, smem, L.stream>>>(q);
   COUNT(L);
 }
 
