@@ -259,7 +259,7 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     vbytes[l] = (size_t)pitch[l] * ((Y << l) + 2);
     vtotal += vbytes[l];
   }
-  const size_t per_slot = slot_shorts * sizeof(short) + vtotal;
+  const size_t per_slot = slot_shorts * sizeof(short) * 3 + vtotal;  // planes + LL snapshots (< 1.34x)
   const int per_pair_slots = pr ? 2 : 3;
   long long max_pairs = (long long)(c->me_budget / per_slot - 1) / per_pair_slots;
   if (max_pairs < 1) max_pairs = 1;
@@ -334,10 +334,35 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       launch_search(Lh, q, m);
       j++;
     };
-    dwt_analyze(Lh, img, 0, nslots, Y, X, L);
+    // For an invertible pyramid the descent only restores what the analysis overwrote:
+    // snapshot each LL region before it is transformed and copy it back instead of
+    // running the inverse transform (identical result, half the passes).
+    short *snap = nullptr;
+    std::vector<size_t> snap_off(L + 1, 0);
+    std::vector<int> snap_pitch(L + 1, 0);
+    size_t snap_per_slot = 0;
+    if (pr && L > 0) {
+      for (int l = 0; l < L; l++) {
+        snap_off[l] = snap_per_slot;
+        snap_pitch[l] = ((X >> l) + 7) & ~7;
+        snap_per_slot += (size_t)(Y >> l) * snap_pitch[l];
+      }
+      TRY(s.get(snap_per_slot * nslots * sizeof(short), (void **)&snap));
+      for (int l = 0; l < L; l++) {
+        launch_region_copy(Lh, img, 0, nslots, Y >> l, X >> l, snap + snap_off[l], (long long)snap_per_slot,
+                           snap_pitch[l], true);
+        launch_dwt_level(Lh, img, 0, nslots, Y >> l, X >> l, false);
+      }
+    } else {
+      dwt_analyze(Lh, img, 0, nslots, Y, X, L);
+    }
     run_search(ME_INIT, desp(BY, L), desp(BX, L), 0);
     for (int l = L - 1; l >= 0; --l) {
-      dwt_synthesize(Lh, img, 0, nslots, desp(Y, l), desp(X, l), 1);
+      if (snap)
+        launch_region_copy(Lh, img, 0, nslots, Y >> l, X >> l, snap + snap_off[l], (long long)snap_per_slot,
+                           snap_pitch[l], false);
+      else
+        dwt_synthesize(Lh, img, 0, nslots, desp(Y, l), desp(X, l), 1);
       run_search(ME_DESCEND, desp(BY, l), desp(BX, l), sr);
     }
     // byte planes of the level-0 interiors and their zero-high-band interpolations

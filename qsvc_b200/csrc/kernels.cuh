@@ -49,6 +49,9 @@ void launch_fill_border(const Launch &L, Plane p, int slot0, int nslots, int y_d
 void launch_store_u8(const Launch &L, Plane src, int slot0, int nslots, uint8_t *dst,
                      long long frame_stride, long long comp_off, int f0, int fstep, int h, int w);
 
+void launch_region_copy(const Launch &L, Plane p, int slot0, int nslots, int h, int w, short *snap,
+                        long long snap_slot_stride, int pitch, bool to_snapshot);
+
 // ---- 5/3 transforms (kernels_dwt.cu), in place, reference Mallat layout ----
 int dwt_init_attributes();
 // one level on the top-left ny x nx of each slot

@@ -135,3 +135,32 @@ void launch_fill_border(const Launch &L, Plane p, int slot0, int nslots, int Y, 
     COUNT(L);
   }
 }
+
+// Copies the top-left h x w region of every slot between the planes and a dense
+// snapshot buffer (row pitch `pitch` shorts, `snap_slot_stride` shorts per slot).
+__global__ void k_region_copy(Plane p, int slot0, int h, int w, short *snap, long long snap_slot_stride,
+                              int pitch, int to_snapshot) {
+  const int s = blockIdx.z;
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    short *row = p.row(slot0 + s, y);
+    short *srow = snap + (long long)s * snap_slot_stride + (long long)y * pitch;
+    const bool vec = (((uintptr_t)row | (uintptr_t)srow) & 15) == 0;
+    const int nv = vec ? (w >> 3) : 0;
+    uint4 *a = reinterpret_cast<uint4 *>(to_snapshot ? srow : row);
+    const uint4 *b = reinterpret_cast<const uint4 *>(to_snapshot ? row : srow);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) a[i] = b[i];
+    for (int x = (nv << 3) + blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
+      if (to_snapshot) srow[x] = row[x];
+      else row[x] = srow[x];
+    }
+  }
+}
+
+void launch_region_copy(const Launch &L, Plane p, int slot0, int nslots, int h, int w, short *snap,
+                        long long snap_slot_stride, int pitch, bool to_snapshot) {
+  if (nslots <= 0 || h <= 0 || w <= 0) return;
+  dim3 grid((w / 8 + 127) / 128 > 0 ? (w / 8 + 127) / 128 : 1, h < 2048 ? h : 2048, nslots);
+  ProfScope ps_(L, KC_IMG);
+  k_region_copy<<<grid, 128, 0, L.stream>>>(p, slot0, h, w, snap, snap_slot_stride, pitch, to_snapshot ? 1 : 0);
+  COUNT(L);
+}
