@@ -60,12 +60,26 @@ __global__ void __launch_bounds__(256) k_predict_u8(PredU8Params q) {
     return y0 + my >= 0 && y0 + my + q.bsa <= q.Ya && x0 + mx >= 0 && x0 + mx + q.bsa <= q.Xa;
   };
   if (inside(my0, mx0) && inside(my1, mx1)) {
-    for (int i = threadIdx.x; i < q.bsa * wpr; i += blockDim.x) {
-      const int y = y0 + i / wpr, x = x0 + 4 * (i % wpr);
-      unsigned a = load_u32_unaligned(V0 + (long long)(y + my0) * q.v_pitch + x + mx0);
-      unsigned b = load_u32_unaligned(V1 + (long long)(y + my1) * q.v_pitch + x + mx1);
+    // thread = (row within a pass, word column); pointers advance by whole passes so the
+    // loop body is two unaligned word loads, one halving add and one store
+    const int wl = 31 - __clz(wpr);  // wpr is a power of two here (checked by the launcher)
+    const int w = threadIdx.x & (wpr - 1), r0 = threadIdx.x >> wl, rstep = blockDim.x >> wl;
+    const uint8_t *a = V0 + (long long)(y0 + r0 + my0) * q.v_pitch + x0 + 4 * w + mx0;
+    const uint8_t *b = V1 + (long long)(y0 + r0 + my1) * q.v_pitch + x0 + 4 * w + mx1;
+    uint8_t *o = P + (long long)(y0 + r0) * q.p_pitch + x0 + 4 * w;
+    const long long vs = (long long)rstep * q.v_pitch, ps = (long long)rstep * q.p_pitch;
+    const int sa = 8 * (int)((uintptr_t)a & 3), sb = 8 * (int)((uintptr_t)b & 3);
+    const unsigned *a4 = reinterpret_cast<const unsigned *>((uintptr_t)a & ~(uintptr_t)3);
+    const unsigned *b4 = reinterpret_cast<const unsigned *>((uintptr_t)b & ~(uintptr_t)3);
+    const long long vs4 = vs >> 2;  // pitches are multiples of 16 bytes
+    for (int r = r0; r < q.bsa; r += rstep) {
+      unsigned va = __funnelshift_r(a4[0], a4[1], sa);
+      unsigned vb = __funnelshift_r(b4[0], b4[1], sb);
       // (r0 + r1) / 2 of bytes; the [0,255] clip of decorrelate.cpp:841-848 is a no-op
-      *reinterpret_cast<unsigned *>(P + (long long)y * q.p_pitch + x) = __vhaddu4(a, b);
+      *reinterpret_cast<unsigned *>(o) = __vhaddu4(va, vb);
+      a4 += vs4;
+      b4 += vs4;
+      o += ps;
     }
   } else {
     for (int i = threadIdx.x; i < q.bsa * q.bsa; i += blockDim.x) {
@@ -81,7 +95,10 @@ void launch_predict_u8(const Launch &L, const PredU8Params &q, int npairs) {
   if (npairs <= 0 || q.BY <= 0 || q.BX <= 0) return;
   dim3 grid(q.BX, q.BY, npairs * 3);
   ProfScope ps_(L, KC_PREDICT);
-  k_predict_u8<<<grid, q.bsa >= 32 ? 256 : 64, 0, L.stream>>>(q);
+  const int wpr = q.bsa >> 2;
+  int threads = q.bsa >= 32 ? 256 : 64;
+  if (wpr > threads) threads = wpr <= 1024 ? wpr : 1024;
+  k_predict_u8<<<grid, threads, 0, L.stream>>>(q);
   COUNT(L);
 }
 

@@ -397,14 +397,20 @@ __global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_tma(SubpelParams q
       }
     }
   }
-  // re-align the windows so that window column 0 sits on a word boundary
+  // re-align the windows so that window column 0 sits on a word boundary: thread =
+  // (row of a pass, word column); the threads of column 0 also produce word WPR
+  {
+    const int w = threadIdx.x % WPR, r0 = threadIdx.x / WPR;  // WPR is a power of two
+    constexpr int RSTEP = NT / WPR;
 #pragma unroll
-  for (int d = 0; d < 2; d++) {
-    const unsigned *T4 = reinterpret_cast<const unsigned *>(sT[d]) + ((wx[d] & 15) >> 2);
-    const int sa = 8 * (wx[d] & 3);
-    for (int i = threadIdx.x; i < (W + 2) * (WPR + 1); i += NT) {
-      const int y = i / (WPR + 1), w = i % (WPR + 1);
-      sR[d][y * RS + w] = __funnelshift_r(T4[y * TP + w], T4[y * TP + w + 1], sa);
+    for (int d = 0; d < 2; d++) {
+      const unsigned *T4 = reinterpret_cast<const unsigned *>(sT[d]) + ((wx[d] & 15) >> 2);
+      const int sa = 8 * (wx[d] & 3);
+      for (int y = r0; y < W + 2; y += RSTEP) {
+        const unsigned *t = T4 + y * TP + w;
+        sR[d][y * RS + w] = __funnelshift_r(t[0], t[1], sa);
+        if (w == 0) sR[d][y * RS + WPR] = __funnelshift_r(t[WPR], t[WPR + 1], sa);
+      }
     }
   }
   __syncthreads();
