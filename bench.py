@@ -325,7 +325,7 @@ def main():
     cls_ms = {k: v[0] / steps for k, v in prof.items()}
     cls_n = {k: v[1] // steps for k, v in prof.items()}
     sad = sad_ops_total(w)
-    search_ms = cls_ms["search"]
+    search_ms = cls_ms["search"] + cls_ms.get("search_exact", 0.0)
     me_ms = cls_ms["search"] + cls_ms["dwt_rows"] + cls_ms["dwt_cols"]  # upper bound: includes MC's DWT
     mc_ms = cls_ms["predict"] + cls_ms["residue"] + cls_ms["update"]
     dominant = max(cls_ms, key=cls_ms.get)
@@ -341,18 +341,29 @@ def main():
     }
     # the dominant kernel class of the step, against the bound that applies to it
     share = cls_ms[dominant] / max(1e-9, sum(cls_ms.values()))
-    if dominant == "search":
-        roof = {"bound": "int-sad", "kernel": "k_search", "achieved": rooflines["me_search"]["achieved"],
+    pairs_total = sum(p // 2 for p in _pictures_per_level(w))
+    Ya, Xa = w["Y"] << w["a"], w["X"] << w["a"]
+    fbytes = w["X"] * w["Y"] * 3 // 2
+    # algorithmic bytes per pair of the byte-plane MC kernels
+    alg = {"residue": (3 * Ya * Xa + 2 * fbytes) * pairs_total,   # k_ll_residue: 3 P_a planes + odd in + high out
+           "predict": 9 * Ya * Xa * pairs_total,                  # k_predict_u8: 2 reads + 1 write of 3 planes
+           "image": None, "dwt_rows": None, "dwt_cols": None, "update": None}
+    # dram__bytes_read+write of one ncu --set full capture (profiles/r1_summary.md), scaled per pair
+    ncu_traffic_per_pair = {"residue": (6.583642e9 + 0.230740e9) / 64, "predict": (12.688434e9 + 6.315000e9) / 64}
+    if dominant in ("search", "search_exact"):
+        roof = {"bound": "int-sad", "kernel": dominant, "achieved": rooflines["me_search"]["achieved"],
                 "peak": u8_peak / 1e9, "unit": "G SAD-op/s", "frac": rooflines["me_search"]["frac"],
                 "traffic": None, "share_of_step": share}
     else:
-        # DWT / predict / image kernels stream int16 planes: report them against HBM using
-        # the step's algorithmic bytes attributed to that class
-        alg = mc_bytes_total(w)
-        ach = alg / (cls_ms[dominant] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "share_of_step": share,
-                "peak_source": hbm_src}
+        a_bytes = alg.get(dominant) or mc_bytes_total(w)
+        ach = a_bytes / (cls_ms[dominant] * 1e-3) / 1e9
+        kname = {"residue": "k_ll_residue", "predict": "k_predict_u8"}.get(dominant, dominant)
+        tr = ncu_traffic_per_pair.get(dominant)
+        roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": tr * pairs_total if (tr and wname == "cfg3") else None,
+                "algorithmic_bytes": a_bytes, "share_of_step": share, "peak_source": hbm_src,
+                "note": "bytes and time summed over the class's launches of one step; the kernel is "
+                        "integer-ALU bound (see profiles/r1_summary.md), the HBM fraction is reported as required"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
