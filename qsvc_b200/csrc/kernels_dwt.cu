@@ -11,15 +11,41 @@
 
 static const int kMaxDynSmem = 200 * 1024;
 
+// One line of the lifting, "pair" formulation: task i produces l[i] and h[i] (analysis)
+// or s[2i] and s[2i+1] (synthesis) of an n-sample line held in shared memory with
+// stride st.  half = n/2 pairs, plus the unpaired last low sample when n is odd.
+__device__ __forceinline__ void ana_pair(const short *s, int st, int i, int n, int &l, int &h) {
+  const int half = n >> 1;
+  const int s0 = s[(2 * i) * st], s1 = s[(2 * i + 1) * st];
+  const bool last_even = !(n & 1) && i == half - 1;
+  h = (short)(last_even ? s1 - s0 : s1 - tdiv2(s0 + s[(2 * i + 2) * st]));
+  if (i == 0) {
+    l = (short)(s0 + tdiv2(h));
+  } else {
+    const int hp = (short)(s[(2 * i - 1) * st] - tdiv2(s[(2 * i - 2) * st] + s0));
+    l = (short)(s0 + tdiv4(h + hp));
+  }
+}
+// even sample e(i) of the synthesis; lo = lows, hi = highs (stride st)
+__device__ __forceinline__ int syn_e(const short *lo, const short *hi, int st, int i, int n) {
+  const int half = n >> 1;
+  if (i == 0) return (short)(lo[0] - tdiv2(hi[0]));
+  if (i < half) return (short)(lo[i * st] - tdiv4(hi[i * st] + hi[(i - 1) * st]));
+  return (short)(lo[half * st] - tdiv2(hi[(half - 1) * st]));
+}
+
+// Row pass.  One CTA per row at a time: the row is staged in shared memory (128-bit
+// loads when aligned), thread i produces one output pair and stores it straight to
+// the row (coalesced 16-bit stores for analysis, one 32-bit store for synthesis).
 template <bool SYNTH>
 __global__ void __launch_bounds__(256) k_dwt_rows(Plane p, int slot0, int ny, int nx) {
   extern __shared__ __align__(16) short sm[];
   const int slot = slot0 + blockIdx.z;
   const int nvec = nx >> 3;
+  const int half = nx >> 1, nlow = nx - half;
   for (int y = blockIdx.x; y < ny; y += gridDim.x) {
     short *row = p.row(slot, y);
-    const bool aligned = (((uintptr_t)row) & 15) == 0;
-    if (aligned) {
+    if ((((uintptr_t)row) & 15) == 0) {
       const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
       uint4 *s4 = reinterpret_cast<uint4 *>(sm);
       for (int i = threadIdx.x; i < nvec; i += blockDim.x) s4[i] = r4[i];
@@ -28,28 +54,38 @@ __global__ void __launch_bounds__(256) k_dwt_rows(Plane p, int slot0, int ny, in
       for (int i = threadIdx.x; i < nx; i += blockDim.x) sm[i] = row[i];
     }
     __syncthreads();
-    if (aligned) {
-      uint4 *r4 = reinterpret_cast<uint4 *>(row);
-      for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        union { uint4 v; short h[8]; } u;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          u.h[k] = SYNTH ? l53_syn_out(sm, 1, 8 * i + k, nx) : l53_ana_out(sm, 1, 8 * i + k, nx);
-        r4[i] = u.v;
+    if (!SYNTH) {
+      for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        int l, h;
+        ana_pair(sm, 1, i, nx, l, h);
+        row[i] = (short)l;
+        row[nlow + i] = (short)h;
+        if ((nx & 1) && i == half - 1) row[half] = (short)(sm[nx - 1] + tdiv2(h));
       }
-      for (int j = (nvec << 3) + threadIdx.x; j < nx; j += blockDim.x)
-        row[j] = SYNTH ? l53_syn_out(sm, 1, j, nx) : l53_ana_out(sm, 1, j, nx);
     } else {
-      for (int j = threadIdx.x; j < nx; j += blockDim.x)
-        row[j] = SYNTH ? l53_syn_out(sm, 1, j, nx) : l53_ana_out(sm, 1, j, nx);
+      const short *lo = sm, *hi = sm + nlow;
+      const bool al4 = (((uintptr_t)row) & 3) == 0;
+      for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        const int e0 = syn_e(lo, hi, 1, i, nx);
+        int o;
+        if (!(nx & 1) && i == half - 1) o = (short)(hi[i] + e0);
+        else o = (short)(hi[i] + tdiv2(e0 + syn_e(lo, hi, 1, i + 1, nx)));
+        if (al4) {
+          reinterpret_cast<unsigned *>(row)[i] = ((unsigned)(unsigned short)e0) | ((unsigned)(unsigned short)o << 16);
+        } else {
+          row[2 * i] = (short)e0;
+          row[2 * i + 1] = (short)o;
+        }
+        if ((nx & 1) && i == half - 1) row[nx - 1] = (short)syn_e(lo, hi, 1, half, nx);
+      }
     }
     __syncthreads();
   }
 }
 
-// Column pass: the CTA stages a strip of CW = 2^cw_log2 columns x ny rows in
-// shared memory, then every thread produces 8 horizontally adjacent outputs of
-// one row (one 128-bit store).  1024 threads keep enough loads in flight.
+// Column pass: the CTA stages a strip of CW = 2^cw_log2 columns x ny rows in shared
+// memory (in-place de-interleave needs the whole column), then thread (column, row
+// segment) slides down its segment reusing the previous step's samples.
 template <bool SYNTH>
 __global__ void __launch_bounds__(1024) k_dwt_cols(Plane p, int slot0, int ny, int nx, int cw_log2) {
   extern __shared__ __align__(16) short sm[];
@@ -71,33 +107,44 @@ __global__ void __launch_bounds__(1024) k_dwt_cols(Plane p, int slot0, int ny, i
         for (int k = 0; k < 8 && c0 + k < cw; k++) dst[k] = src[k];
       }
     }
-    __syncthreads();
-    for (int u = threadIdx.x; u < units; u += blockDim.x) {
-      int y = u >> upr_log2, c0 = (u & ((1 << upr_log2) - 1)) << 3;
-      if (c0 >= cw) continue;
-      short *dst = p.row(slot, y) + x0 + c0;
-      union { uint4 v; short h[8]; } o;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        o.h[k] = SYNTH ? l53_syn_out(sm + c0 + k, CW, y, ny) : l53_ana_out(sm + c0 + k, CW, y, ny);
-      if (c0 + 8 <= cw && (((uintptr_t)dst) & 15) == 0) {
-        *reinterpret_cast<uint4 *>(dst) = o.v;
-      } else {
-        for (int k = 0; k < 8 && c0 + k < cw; k++) dst[k] = o.h[k];
-      }
-    }
   } else {
     const int total = ny << cw_log2;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
       int y = idx >> cw_log2, c = idx & (CW - 1);
       if (c < cw) sm[idx] = p.row(slot, y)[x0 + c];
     }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      int y = idx >> cw_log2, c = idx & (CW - 1);
-      if (c < cw)
-        p.row(slot, y)[x0 + c] =
-            SYNTH ? l53_syn_out(sm + c, CW, y, ny) : l53_ana_out(sm + c, CW, y, ny);
+  }
+  __syncthreads();
+  const int c = threadIdx.x & (CW - 1), seg = threadIdx.x >> cw_log2, nseg = blockDim.x >> cw_log2;
+  if (c >= cw) return;
+  const int half = ny >> 1, nlow = ny - half;
+  const int per = (half + nseg - 1) / nseg;
+  const int i0 = seg * per, i1 = min(half, i0 + per);
+  const short *s = sm + c;
+  // one row pointer walk per output stream
+  if (!SYNTH) {
+    for (int i = i0; i < i1; i++) {
+      int l, h;
+      ana_pair(s, CW, i, ny, l, h);
+      p.row(slot, i)[x0 + c] = (short)l;
+      p.row(slot, nlow + i)[x0 + c] = (short)h;
+      if ((ny & 1) && i == half - 1) p.row(slot, half)[x0 + c] = (short)(s[(ny - 1) * CW] + tdiv2(h));
+    }
+  } else {
+    const short *lo = s, *hi = s + (long long)nlow * CW;
+    int e0 = i0 < i1 ? syn_e(lo, hi, CW, i0, ny) : 0;
+    for (int i = i0; i < i1; i++) {
+      int o, e1 = 0;
+      if (!(ny & 1) && i == half - 1) {
+        o = (short)(hi[i * CW] + e0);
+      } else {
+        e1 = syn_e(lo, hi, CW, i + 1, ny);
+        o = (short)(hi[i * CW] + tdiv2(e0 + e1));
+      }
+      p.row(slot, 2 * i)[x0 + c] = (short)e0;
+      p.row(slot, 2 * i + 1)[x0 + c] = (short)o;
+      if ((ny & 1) && i == half - 1) p.row(slot, ny - 1)[x0 + c] = (short)e1;
+      e0 = e1;
     }
   }
 }
