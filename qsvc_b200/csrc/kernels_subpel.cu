@@ -472,6 +472,12 @@ __global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_tma(SubpelParams q
 
 // ------------------------------------------------------------ exact path
 
+// Flattened 2-D loop over h x w cells by 256 threads: one division per thread, not per cell.
+#define FOR_CELLS(r, c, h, w)                                                                  \
+  for (int i_ = threadIdx.x, r = i_ / (w), c = i_ - r * (w), dc_ = 256 % (w), dr_ = 256 / (w); \
+       i_ < (h) * (w); i_ += 256, c += dc_, r += dr_, r += (c >= (w)), c -= (c >= (w)) ? (w) : 0)
+
+
 struct B0View {
   Plane p;
   int Y, X, B, Bc;       // picture, fill border, compact border
@@ -541,11 +547,12 @@ __device__ __forceinline__ int b1_cell(const B0View &v, int slot, int y, int x) 
   return b0_cell(v, slot, y, x);
 }
 
-// Level-1 window (h x w at (y0, x0)) into dst.  The column-pass samples T(y, j)
-// (low columns) and T(y, X + j) (high columns) that the row pass needs are staged
-// in TL / TH first, so every level-0 cell is read a bounded number of times.
+// Level-1 window (h x w at (y0, x0)) into dst.  The four level-0 sub-windows it depends
+// on -- low/low, low/high (columns >= X), high/low (rows >= Y), high/high -- are staged in
+// shared memory first (high-band cells are zero beyond the fill_border replicas), then the
+// column pass T (5_3.cpp:81-94 on columns) and the row pass run from shared memory.
 __device__ void gen_level1(const B0View &v, int slot, int y0, int x0, int h, int w, short *dst,
-                           short *TL, short *TH, int nthreads) {
+                           short *TL, short *TH, short *stage, int nthreads) {
   const int Y1 = 2 * v.Y, X1 = 2 * v.X;
   const int ya = max(y0, 0), yb = min(y0 + h, Y1);
   const int xa = max(x0, 0), xb = min(x0 + w, X1);
@@ -556,15 +563,43 @@ __device__ void gen_level1(const B0View &v, int slot, int y0, int x0, int h, int
     nj = j1 - j0 + 1;
     hj0 = max(j0 - 1, 0);
     nh = j1 - hj0 + 1;
+    const int ilo = max((ya >> 1) - 1, 0), ihi = min(((yb - 1) >> 1) + 1, v.Y - 1);
+    const int ni = ihi - ilo + 1;
+    short *SLL = stage, *SHL = SLL + ni * nh, *SLH = SHL + ni * nh, *SHH = SLH + ni * nh;
+    FOR_CELLS(r, cc, ni, nh) {
+      const int yy = ilo + r, xx = hj0 + cc, i = r * nh + cc;
+      SLL[i] = v.p.row(slot, yy)[xx];
+      SHL[i] = (short)b0_high(v, slot, yy, v.X + xx);
+      SLH[i] = (short)b0_high(v, slot, v.Y + yy, xx);
+      SHH[i] = (short)b0_high(v, slot, v.Y + yy, v.X + xx);
+    }
+    __syncthreads();
     const int rows = yb - ya;
-    for (int i = threadIdx.x; i < rows * nj; i += nthreads)
-      TL[i] = (short)t1_cell(v, slot, ya + i / nj, j0 + i % nj);
-    for (int i = threadIdx.x; i < rows * nh; i += nthreads)
-      TH[i] = (short)t1_cell(v, slot, ya + i / nh, v.X + hj0 + i % nh);
+    // column pass for the low columns (TL) and the high columns (TH)
+    FOR_CELLS(r2, cc, rows * 2, nh) {
+      const int which = r2 >= rows;  // 0: low columns, 1: high columns
+      const int r = which ? r2 - rows : r2;
+      const short *lo = (which ? SHL : SLL) + cc, *hi = (which ? SHH : SLH) + cc;
+      const int y = ya + r, ii = y >> 1, li = ii - ilo;
+      auto te = [&](int q) -> int {  // even sample 2*(ilo+q) of the column
+        const int gi = ilo + q;
+        const int hh = gi == 0 ? tdiv2(hi[0]) : tdiv4(hi[q * nh] + hi[(q - 1) * nh]);
+        return (short)(lo[q * nh] - hh);
+      };
+      int val;
+      if (!(y & 1)) {
+        val = te(li);
+      } else {
+        const int e0 = te(li);
+        val = (ii < v.Y - 1) ? (short)(hi[li * nh] + tdiv2(e0 + te(li + 1))) : (short)(hi[li * nh] + e0);
+      }
+      if (which) TH[r * nh + cc] = (short)val;
+      else if (cc >= j0 - hj0) TL[r * nj + cc - (j0 - hj0)] = (short)val;
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < h * w; i += nthreads) {
-    const int y = y0 + i / w, x = x0 + i % w;
+  FOR_CELLS(ry, rx, h, w) {
+    const int y = y0 + ry, x = x0 + rx, i = ry * w + rx;
     int val;
     if (y >= 0 && y < Y1 && x >= 0 && x < X1) {
       const short *tl = TL + (y - ya) * nj - j0;
@@ -587,40 +622,43 @@ __device__ void gen_level1(const B0View &v, int slot, int y0, int x0, int h, int
   }
 }
 
-// Fills dst (h x w, row stride w) with the level-l window whose top-left is (y0, x0).
+// Fills dst (H x WW, row stride WW) with the level-l window whose top-left is (y0, x0).
 // Level 2 is built from a level-1 window staged in `tmp` (high bands of the second
-// synthesis are zero because B <= min(X, Y): checked on the host).
-__device__ void gen_window(const B0View &v, int slot, int l, int y0, int x0, int h, int w,
-                           short *dst, short *tmp, short *TL, short *TH, int nthreads) {
+// synthesis are zero because B <= min(X, Y): checked on the host), separably: column
+// pass into `vbuf` (H x tw), then row pass.
+template <int H, int WW>
+__device__ void gen_window(const B0View &v, int slot, int l, int y0, int x0, short *dst, short *tmp,
+                           short *TL, short *TH, short *stage, int nthreads) {
   if (l == 1) {
-    gen_level1(v, slot, y0, x0, h, w, dst, TL, TH, nthreads);
+    gen_level1(v, slot, y0, x0, H, WW, dst, TL, TH, stage, nthreads);
     return;
   }
-  // level-1 window covering rows [y0>>1, ((y0+h-1)>>1)+1], same for columns (floor division)
+  // level-1 window covering rows [y0>>1, ((y0+H-1)>>1)+1], same for columns (floor division)
   const int ty0 = y0 >> 1, tx0 = x0 >> 1;
-  const int th = ((y0 + h - 1) >> 1) - ty0 + 2, tw = ((x0 + w - 1) >> 1) - tx0 + 2;
+  const int th = ((y0 + H - 1) >> 1) - ty0 + 2, tw = ((x0 + WW - 1) >> 1) - tx0 + 2;
   const int Y2 = 4 * v.Y, X2 = 4 * v.X;
-  gen_level1(v, slot, ty0, tx0, th, tw, tmp, TL, TH, nthreads);
+  gen_level1(v, slot, ty0, tx0, th, tw, tmp, TL, TH, stage, nthreads);
   __syncthreads();
-  for (int i = threadIdx.x; i < h * w; i += nthreads) {
-    int y = y0 + i / w, x = x0 + i % w;
+  short *vbuf = TL;  // free again after gen_level1
+  // column pass (zero high band): vbuf[yy][xp] = T(y0 + yy, tx0 + xp)
+  FOR_CELLS(yy, xp, H, tw) {
+    const int y = y0 + yy, i = yy * tw + xp;
+    int val = 0;
+    if (y >= 0 && y < Y2) {
+      const int i0 = (y >> 1) - ty0;
+      const int a = tmp[i0 * tw + xp];
+      val = (!(y & 1) || y == Y2 - 1) ? a : (short)tdiv2(a + tmp[(i0 + 1) * tw + xp]);
+    }
+    vbuf[i] = (short)val;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * WW; i += nthreads) {
+    const int yy = i / WW, xx = i - yy * WW;  // WW is a compile-time constant
+    const int y = y0 + yy, x = x0 + xx;
     int val;
     if (y >= 0 && y < Y2 && x >= 0 && x < X2) {
-      // column pass (zero high band): T(y, xp) for xp = x>>1 and (x>>1)+1
-      auto T = [&](int yy, int xp) -> int {
-        const short *col = tmp + (xp - tx0);
-        int i0 = yy >> 1;
-        int a = col[(i0 - ty0) * tw];
-        if (!(yy & 1)) return a;
-        if (yy == Y2 - 1) return a;
-        return (short)(tdiv2(a + col[(i0 + 1 - ty0) * tw]));
-      };
-      int j0 = x >> 1;
-      int a = T(y, j0);
-      if (!(x & 1) || x == X2 - 1)
-        val = a;
-      else
-        val = (short)(tdiv2(a + T(y, j0 + 1)));
+      const short *r = vbuf + yy * tw + ((x >> 1) - tx0);
+      val = (!(x & 1) || x == X2 - 1) ? (int)r[0] : (short)tdiv2(r[0] + r[1]);
     } else {
       val = b0_cell(v, slot, y, x);
     }
@@ -638,6 +676,7 @@ __global__ void __launch_bounds__(256) k_subpel_exact(SubpelParams q, B0View v) 
   short *tmp = Rs1 + RW * RW;  // (W/2 + 4)^2 level-1 staging
   short *TL = tmp + (W / 2 + 4) * (W / 2 + 4);
   short *TH = TL + (W + 2) * (W / 2 + 4);
+  short *stage = TH + (W + 2) * (W / 2 + 4);  // 4 x (W/2 + 4) x (W/2 + 4) level-0 sub-windows
   __shared__ int s_part[8][18];
   __shared__ int s_fin[18];
   const int total = *q.slow_count;
@@ -648,37 +687,53 @@ __global__ void __launch_bounds__(256) k_subpel_exact(SubpelParams q, B0View v) 
     subpel_centre(q, pair, by, bx, c);
     const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
     const int py0 = by * W, px0 = bx * W;
-    gen_window(v, ps, q.l, py0, px0, W, W, Ps, tmp, TL, TH, blockDim.x);
+    gen_window<W, W>(v, ps, q.l, py0, px0, Ps, tmp, TL, TH, stage, blockDim.x);
     __syncthreads();
-    gen_window(v, r0s, q.l, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, RW, RW, Rs0, tmp, TL, TH, blockDim.x);
+    gen_window<RW, RW>(v, r0s, q.l, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, Rs0, tmp, TL, TH, stage, blockDim.x);
     __syncthreads();
-    gen_window(v, r1s, q.l, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, RW, RW, Rs1, tmp, TL, TH, blockDim.x);
+    gen_window<RW, RW>(v, r1s, q.l, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, Rs1, tmp, TL, TH, stage, blockDim.x);
     __syncthreads();
+    // SAD: thread = (block row, segment of SEG pixels); accumulators indexed by window shift
+    constexpr int SEG = W * W / 256, SPR = W / SEG;  // 16 px x 4 segments (W=64), 4 px x 8 (W=32)
     unsigned acc[18];
 #pragma unroll
     for (int k = 0; k < 18; k++) acc[k] = 0;
-    for (int i = threadIdx.x; i < W * W; i += blockDim.x) {
-      int y = i / W, x = i % W;
-      int p = Ps[i];
-      const short *a = Rs0 + (y + 1) * RW + x + 1;
-      const short *b = Rs1 + (y + 1) * RW + x + 1;
+    {
+      const int y = threadIdx.x / SPR, x0s = (threadIdx.x % SPR) * SEG;
+      int p[SEG];
 #pragma unroll
-      for (int k = 0; k < 9; k++) {
-        int off = c_cand9[k][0] * RW + c_cand9[k][1];
-        acc[k] = __sad(p, (int)a[off], acc[k]);
-        acc[9 + k] = __sad(p, (int)b[-off], acc[9 + k]);
+      for (int i = 0; i < SEG; i++) p[i] = Ps[y * W + x0s + i];
+#pragma unroll
+      for (int d = 0; d < 2; d++) {
+        const short *R = (d ? Rs1 : Rs0) + y * RW + x0s;
+#pragma unroll
+        for (int wr = 0; wr < 3; wr++) {
+          int vv[SEG + 2];
+#pragma unroll
+          for (int i = 0; i < SEG + 2; i++) vv[i] = R[wr * RW + i];
+#pragma unroll
+          for (int wc = 0; wc < 3; wc++)
+#pragma unroll
+            for (int i = 0; i < SEG; i++) acc[d * 9 + wr * 3 + wc] = __sad(p[i], vv[i + wc], acc[d * 9 + wr * 3 + wc]);
+        }
       }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < 18; k++) {
-      unsigned s = __reduce_add_sync(0xffffffffu, acc[k]);
-      if (lane == 0) s_part[warp][k] = (int)s;
+      unsigned sacc = __reduce_add_sync(0xffffffffu, acc[k]);
+      if (lane == 0) s_part[warp][k] = (int)sacc;
     }
     __syncthreads();
     if (threadIdx.x < 18) {
+      // candidate k of direction dd tests the window shift sgn * (dy, dx)
+      constexpr int DY[9] = {-1, -1, 1, 1, -1, 1, 0, 0, 0};
+      constexpr int DX[9] = {-1, 1, -1, 1, 0, 0, 1, -1, 0};
+      const int dd = threadIdx.x / 9, k = threadIdx.x % 9;
+      const int sgn = dd ? -1 : 1;
+      const int slot_i = dd * 9 + (sgn * DY[k] + 1) * 3 + sgn * DX[k] + 1;
       int e = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); w++) e += s_part[w][threadIdx.x];
+      for (int w = 0; w < 8; w++) e += s_part[w][slot_i];
       s_fin[threadIdx.x] = e;
     }
     __syncthreads();
@@ -710,7 +765,8 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
   v.Ba = q.Ba;
   v.size_field = q.size_field;
   const int RW = W + 2, TW = W / 2 + 4;
-  size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW + (size_t)TW * TW + 2 * (size_t)RW * TW) * sizeof(short);
+  size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW + (size_t)TW * TW + 2 * (size_t)RW * TW + 4 * (size_t)TW * TW) *
+                sizeof(short);
   static size_t s_attr = 0;
   if (smem > 48 * 1024 && smem > s_attr) {
     cudaFuncSetAttribute(k_subpel_exact<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
