@@ -692,6 +692,8 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
   // residue[1|2] is only ever written in its top-left quarter (update.cpp:512-520,
   // UPDATE_STEP undefined); the rest stays at the allocator's zeros.
   CU(cudaMemsetAsync(res.raw, 0, res.bytes, c->stream));
+  int *d_reach;
+  TRY(s.get(256, (void **)&d_reach));
   for (int k = 0; k <= n_pairs; k++) {
     const uint8_t *frame = in + (long long)k * in_stride;
     uint8_t *dst = out + (long long)k * out_stride;
@@ -722,6 +724,8 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
       q.res = res.p;
       q.mv = mv + (long long)pair * field;
       q.dir = pass == 0 ? MV_NEXT_X : MV_PREV_X;
+      launch_mv_reach(Lh, q.mv + (long long)q.dir * BY * BX, 2 * BY * BX, d_reach);
+      q.reach = d_reach;
       q.BY = BY;
       q.BX = BX;
       q.bs = bs;

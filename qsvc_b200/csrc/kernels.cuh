@@ -149,8 +149,10 @@ struct UpdateParams {
   int BY, BX, bs, Y, X;
   float uf;
   int inverse;
+  const int *reach;     // device: max |vector component| of this direction (launch_mv_reach)
 };
 void launch_update(const Launch &L, const UpdateParams &q);
+void launch_mv_reach(const Launch &L, const short *mv, int n, int *out);
 // residue plane: top-left h x w = high - 128 (rest untouched)
 void launch_load_residue(const Launch &L, Plane dst, int slot, const uint8_t *src, int h, int w);
 

@@ -200,7 +200,15 @@ __global__ void __launch_bounds__(256) k_update(UpdateParams q) {
   const long long plane = (long long)q.BY * q.BX;
   const short *mvx = q.mv + (long long)q.dir * plane;
   const short *mvy = q.mv + (long long)(q.dir + 1) * plane;
-  const int nblocks = q.BY * q.BX;
+  // only blocks within `reach` (largest |vector component| of this field) of the tile can
+  // touch it; candidates are enumerated in raster order, like the reference's scatter
+  const int reach = *q.reach;
+  const int by_lo = max(0, (tile_y0 - reach - q.bs + 1 + (q.bs - 1) * (tile_y0 - reach - q.bs + 1 > 0)) / q.bs);
+  const int by_hi = min(q.BY - 1, (tile_y1 + reach) / q.bs);
+  const int bx_lo = max(0, (tile_x0 - reach - q.bs + 1 + (q.bs - 1) * (tile_x0 - reach - q.bs + 1 > 0)) / q.bs);
+  const int bx_hi = min(q.BX - 1, (tile_x1 + reach) / q.bs);
+  const int nbw = max(bx_hi - bx_lo + 1, 0), nbh = max(by_hi - by_lo + 1, 0);
+  const int nblocks = nbw * nbh;
   float aux = 0.f;
   short *target = nullptr;
   if (active) {
@@ -212,10 +220,13 @@ __global__ void __launch_bounds__(256) k_update(UpdateParams q) {
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
     // ordered compaction of the blocks that can reach this tile
-    int b = base + threadIdx.x;
+    int b = -1;
     bool hit = false;
-    if (b < nblocks) {
-      int oy = (b / q.BX) * q.bs + mvy[b], ox = (b % q.BX) * q.bs + mvx[b];
+    if (base + threadIdx.x < nblocks) {
+      const int k = base + threadIdx.x;
+      const int cby = by_lo + k / nbw, cbx = bx_lo + k % nbw;
+      b = cby * q.BX + cbx;
+      int oy = cby * q.bs + mvy[b], ox = cbx * q.bs + mvx[b];
       int fy0 = iclamp(oy, 0, q.Y - 1), fy1 = iclamp(oy + q.bs - 1, 0, q.Y - 1);
       int fx0 = iclamp(ox, 0, q.X - 1), fx1 = iclamp(ox + q.bs - 1, 0, q.X - 1);
       hit = fy0 <= tile_y1 && fy1 >= tile_y0 && fx0 <= tile_x1 && fx1 >= tile_x0;
@@ -258,6 +269,24 @@ __global__ void __launch_bounds__(256) k_update(UpdateParams q) {
     __syncthreads();
   }
   if (active) *target = cur;
+}
+
+// largest |component| of the two planes (x, y) of one direction of a field
+__global__ void k_mv_reach(const short *__restrict__ mv, int n, int *out) {
+  __shared__ int s_max;
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  int m = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = max(m, abs((int)mv[i]));
+  atomicMax(&s_max, m);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = s_max;
+}
+
+void launch_mv_reach(const Launch &L, const short *mv, int n, int *out) {
+  ProfScope ps_(L, KC_UPDATE);
+  k_mv_reach<<<1, 256, 0, L.stream>>>(mv, n, out);
+  COUNT(L);
 }
 
 void launch_update(const Launch &L, const UpdateParams &q) {
