@@ -288,6 +288,19 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     TRY(s.get((size_t)m * 3 * sizeof(int), (void **)&d_slots));
     TRY(s.get((size_t)nslots * tiles_per_slot + 16, (void **)&d_flags));
     TRY(s.get(((size_t)m * BY * BX + 1) * sizeof(int), (void **)&d_slow));
+    int *d_bad;
+    TRY(s.get(((size_t)m * BY * BX + 1) * sizeof(int), (void **)&d_bad));
+    // int16 strips of the sub-pixel images where fill_border's replicas reach (top rows, left columns)
+    int cleanl[3] = {0, 0, 0};
+    size_t top_sz[3] = {0, 0, 0}, left_sz[3] = {0, 0, 0};
+    short *stop[3] = {nullptr, nullptr, nullptr}, *sleft[3] = {nullptr, nullptr, nullptr};
+    for (int l = 1; l <= a; l++) {
+      cleanl[l] = std::min((2 * B + 2) << (l - 1), std::min(Y << l, X << l));
+      top_sz[l] = (size_t)cleanl[l] * (X << l);
+      left_sz[l] = std::max<size_t>((size_t)((Y << l) - cleanl[l]) * cleanl[l], 8);
+      TRY(s.get(top_sz[l] * nslots * sizeof(short), (void **)&stop[l]));
+      TRY(s.get(left_sz[l] * nslots * sizeof(short), (void **)&sleft[l]));
+    }
     std::vector<int> slots(3 * m);
     for (int i = 0; i < m; i++) {
       slots[3 * i] = (!pr && i >= 1) ? 2 * m + i : i;
@@ -397,6 +410,16 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       q.lim = sr << a;
       q.slow_count = d_slow;
       q.slow_list = d_slow + 1;
+      CU(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+      q.bad_count = d_bad;
+      q.bad_list = d_bad + 1;
+      q.clean = cleanl[l];
+      q.strip_top = stop[l];
+      q.strip_left = sleft[l];
+      q.strip_top_stride = (long long)top_sz[l];
+      q.strip_left_stride = (long long)left_sz[l];
+      launch_strips(Lh, q, l, nslots, stop[l], sleft[l], stop[1], sleft[1], (long long)top_sz[1],
+                    (long long)left_sz[1], cleanl[1], v[1], (long long)vbytes[1], pitch[1]);
       q.v_rows_per_slot = (int)(vbytes[l] / pitch[l]);
       q.use_tma = (c->tma_mode != 0 &&
                    subpel_make_tensor_maps(v[l], pitch[l], (long long)q.v_rows_per_slot * nslots, bs << l, q.tm_p, q.tm_r))

@@ -92,8 +92,14 @@ struct SubpelParams {
   int Ya, Ba;          // rows / border of the reference's allocation (size-field rows)
   unsigned long long size_field;
   int lim;             // vector clamp, search_range << a
-  int *slow_count;
+  int *slow_count;       // blocks for the strip path (windows touch polluted strips / leave the picture)
   int *slow_list;
+  int *bad_count;        // blocks over a non-byte tile: full exact generator
+  int *bad_list;
+  const short *strip_top;   // per slot [clean][X << l]: level-l samples of the polluted top rows
+  const short *strip_left;  // per slot [(Y << l) - clean][clean]: polluted left columns below them
+  long long strip_top_stride, strip_left_stride;
+  int clean;             // min((2B + 2) << (l - 1), Y << l, X << l)
   int v_rows_per_slot;   // v_slot_stride / v_pitch
   int use_tma;           // tm_p / tm_r hold valid CUtensorMap objects
   alignas(64) unsigned char tm_p[128];
@@ -102,6 +108,11 @@ struct SubpelParams {
 bool subpel_make_tensor_maps(const uint8_t *v, int pitch, long long total_rows, int W, void *tm_p,
                              void *tm_r);
 bool subpel_supported(int W);
+// int16 strips of the level-l images where they differ from the byte planes (first
+// `clean` rows and columns); level 2 is derived from the level-1 strips and V_1.
+void launch_strips(const Launch &L, const SubpelParams &q, int level, int nslots, short *top, short *left,
+                   const short *top1, const short *left1, long long top1_stride, long long left1_stride,
+                   int clean1, const uint8_t *v1, long long v1_slot_stride, int v1_pitch);
 int subpel_tma_timeouts();
 void launch_subpel(const Launch &L, const SubpelParams &q, int W, int npairs);
 void launch_plane_to_u8(const Launch &L, Plane src, int slot0, int nslots, int Y, int X,

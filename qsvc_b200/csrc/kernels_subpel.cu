@@ -22,6 +22,8 @@
 //    the high-band reads) and accumulates with __sad.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 
 #define COUNT(L) (++*(L).counter)
@@ -157,6 +159,41 @@ __device__ __forceinline__ void subpel_store(const SubpelParams &q, int pair, in
   }
 }
 
+// 0: fast byte path, 1: strip path (a window touches the polluted strips or leaves the
+// picture), 2: exact generator (a level-0 pixel under a window is not a byte).
+template <int W, int NT>
+__device__ __forceinline__ int classify_block(const SubpelParams &q, int l, int r0s, int r1s, int ps,
+                                              int py0, int px0, const int wy[2], const int wx[2]) {
+  const int Yl = q.Y << l, Xl = q.X << l;
+  bool fast = true;
+#pragma unroll
+  for (int d = 0; d < 2; d++)
+    fast = fast && wy[d] >= q.clean && wx[d] >= q.clean && wy[d] + W + 2 <= Yl && wx[d] + W + 2 <= Xl;
+  int bad = 0;
+  for (int img = 0; img < 3; img++) {
+    const int slot = img == 0 ? r0s : (img == 1 ? r1s : ps);
+    const int y0 = img == 2 ? py0 : wy[img], x0 = img == 2 ? px0 : wx[img];
+    const int span = img == 2 ? W : W + 2;
+    const int pyl = max(y0 >> l, 0), pyh = min(((y0 + span - 1) >> l) + 1, q.Y - 1);
+    const int pxl = max(x0 >> l, 0), pxh = min(((x0 + span - 1) >> l) + 1, q.X - 1);
+    if (pyl > pyh || pxl > pxh) continue;
+    const int ty0 = pyl >> 4, nty = (pyh >> 4) - ty0 + 1, tx0 = pxl >> 4, ntx = (pxh >> 4) - tx0 + 1;
+    const uint8_t *map = q.tile_bad + (long long)slot * q.tiles_per_slot;
+    for (int i = threadIdx.x; i < nty * ntx; i += NT)
+      bad |= map[(ty0 + i / ntx) * q.tiles_x + tx0 + i % ntx];
+  }
+  bad = __syncthreads_or(bad);
+  return bad ? 2 : (fast ? 0 : 1);
+}
+
+__device__ __forceinline__ void queue_block(const SubpelParams &q, int kind, int pair, int by, int bx) {
+  if (threadIdx.x == 0) {
+    int *cnt = kind == 2 ? q.bad_count : q.slow_count;
+    int *list = kind == 2 ? q.bad_list : q.slow_list;
+    list[atomicAdd(cnt, 1)] = (pair * q.BY + by) * q.BX + bx;
+  }
+}
+
 // W = block size at this level (bs << l), W in {16, 32, 64}.  Thread t owns the
 // 32-bit word column j = t % (W/4) of RPT consecutive block rows.
 template <int W>
@@ -181,36 +218,12 @@ __global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_fast(SubpelParams 
   const int py0 = by * W, px0 = bx * W;
   const int wy[2] = {py0 + c[MV_PREV_Y] - 1, py0 + c[MV_NEXT_Y] - 1};
   const int wx[2] = {px0 + c[MV_PREV_X] - 1, px0 + c[MV_NEXT_X] - 1};
-  // B_l == V_l on [clean, dim) x [clean, dim): outside the rows/columns reached by the
-  // fill_border replicas that sit in the first high-band rows/columns of level 1
-  const int clean = (2 * q.B + 2) << (l - 1);
-  bool fast = true;
-#pragma unroll
-  for (int d = 0; d < 2; d++)
-    fast = fast && wy[d] >= clean && wx[d] >= clean && wy[d] + W + 2 <= Yl && wx[d] + W + 2 <= Xl;
-  if (fast) {
-    // every level-0 pixel under the three windows must be a byte (non-invertible
-    // pyramids leave a few out-of-range samples near the picture edges)
-    int bad = 0;
-    for (int img = 0; img < 3; img++) {
-      const int slot = img == 0 ? r0s : (img == 1 ? r1s : ps);
-      const int y0 = img == 2 ? py0 : wy[img], x0 = img == 2 ? px0 : wx[img];
-      const int span = img == 2 ? W : W + 2;
-      const int ty0 = (y0 >> l) >> 4, ty1 = min((((y0 + span - 1) >> l) + 1), q.Y - 1) >> 4;
-      const int tx0 = (x0 >> l) >> 4, tx1 = min((((x0 + span - 1) >> l) + 1), q.X - 1) >> 4;
-      const int nty = ty1 - ty0 + 1, ntx = tx1 - tx0 + 1;
-      const uint8_t *map = q.tile_bad + (long long)slot * q.tiles_per_slot;
-      for (int i = threadIdx.x; i < nty * ntx; i += NT)
-        bad |= map[(ty0 + i / ntx) * q.tiles_x + tx0 + i % ntx];
+  {
+    const int kind = classify_block<W, NT>(q, l, r0s, r1s, ps, py0, px0, wy, wx);
+    if (kind) {
+      queue_block(q, kind, pair, by, bx);
+      return;
     }
-    fast = !__syncthreads_or(bad);
-  }
-  if (!fast) {
-    if (threadIdx.x == 0) {
-      int idx = atomicAdd(q.slow_count, 1);
-      q.slow_list[idx] = (pair * q.BY + by) * q.BX + bx;
-    }
-    return;
   }
 
   const uint8_t *vP = q.v + (long long)ps * q.v_slot_stride;
@@ -337,37 +350,17 @@ __global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_tma(SubpelParams q
   const int py0 = by * W, px0 = bx * W;
   const int wy[2] = {py0 + c[MV_PREV_Y] - 1, py0 + c[MV_NEXT_Y] - 1};
   const int wx[2] = {px0 + c[MV_PREV_X] - 1, px0 + c[MV_NEXT_X] - 1};
-  const int clean = (2 * q.B + 2) << (l - 1);
-  bool fast = true;
-#pragma unroll
-  for (int d = 0; d < 2; d++)
-    fast = fast && wy[d] >= clean && wx[d] >= clean && wy[d] + W + 2 <= Yl && wx[d] + W + 2 <= Xl;
-  if (fast) {
-    int bad = 0;
-    for (int img = 0; img < 3; img++) {
-      const int slot = img == 0 ? r0s : (img == 1 ? r1s : ps);
-      const int y0 = img == 2 ? py0 : wy[img], x0 = img == 2 ? px0 : wx[img];
-      const int span = img == 2 ? W : W + 2;
-      const int ty0 = (y0 >> l) >> 4, ty1 = min((((y0 + span - 1) >> l) + 1), q.Y - 1) >> 4;
-      const int tx0 = (x0 >> l) >> 4, tx1 = min((((x0 + span - 1) >> l) + 1), q.X - 1) >> 4;
-      const int nty = ty1 - ty0 + 1, ntx = tx1 - tx0 + 1;
-      const uint8_t *map = q.tile_bad + (long long)slot * q.tiles_per_slot;
-      for (int i = threadIdx.x; i < nty * ntx; i += NT)
-        bad |= map[(ty0 + i / ntx) * q.tiles_x + tx0 + i % ntx];
-    }
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    fast = !__syncthreads_or(bad);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (!fast) {
-    if (threadIdx.x == 0) {
-      int idx = atomicAdd(q.slow_count, 1);
-      q.slow_list[idx] = (pair * q.BY + by) * q.BX + bx;
+  {
+    const int kind = classify_block<W, NT>(q, l, r0s, r1s, ps, py0, px0, wy, wx);  // contains a block barrier
+    if (kind) {
+      queue_block(q, kind, pair, by, bx);
+      return;
     }
-    return;
   }
   if (threadIdx.x == 0) {
     // TMA needs 16-byte aligned inner coordinates: fetch from wx & ~15, W + 32 bytes wide
@@ -666,33 +659,12 @@ __device__ void gen_window(const B0View &v, int slot, int l, int y0, int x0, sho
   }
 }
 
+// SAD of the W x W block against the two (W+2) x (W+2) int16 windows for the nine window
+// shifts per direction; 256 threads; result s_fin[direction * 9 + candidate].
 template <int W>
-__global__ void __launch_bounds__(256) k_subpel_exact(SubpelParams q, B0View v) {
+__device__ __forceinline__ void sad_windows(const short *Ps, const short *Rs0, const short *Rs1,
+                                            int (*s_part)[18], int *s_fin) {
   constexpr int RW = W + 2;
-  extern __shared__ short sm[];
-  short *Ps = sm;
-  short *Rs0 = Ps + W * W;
-  short *Rs1 = Rs0 + RW * RW;
-  short *tmp = Rs1 + RW * RW;  // (W/2 + 4)^2 level-1 staging
-  short *TL = tmp + (W / 2 + 4) * (W / 2 + 4);
-  short *TH = TL + (W + 2) * (W / 2 + 4);
-  short *stage = TH + (W + 2) * (W / 2 + 4);  // 4 x (W/2 + 4) x (W/2 + 4) level-0 sub-windows
-  __shared__ int s_part[8][18];
-  __shared__ int s_fin[18];
-  const int total = *q.slow_count;
-  for (int item = blockIdx.x; item < total; item += gridDim.x) {
-    const int id = q.slow_list[item];
-    const int bx = id % q.BX, by = (id / q.BX) % q.BY, pair = id / (q.BX * q.BY);
-    short c[4];
-    subpel_centre(q, pair, by, bx, c);
-    const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
-    const int py0 = by * W, px0 = bx * W;
-    gen_window<W, W>(v, ps, q.l, py0, px0, Ps, tmp, TL, TH, stage, blockDim.x);
-    __syncthreads();
-    gen_window<RW, RW>(v, r0s, q.l, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, Rs0, tmp, TL, TH, stage, blockDim.x);
-    __syncthreads();
-    gen_window<RW, RW>(v, r1s, q.l, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, Rs1, tmp, TL, TH, stage, blockDim.x);
-    __syncthreads();
     // SAD: thread = (block row, segment of SEG pixels); accumulators indexed by window shift
     constexpr int SEG = W * W / 256, SPR = W / SEG;  // 16 px x 4 segments (W=64), 4 px x 8 (W=32)
     unsigned acc[18];
@@ -737,6 +709,154 @@ __global__ void __launch_bounds__(256) k_subpel_exact(SubpelParams q, B0View v) 
       s_fin[threadIdx.x] = e;
     }
     __syncthreads();
+}
+
+// ---- strip path ----
+// Sample (y, x) of the level-l image of `slot`: polluted strips (int16), byte plane, or --
+// outside the picture -- the level-0 buffer cell the reference would read.
+__device__ __forceinline__ int level_cell(const SubpelParams &q, const B0View &v, int slot, int y, int x) {
+  const int Yl = q.Y << q.l, Xl = q.X << q.l;
+  if (y >= 0 && y < Yl && x >= 0 && x < Xl) {
+    if (y < q.clean) return q.strip_top[(long long)slot * q.strip_top_stride + (long long)y * Xl + x];
+    if (x < q.clean)
+      return q.strip_left[(long long)slot * q.strip_left_stride + (long long)(y - q.clean) * q.clean + x];
+    return q.v[(long long)slot * q.v_slot_stride + (long long)y * q.v_pitch + x];
+  }
+  return b0_cell(v, slot, y, x);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) k_subpel_strip(SubpelParams q, B0View v) {
+  constexpr int RW = W + 2;
+  extern __shared__ short sm[];
+  short *Ps = sm, *Rs0 = Ps + W * W, *Rs1 = Rs0 + RW * RW;
+  __shared__ int s_part[8][18];
+  __shared__ int s_fin[18];
+  const int total = *q.slow_count;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int id = q.slow_list[item];
+    const int bx = id % q.BX, by = (id / q.BX) % q.BY, pair = id / (q.BX * q.BY);
+    short c[4];
+    subpel_centre(q, pair, by, bx, c);
+    const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
+    const int py0 = by * W, px0 = bx * W;
+    const int wy0 = py0 + c[MV_PREV_Y] - 1, wx0 = px0 + c[MV_PREV_X] - 1;
+    const int wy1 = py0 + c[MV_NEXT_Y] - 1, wx1 = px0 + c[MV_NEXT_X] - 1;
+    for (int i = threadIdx.x; i < W * W; i += 256) Ps[i] = (short)level_cell(q, v, ps, py0 + i / W, px0 + i % W);
+    for (int i = threadIdx.x; i < RW * RW; i += 256) {
+      const int yy = i / RW, xx = i - yy * RW;
+      Rs0[i] = (short)level_cell(q, v, r0s, wy0 + yy, wx0 + xx);
+      Rs1[i] = (short)level_cell(q, v, r1s, wy1 + yy, wx1 + xx);
+    }
+    __syncthreads();
+    sad_windows<W>(Ps, Rs0, Rs1, s_part, s_fin);
+    if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
+    __syncthreads();
+  }
+}
+
+// Level-1 strips straight from the level-0 buffer (exact lifting formulas).
+// grid (rows of the level-1 image, slots): rows < clean span the whole width, the others
+// only the first `clean` columns.
+__global__ void __launch_bounds__(128) k_strip1(B0View v, short *top, long long top_stride, short *left,
+                                                long long left_stride, int clean) {
+  const int slot = blockIdx.y, y = blockIdx.x;
+  const int X1 = 2 * v.X;
+  const bool in_top = y < clean;
+  const int n = in_top ? X1 : clean;
+  short *dst = in_top ? top + slot * top_stride + (long long)y * X1
+                      : left + slot * left_stride + (long long)(y - clean) * clean;
+  for (int x = threadIdx.x; x < n; x += blockDim.x) dst[x] = (short)b1_inside(v, slot, y, x);
+}
+
+// Level-2 strips from the level-1 image (level-1 strips where polluted, V_1 bytes elsewhere):
+// zero-high-band synthesis, columns first, then rows.  Same grid shape as k_strip1.
+__global__ void __launch_bounds__(128) k_strip2(int Y, int X, const short *top1, long long top1_stride,
+                                                const short *left1, long long left1_stride, int clean1,
+                                                const uint8_t *v1, long long v1_slot_stride, int v1_pitch,
+                                                short *top, long long top_stride, short *left,
+                                                long long left_stride, int clean) {
+  const int slot = blockIdx.y, y = blockIdx.x;
+  const int X1 = 2 * X, Y2 = 4 * Y, X2 = 4 * X;
+  const short *t1 = top1 + slot * top1_stride, *l1 = left1 + slot * left1_stride;
+  const uint8_t *b1 = v1 + slot * v1_slot_stride;
+  auto B1 = [&](int yy, int xx) -> int {
+    if (yy < clean1) return t1[yy * X1 + xx];
+    if (xx < clean1) return l1[(yy - clean1) * clean1 + xx];
+    return b1[(long long)yy * v1_pitch + xx];
+  };
+  const int ya = y >> 1;
+  const bool vavg = (y & 1) && y != Y2 - 1;
+  auto T2 = [&](int xp) -> int {
+    const int a0 = B1(ya, xp);
+    return vavg ? (int)(short)tdiv2(a0 + B1(ya + 1, xp)) : a0;
+  };
+  const bool in_top = y < clean;
+  const int n = in_top ? X2 : clean;
+  short *dst = in_top ? top + slot * top_stride + (long long)y * X2
+                      : left + slot * left_stride + (long long)(y - clean) * clean;
+  for (int x = threadIdx.x; x < n; x += blockDim.x) {
+    const int a0 = T2(x >> 1);
+    dst[x] = (!(x & 1) || x == X2 - 1) ? (short)a0 : (short)tdiv2(a0 + T2((x >> 1) + 1));
+  }
+}
+
+static B0View make_b0view(const SubpelParams &q) {
+  B0View v;
+  v.p = q.b0;
+  v.Y = q.Y;
+  v.X = q.X;
+  v.B = q.B;
+  v.Bc = q.Bc;
+  v.Ya = q.Ya;
+  v.Ba = q.Ba;
+  v.size_field = q.size_field;
+  return v;
+}
+
+void launch_strips(const Launch &L, const SubpelParams &q, int level, int nslots, short *top, short *left,
+                   const short *top1, const short *left1, long long top1_stride, long long left1_stride,
+                   int clean1, const uint8_t *v1, long long v1_slot_stride, int v1_pitch) {
+  if (nslots <= 0) return;
+  dim3 grid(q.Y << level, nslots);
+  ProfScope ps_(L, KC_SEARCH_EXACT);
+  if (level == 1)
+    k_strip1<<<grid, 128, 0, L.stream>>>(make_b0view(q), top, q.strip_top_stride, left, q.strip_left_stride, q.clean);
+  else
+    k_strip2<<<grid, 128, 0, L.stream>>>(q.Y, q.X, top1, top1_stride, left1, left1_stride, clean1, v1,
+                                         v1_slot_stride, v1_pitch, top, q.strip_top_stride, left,
+                                         q.strip_left_stride, q.clean);
+  COUNT(L);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) k_subpel_exact(SubpelParams q, B0View v) {
+  constexpr int RW = W + 2;
+  extern __shared__ short sm[];
+  short *Ps = sm;
+  short *Rs0 = Ps + W * W;
+  short *Rs1 = Rs0 + RW * RW;
+  short *tmp = Rs1 + RW * RW;  // (W/2 + 4)^2 level-1 staging
+  short *TL = tmp + (W / 2 + 4) * (W / 2 + 4);
+  short *TH = TL + (W + 2) * (W / 2 + 4);
+  short *stage = TH + (W + 2) * (W / 2 + 4);  // 4 x (W/2 + 4) x (W/2 + 4) level-0 sub-windows
+  __shared__ int s_part[8][18];
+  __shared__ int s_fin[18];
+  const int total = *q.bad_count;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int id = q.bad_list[item];
+    const int bx = id % q.BX, by = (id / q.BX) % q.BY, pair = id / (q.BX * q.BY);
+    short c[4];
+    subpel_centre(q, pair, by, bx, c);
+    const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
+    const int py0 = by * W, px0 = bx * W;
+    gen_window<W, W>(v, ps, q.l, py0, px0, Ps, tmp, TL, TH, stage, blockDim.x);
+    __syncthreads();
+    gen_window<RW, RW>(v, r0s, q.l, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, Rs0, tmp, TL, TH, stage, blockDim.x);
+    __syncthreads();
+    gen_window<RW, RW>(v, r1s, q.l, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, Rs1, tmp, TL, TH, stage, blockDim.x);
+    __syncthreads();
+    sad_windows<W>(Ps, Rs0, Rs1, s_part, s_fin);
     if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
     __syncthreads();
   }
@@ -755,16 +875,19 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
       k_subpel_fast<W><<<grid, NT, 0, L.stream>>>(q);
     COUNT(L);
   }
-  B0View v;
-  v.p = q.b0;
-  v.Y = q.Y;
-  v.X = q.X;
-  v.B = q.B;
-  v.Bc = q.Bc;
-  v.Ya = q.Ya;
-  v.Ba = q.Ba;
-  v.size_field = q.size_field;
+  B0View v = make_b0view(q);
   const int RW = W + 2, TW = W / 2 + 4;
+  {
+    size_t smem1 = ((size_t)W * W + 2 * (size_t)RW * RW) * sizeof(short);
+    static size_t s_attr1 = 0;
+    if (smem1 > 48 * 1024 && smem1 > s_attr1) {
+      cudaFuncSetAttribute(k_subpel_strip<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+      s_attr1 = smem1;
+    }
+    ProfScope ps_(L, KC_SEARCH_EXACT);
+    k_subpel_strip<W><<<148 * 6, 256, smem1, L.stream>>>(q, v);
+    COUNT(L);
+  }
   size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW + (size_t)TW * TW + 2 * (size_t)RW * TW + 4 * (size_t)TW * TW) *
                 sizeof(short);
   static size_t s_attr = 0;
@@ -774,7 +897,7 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
   }
   {
     ProfScope ps_(L, KC_SEARCH_EXACT);
-    k_subpel_exact<W><<<148 * 4, 256, smem, L.stream>>>(q, v);
+    k_subpel_exact<W><<<148 * 2, 256, smem, L.stream>>>(q, v);
     COUNT(L);
   }
 }
