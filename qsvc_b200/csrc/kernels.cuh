@@ -178,6 +178,7 @@ struct PredU8Params {
   const short *mv;           // fields of the pairs
   int f0;                    // V frame index of pair 0's reference[0]
   int BY, BX, bsa, Ya, Xa, ba, padh;
+  int by0, nby;              // block rows [by0, by0 + nby) are predicted (nby == 0: all)
 };
 void launch_predict_u8(const Launch &L, const PredU8Params &q, int npairs);
 
@@ -198,6 +199,30 @@ struct LLParams {
   int smem_a, smem_b;        // filled by the launcher
 };
 void launch_ll_residue(const Launch &L, LLParams q, int npairs);
+// ---- line-based decorrelate / correlate (kernels_mcmarch.cu) ----
+struct MarchParams {
+  const uint8_t *v;          // V_a planes, [even frame][component], (Ya + 2) x v_pitch each
+  long long v_plane_stride;
+  int v_pitch;
+  int f0;                    // V frame index of pair 0's reference[0]
+  const uint8_t *tail;       // nullable: planes [pair][component] holding the prediction rows >= cy,
+  long long tail_plane_stride;  //   addressed by absolute row (pointer pre-offset), pitch v_pitch
+  const short *mv;
+  const uint8_t *in;         // analysis: odd frames; synthesis: high frames (I420, per pair)
+  long long in_stride;
+  uint8_t *out;              // analysis: high frames ('B' variant); synthesis: odd frames
+  long long out_stride;
+  uint8_t *prediction;       // nullable: prediction_<even> side output
+  long long pred_stride;
+  int *hist;                 // nullable: per pair [0,256) predicted luma, [256,512) residue + 128
+  int hist_stride;
+  const char *types;         // synthesis: frame types (device)
+  int X, Y, a, synth;
+  int BY, BX, bsa, Ya, Xa, ba, padh, cy;
+  int bs_shift, nstrips, nsegs, seg_p;  // filled by the launcher
+};
+void launch_mc_march(const Launch &L, MarchParams q, int npairs);
+
 void launch_tail_state(const Launch &L, const uint8_t *P, long long plane_stride, int pitch,
                        uint8_t *Pnext, int Ya, int Xa, int cy, int first_comp, int ncomp);
 void launch_copy_rows(const Launch &L, const uint8_t *src, uint8_t *dst, long long plane_stride,

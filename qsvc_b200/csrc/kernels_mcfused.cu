@@ -45,7 +45,7 @@ __device__ __forceinline__ unsigned load_u32_unaligned(const uint8_t *p) {
 
 // grid (BX, BY, pairs * 3); one CTA = one (block, component) of bsa x bsa samples.
 __global__ void __launch_bounds__(256) k_predict_u8(PredU8Params q) {
-  const int bx = blockIdx.x, by = blockIdx.y;
+  const int bx = blockIdx.x, by = q.by0 + blockIdx.y;
   const int pair = blockIdx.z / 3, c = blockIdx.z % 3;
   const long long plane = (long long)q.BY * q.BX;
   const short *mv = q.mv + (long long)pair * 4 * plane + (long long)by * q.BX + bx;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) k_predict_u8(PredU8Params q) {
 
 void launch_predict_u8(const Launch &L, const PredU8Params &q, int npairs) {
   if (npairs <= 0 || q.BY <= 0 || q.BX <= 0) return;
-  dim3 grid(q.BX, q.BY, npairs * 3);
+  dim3 grid(q.BX, q.nby > 0 ? q.nby : q.BY, npairs * 3);
   ProfScope ps_(L, KC_PREDICT);
   const int wpr = q.bsa >> 2;
   int threads = q.bsa >= 32 ? 256 : 64;

@@ -1,0 +1,417 @@
+// kernels_mcmarch.cu -- decorrelate / correlate as ONE line-based pass per temporal level.
+//
+// Reference pipeline per pair (decorrelate.cpp:732-861, 920-1066): predict() averages the two
+// displaced up-sampled references block by block into prediction[c] (luma size << a), the planes
+// are clipped, analysed `a` levels (chroma one more) in place with the integer 5/3 lifting
+// (dwt2d.cpp:76-119: rows, then columns, per level), and only the LL band meets the odd frame
+// (residue) or the high frame (reconstruction).
+//
+// Here nothing between the up-sampled reference bytes (V planes, k_upsample2x) and the output
+// frame touches memory.  One WARP owns a strip of 29 x 8 prediction columns (plus two halo lanes
+// on the left and one on the right) and marches down the rows:
+//   * each lane fetches its 8 prediction bytes of a row from the two displaced references
+//     (unaligned 8-byte window = three aligned words + funnel shift) and averages them with
+//     packed-byte arithmetic; blocks whose footprint leaves the picture evaluate the reference's
+//     border rule (bordered_ref_u8) per sample; rows below the last whole block come from the
+//     chained tail state (k_tail_state);
+//   * the row pass of every level exchanges one sample and one high-pass value with the
+//     neighbouring lanes by warp shuffles;
+//   * the column pass of every level is a streaming lifting step per column held in registers
+//     (state: last even sample, last odd sample, last high-pass value); level k+1 consumes the
+//     rows level k emits, so the whole multi-level LL analysis is a register pipeline;
+//   * the LL rows that fall into the warp's row segment are turned into residue / reconstruction
+//     bytes (and histograms) on the spot.
+// No shared memory (except the optional histograms), no block barriers, no intermediate planes.
+#include "kernels.cuh"
+
+#define COUNT(L) (++*(L).counter)
+#define FULL 0xffffffffu
+
+static constexpr int MARCH_HL = 2;   // halo lanes on the left  (16 columns >= 14 = reach of 3 levels)
+static constexpr int MARCH_UL = 29;  // lanes that own outputs  (232 columns per warp)
+
+__device__ __forceinline__ int tq2(int v) { return (v + (int)((unsigned)v >> 31)) >> 1; }  // C "/ 2"
+__device__ __forceinline__ int tq4(int v) { return (v + (int)((unsigned)v >> 30)) >> 2; }  // C "/ 4", |v| < 2^30
+
+__device__ __forceinline__ int bref_u8(const uint8_t *U, int pitch, int Yd, int Xd, int b, int padh, int y,
+                                       int x) {
+  // closed form of texture::alloc + fill_border (common.cuh bordered_ref) on a byte plane
+  if ((unsigned)y < (unsigned)Yd && (unsigned)x < (unsigned)Xd) return U[(long long)y * pitch + x];
+  if (b > padh) {
+    int y0 = Yd - b;
+    if (y0 != 0) {
+      if (y == y0 && x < -padh) return U[(long long)iclamp(y0 - 1, 0, Yd - 1) * pitch + Xd - 1];
+    } else if (y == -1 && x >= Xd + padh) {
+      return U[0];
+    }
+  }
+  if (y >= Yd && x < 0) return U[(long long)(Yd - 1) * pitch + Xd - 1];
+  return U[(long long)iclamp(y, 0, Yd - 1) * pitch + iclamp(x, 0, Xd - 1)];
+}
+
+// Streaming 5/3 analysis of one line of 2*half samples (5_3.cpp:39-52).  Step k consumes
+// x[2k], x[2k+1] and returns l[k-1]; step k == half is virtual and flushes l[half-1]
+// (h[half-1] = x[n-1] - x[n-2] is the generic formula with x[n] := x[n-2]); l[0] = x[0] + h[0]/2
+// is the generic formula with h[-1] := h[0].
+struct VState {
+  int e, o, hp;
+};
+__device__ __forceinline__ int vstep(VState &s, int k, int half, int xe, int xo) {
+  if (k == half) xe = s.e;
+  const int h = s.o - tq2(s.e + xe);
+  const int l = s.e + tq4(h + (k == 1 ? h : s.hp));
+  s.hp = h;
+  s.e = xe;
+  s.o = xo;
+  return l;
+}
+
+// Row pass of one level across the warp: every lane holds N consecutive samples of the row and
+// produces the N/2 low-pass samples of its columns.
+template <int N>
+__device__ __forceinline__ void hpass(const int *v, int *out, bool first, bool last) {
+  int nxt = __shfl_down_sync(FULL, v[0], 1);
+  if (last) nxt = v[N - 2];
+  int h[N / 2];
+#pragma unroll
+  for (int i = 0; i < N / 2; i++) h[i] = v[2 * i + 1] - tq2(v[2 * i] + (i + 1 < N / 2 ? v[2 * i + 2] : nxt));
+  int hp = __shfl_up_sync(FULL, h[N / 2 - 1], 1);
+  if (first) hp = h[0];
+  out[0] = v[0] + tq4(h[0] + hp);
+#pragma unroll
+  for (int i = 1; i < N / 2; i++) out[i] = v[2 * i] + tq4(h[i] + h[i - 1]);
+}
+
+// Level-0 row pass on the 8 prediction bytes of a lane.
+__device__ __forceinline__ void hpass_u8(unsigned lo, unsigned hi, int *out, bool first, bool last) {
+  const unsigned nlo = __shfl_down_sync(FULL, lo, 1);
+  int s[9];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    s[k] = (lo >> (8 * k)) & 0xff;
+    s[4 + k] = (hi >> (8 * k)) & 0xff;
+  }
+  s[8] = last ? s[6] : (int)(nlo & 0xff);
+  int h[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = s[2 * i + 1] - ((s[2 * i] + s[2 * i + 2]) >> 1);
+  int hp = __shfl_up_sync(FULL, h[3], 1);
+  if (first) hp = h[0];
+  out[0] = s[0] + tq4(h[0] + hp);
+#pragma unroll
+  for (int i = 1; i < 4; i++) out[i] = s[2 * i] + tq4(h[i] + h[i - 1]);
+}
+
+struct RawRow {
+  unsigned a0, a1, a2, b0, b1, b2;
+  int sa, sb;
+};
+
+// Eight samples V(y, x0 .. x0+7) of a bordered reference plane whose window leaves the picture
+// on the left or right (rare: edge blocks with outward vectors).
+__device__ __noinline__ uint2 bref_row8(const uint8_t *U, int pitch, int Yd, int Xd, int b, int padh, int y,
+                                        int x0) {
+  unsigned lo = 0, hi = 0;
+  for (int k = 0; k < 4; k++) {
+    lo |= (unsigned)bref_u8(U, pitch, Yd, Xd, b, padh, y, x0 + k) << (8 * k);
+    hi |= (unsigned)bref_u8(U, pitch, Yd, Xd, b, padh, y, x0 + 4 + k) << (8 * k);
+  }
+  return make_uint2(lo, hi);
+}
+
+template <int NLEV>
+struct Marcher {
+  const MarchParams &q;
+  int pair, c, x, xs, og0, og1, OW;
+  bool in_pic, first, last, owner, do_hist;
+  const uint8_t *V0, *V1, *TL, *in;
+  uint8_t *out, *pout;
+  const short *mvp;
+  int *h_pred, *h_res;
+  int is_I;
+  // block-row cache: vectors, first source column and "window inside the row" flag per reference
+  int cur_by, my0, my1, col0, col1;
+  bool xin0, xin1;
+
+  __device__ __forceinline__ Marcher(const MarchParams &qq) : q(qq) {}
+
+  // Raw words of prediction row r for this lane's 8 columns.  Lanes outside the picture read
+  // column 0 (their values never reach an owner lane).
+  __device__ __forceinline__ void fetch(int r, RawRow &w) {
+    if (r >= q.cy) {  // rows below the last whole block: chained state (A.2.6)
+      const uint2 t = __ldg(reinterpret_cast<const uint2 *>(TL + (unsigned)(r * q.v_pitch + xs)));
+      w.a0 = w.b0 = t.x;
+      w.a1 = w.b1 = t.y;
+      w.a2 = w.b2 = 0;
+      w.sa = w.sb = 0;
+      return;
+    }
+    const int by = r >> q.bs_shift;
+    if (by != cur_by) {
+      cur_by = by;
+      const int plane = q.BY * q.BX;
+      const short *m = mvp + by * q.BX + (xs >> q.bs_shift);
+      const int mx0 = in_pic ? (int)__ldg(m + MV_PREV_X * plane) : 0;
+      const int mx1 = in_pic ? (int)__ldg(m + MV_NEXT_X * plane) : 0;
+      my0 = __ldg(m + MV_PREV_Y * plane);
+      my1 = __ldg(m + MV_NEXT_Y * plane);
+      col0 = xs + mx0;
+      col1 = xs + mx1;
+      xin0 = col0 >= 0 && col0 + 8 <= q.Xa;
+      xin1 = col1 >= 0 && col1 + 8 <= q.Xa;
+    }
+    // columns inside the picture: V(y, x) = U[clamp(y)][x] (the border quirks need x < 0 or x >= Xd)
+    if (xin0) {
+      const unsigned off = (unsigned)(min(max(r + my0, 0), q.Ya - 1) * q.v_pitch + col0);
+      const unsigned *a4 = reinterpret_cast<const unsigned *>(V0 + (off & ~3u));
+      w.a0 = __ldg(a4);
+      w.a1 = __ldg(a4 + 1);
+      w.a2 = __ldg(a4 + 2);
+      w.sa = 8 * (int)(off & 3u);
+    } else {
+      const uint2 t = bref_row8(V0, q.v_pitch, q.Ya, q.Xa, q.ba, q.padh, r + my0, col0);
+      w.a0 = t.x;
+      w.a1 = t.y;
+      w.a2 = 0;
+      w.sa = 0;
+    }
+    if (xin1) {
+      const unsigned off = (unsigned)(min(max(r + my1, 0), q.Ya - 1) * q.v_pitch + col1);
+      const unsigned *b4 = reinterpret_cast<const unsigned *>(V1 + (off & ~3u));
+      w.b0 = __ldg(b4);
+      w.b1 = __ldg(b4 + 1);
+      w.b2 = __ldg(b4 + 2);
+      w.sb = 8 * (int)(off & 3u);
+    } else {
+      const uint2 t = bref_row8(V1, q.v_pitch, q.Ya, q.Xa, q.ba, q.padh, r + my1, col1);
+      w.b0 = t.x;
+      w.b1 = t.y;
+      w.b2 = 0;
+      w.sb = 0;
+    }
+  }
+
+  static __device__ __forceinline__ void combine(const RawRow &w, unsigned &lo, unsigned &hi) {
+    // (r0 + r1) / 2 on bytes; the [0,255] clip of decorrelate.cpp:841-848 is a no-op
+    lo = __vhaddu4(__funnelshift_r(w.a0, w.a1, w.sa), __funnelshift_r(w.b0, w.b1, w.sb));
+    hi = __vhaddu4(__funnelshift_r(w.a1, w.a2, w.sa), __funnelshift_r(w.b1, w.b2, w.sb));
+  }
+
+  // NOUT = 8 >> NLEV consecutive LL samples of output row e (component resolution)
+  template <int NOUT>
+  __device__ __forceinline__ void out_row(int e, const int *p) {
+    if (e < og0 || e >= og1 || !owner) return;
+    const long long idx = (long long)e * OW + (x >> NLEV);
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+      const int s = in[idx + k];
+      int o;
+      if (!q.synth) {
+        int rr = s - p[k];
+        rr = rr < -128 ? -128 : (rr > 127 ? 127 : rr);
+        o = rr + 128;
+        if (do_hist) {
+          atomicAdd(&h_pred[s], 1);
+          atomicAdd(&h_res[o], 1);
+        }
+      } else if (is_I) {
+        o = s;
+      } else {
+        o = s - 128 + p[k];
+        o = o < 0 ? 0 : (o > 255 ? 255 : o);
+      }
+      out[idx + k] = (uint8_t)o;
+      if (pout) pout[idx + k] = (uint8_t)p[k];
+    }
+  }
+
+  __device__ void run(int seg) {
+    const int half1 = q.Ya >> 1, half2 = q.Ya >> 2, half3 = q.Ya >> 3;
+    cur_by = -1;
+    my0 = my1 = col0 = col1 = 0;
+    xin0 = xin1 = true;
+    if (NLEV == 0) {
+      for (int r = og0; r < og1; r++) {
+        RawRow w;
+        fetch(r, w);
+        unsigned lo, hi;
+        combine(w, lo, hi);
+        int p[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          p[k] = (lo >> (8 * k)) & 0xff;
+          p[4 + k] = (hi >> (8 * k)) & 0xff;
+        }
+        out_row<8>(r, p);
+      }
+      return;
+    }
+    int t0, t_last;
+    if (NLEV == 1) {
+      t0 = max(0, og0 - 1);
+      t_last = og1;
+    } else if (NLEV == 2) {
+      t0 = max(0, (og0 - 2) * 2);
+      t_last = 2 * (og1 - 1) + 4;
+    } else {
+      t0 = max(0, (og0 - 2) * 4);
+      t_last = 4 * (og1 - 1) + 10;
+    }
+    t_last = min(t_last, half1);
+    VState s1[4], s2[2], s3[1];
+    int st1[2], st2[1];
+#pragma unroll
+    for (int i = 0; i < 4; i++) s1[i].e = s1[i].o = s1[i].hp = 0;
+    s2[0] = s2[1] = s3[0] = s1[0];
+    st1[0] = st1[1] = st2[0] = 0;
+
+    RawRow n0, n1;
+    fetch(2 * t0, n0);
+    fetch(2 * t0 + 1, n1);
+    const int t_fetch = min(t_last, half1 - 1);  // last step that reads rows
+#pragma unroll 1
+    for (int t = t0; t <= t_last; t++) {
+      int xe[4] = {0, 0, 0, 0}, xo[4] = {0, 0, 0, 0};
+      if (t < half1) {
+        unsigned lo0, hi0, lo1, hi1;
+        combine(n0, lo0, hi0);
+        combine(n1, lo1, hi1);
+        if (t < t_fetch) {  // rows of the next step are in flight while this one is computed
+          fetch(2 * t + 2, n0);
+          fetch(2 * t + 3, n1);
+        }
+        hpass_u8(lo0, hi0, xe, first, last);
+        hpass_u8(lo1, hi1, xo, first, last);
+      }
+      int a[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = vstep(s1[i], t, half1, xe[i], xo[i]);
+      const int e1 = t - 1;  // LL1 row just completed
+      if (NLEV == 1) {
+        out_row<4>(e1, a);
+        continue;
+      }
+      if (!(e1 & 1)) {  // even row of the level-1 image: keep its row-passed form
+        hpass<4>(a, st1, first, last);
+        continue;
+      }
+      int x2o[2];
+      hpass<4>(a, x2o, first, last);
+      const int j = (e1 - 1) >> 1;
+#pragma unroll 1
+      for (int rep = 0; rep < 2; rep++) {  // rep 1: virtual step after the last real one
+        if (rep == 1 && j != half2 - 1) break;
+        const int jj = j + rep;
+        int b[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) b[i] = vstep(s2[i], jj, half2, st1[i], x2o[i]);
+        const int e2 = jj - 1;  // LL2 row just completed
+        if (NLEV == 2) {
+          out_row<2>(e2, b);
+          continue;
+        }
+        if (!(e2 & 1)) {
+          hpass<2>(b, st2, first, last);
+          continue;
+        }
+        int x3o[1];
+        hpass<2>(b, x3o, first, last);
+        const int i3 = (e2 - 1) >> 1;
+#pragma unroll 1
+        for (int rep3 = 0; rep3 < 2; rep3++) {
+          if (rep3 == 1 && i3 != half3 - 1) break;
+          const int ii = i3 + rep3;
+          int cc[1];
+          cc[0] = vstep(s3[0], ii, half3, st2[0], x3o[0]);
+          out_row<1>(ii - 1, cc);
+        }
+      }
+    }
+  }
+};
+
+template <int NLEV>
+__device__ __forceinline__ void mc_march(const MarchParams &q, int pair, int c, int strip, int seg, int *h_pred,
+                                         int *h_res, bool do_hist) {
+  Marcher<NLEV> m(q);
+  const int lane = threadIdx.x & 31;
+  m.pair = pair;
+  m.c = c;
+  m.x = (strip * MARCH_UL - MARCH_HL + lane) * 8;
+  m.in_pic = m.x >= 0 && m.x < q.Xa;
+  m.xs = m.in_pic ? m.x : 0;
+  m.first = m.x == 0;
+  m.last = m.x + 8 == q.Xa;
+  m.owner = m.in_pic && lane >= MARCH_HL && lane < MARCH_HL + MARCH_UL;
+  m.do_hist = do_hist;
+  m.OW = c ? q.X >> 1 : q.X;
+  const int OH = q.Ya >> NLEV;
+  m.og0 = (int)(((long long)seg * q.seg_p) >> NLEV);
+  m.og1 = min(OH, (int)(((long long)(seg + 1) * q.seg_p) >> NLEV));
+  if (m.og0 >= m.og1) return;
+  m.V0 = q.v + ((long long)(q.f0 + pair) * 3 + c) * q.v_plane_stride;
+  m.V1 = m.V0 + 3 * q.v_plane_stride;
+  m.TL = q.tail ? q.tail + ((long long)pair * 3 + c) * q.tail_plane_stride : nullptr;
+  m.mvp = q.mv + (long long)pair * 4 * q.BY * q.BX;
+  const long long coff = c == 0 ? 0 : (long long)q.X * q.Y + (long long)(c - 1) * (q.X / 2) * (q.Y / 2);
+  m.in = q.in + (long long)pair * q.in_stride + coff;
+  m.out = q.out + (long long)pair * q.out_stride + coff;
+  m.pout = q.prediction ? q.prediction + (long long)pair * q.pred_stride + coff : nullptr;
+  m.h_pred = h_pred;
+  m.h_res = h_res;
+  m.is_I = q.synth && q.types[pair] == 'I';
+  m.run(seg);
+}
+
+// grid (ceil(nstrips * nsegs / 4), nc * pairs), 128 threads: one warp = one (strip, segment) of
+// component c0 + blockIdx.y % nc (luma and chroma have different level counts: two launches)
+template <int NLEV>
+__global__ void __launch_bounds__(128, 4) k_mc_march(MarchParams q, int c0, int nc) {
+  __shared__ int h_pred[256], h_res[256];
+  const int pair = blockIdx.y / nc, c = c0 + blockIdx.y % nc;
+  const bool do_hist = q.hist && c == 0 && !q.synth;
+  if (do_hist) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h_pred[i] = h_res[i] = 0;
+    __syncthreads();
+  }
+  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int strip = idx % q.nstrips, seg = idx / q.nstrips;
+  if (seg < q.nsegs) mc_march<NLEV>(q, pair, c, strip, seg, h_pred, h_res, do_hist);
+  if (do_hist) {
+    __syncthreads();
+    int *hist = q.hist + (long long)pair * q.hist_stride;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+      if (h_pred[i]) atomicAdd(&hist[i], h_pred[i]);
+      if (h_res[i]) atomicAdd(&hist[256 + i], h_res[i]);
+    }
+  }
+}
+
+template <int NLEV>
+static void launch_march_n(const Launch &L, const MarchParams &q, int npairs, int c0, int nc) {
+  dim3 grid((q.nstrips * q.nsegs + 3) / 4, nc * npairs);
+  ProfScope ps_(L, KC_RESIDUE);
+  k_mc_march<NLEV><<<grid, 128, 0, L.stream>>>(q, c0, nc);
+  COUNT(L);
+}
+
+void launch_mc_march(const Launch &L, MarchParams q, int npairs) {
+  if (npairs <= 0) return;
+  q.bs_shift = 0;
+  while ((1 << q.bs_shift) < q.bsa) q.bs_shift++;
+  q.nstrips = (q.Xa + 8 * MARCH_UL - 1) / (8 * MARCH_UL);
+  // enough warps to fill the machine several times over, segments as tall as that allows
+  const long long cols = (long long)npairs * 3 * q.nstrips;
+  long long want = (148LL * 20 * 8 + cols - 1) / cols;
+  int seg_p = (int)((q.Ya + want - 1) / want);
+  seg_p = (seg_p + 7) & ~7;
+  if (seg_p < 64) seg_p = 64;
+  if (seg_p > 512) seg_p = 512;
+  q.seg_p = seg_p;
+  q.nsegs = (q.Ya + seg_p - 1) / seg_p;
+  switch (q.a) {
+    case 0: launch_march_n<0>(L, q, npairs, 0, 1); launch_march_n<1>(L, q, npairs, 1, 2); break;
+    case 1: launch_march_n<1>(L, q, npairs, 0, 1); launch_march_n<2>(L, q, npairs, 1, 2); break;
+    default: launch_march_n<2>(L, q, npairs, 0, 1); launch_march_n<3>(L, q, npairs, 1, 2); break;
+  }
+}
