@@ -28,7 +28,8 @@
 #define FULL 0xffffffffu
 
 static constexpr int MARCH_HL = 2;   // halo lanes on the left  (16 columns >= 14 = reach of 3 levels)
-static constexpr int MARCH_UL = 29;  // lanes that own outputs  (232 columns per warp)
+static constexpr int MARCH_UL = 29;
+static constexpr int MARCH_PF = 6;   // L2 prefetch distance in steps (two prediction rows each)  // lanes that own outputs  (232 columns per warp)
 
 __device__ __forceinline__ int tq2(int v) { return (v + (int)((unsigned)v >> 31)) >> 1; }  // C "/ 2"
 __device__ __forceinline__ int tq4(int v) { return (v + (int)((unsigned)v >> 30)) >> 2; }  // C "/ 4", |v| < 2^30
@@ -52,14 +53,15 @@ __device__ __forceinline__ int bref_u8(const uint8_t *U, int pitch, int Yd, int 
 // Streaming 5/3 analysis of one line of 2*half samples (5_3.cpp:39-52).  Step k consumes
 // x[2k], x[2k+1] and returns l[k-1]; step k == half is virtual and flushes l[half-1]
 // (h[half-1] = x[n-1] - x[n-2] is the generic formula with x[n] := x[n-2]); l[0] = x[0] + h[0]/2
-// is the generic formula with h[-1] := h[0].
+// is the generic formula with h[-1] := h[0].  SP = false: the caller knows 1 < k < half.
 struct VState {
   int e, o, hp;
 };
+template <bool SP>
 __device__ __forceinline__ int vstep(VState &s, int k, int half, int xe, int xo) {
-  if (k == half) xe = s.e;
+  if (SP && k == half) xe = s.e;
   const int h = s.o - tq2(s.e + xe);
-  const int l = s.e + tq4(h + (k == 1 ? h : s.hp));
+  const int l = s.e + tq4(h + ((SP && k == 1) ? h : s.hp));
   s.hp = h;
   s.e = xe;
   s.o = xo;
@@ -102,9 +104,10 @@ __device__ __forceinline__ void hpass_u8(unsigned lo, unsigned hi, int *out, boo
   for (int i = 1; i < 4; i++) out[i] = s[2 * i] + tq4(h[i] + h[i - 1]);
 }
 
-struct RawRow {
-  unsigned a0, a1, a2, b0, b1, b2;
-  int sa, sb;
+// Raw words of the two prediction rows of one step (both rows lie in the same block row).
+struct RawPair {
+  unsigned a[6], b[6];  // [row][word]: three aligned words per row and reference
+  int sa, sb;           // funnel shifts (bits) that align them
 };
 
 // Eight samples V(y, x0 .. x0+7) of a bordered reference plane whose window leaves the picture
@@ -119,98 +122,193 @@ __device__ __noinline__ uint2 bref_row8(const uint8_t *U, int pitch, int Yd, int
   return make_uint2(lo, hi);
 }
 
-template <int NLEV>
+// EXTRA: histograms and / or the prediction side output are requested
+template <int NLEV, bool EXTRA>
 struct Marcher {
   const MarchParams &q;
   int pair, c, x, xs, og0, og1, OW;
   bool in_pic, first, last, owner, do_hist;
-  const uint8_t *V0, *V1, *TL, *in;
-  uint8_t *out, *pout;
-  const short *mvp;
+  const uint8_t *in;
+  uint8_t *out;
   int *h_pred, *h_res;
   int is_I;
-  // block-row cache: vectors, first source column and "window inside the row" flag per reference
-  int cur_by, my0, my1, col0, col1;
-  bool xin0, xin1;
+  unsigned in_pre;  // input bytes of output row in_pre_row, loaded one output row ahead
+  int in_pre_row;
+  // plane pointers are recomputed where the (rare) general paths need them
+  __device__ __forceinline__ const uint8_t *V0() const {
+    return q.v + ((long long)(q.f0 + pair) * 3 + c) * q.v_plane_stride;
+  }
+  __device__ __forceinline__ const uint8_t *V1() const { return V0() + 3 * q.v_plane_stride; }
+  __device__ __forceinline__ const uint8_t *TL() const {
+    return q.tail + ((long long)pair * 3 + c) * q.tail_plane_stride;
+  }
+  __device__ __forceinline__ uint8_t *pout() const {
+    if (!EXTRA || !q.prediction) return nullptr;
+    const long long coff = c == 0 ? 0 : (long long)q.X * q.Y + (long long)(c - 1) * (q.X / 2) * (q.Y / 2);
+    return q.prediction + (long long)pair * q.pred_stride + coff;
+  }
+  // block-row cache
+  int cur_by, my0, my1, col0, col1, sa, sb;
+  bool xin0, xin1, fastrow;
+  const unsigned *pa, *pb;  // fastrow: word pointers of prediction row 0 in the two references
+  // lifting pipeline
+  int half1, half2, half3, t_fetch;
+  VState s1[4], s2[2], s3[1];
+  int st1[2], st2[1];
+  RawPair nx;
 
   __device__ __forceinline__ Marcher(const MarchParams &qq) : q(qq) {}
 
-  // Raw words of prediction row r for this lane's 8 columns.  Lanes outside the picture read
-  // column 0 (their values never reach an owner lane).
-  __device__ __forceinline__ void fetch(int r, RawRow &w) {
-    if (r >= q.cy) {  // rows below the last whole block: chained state (A.2.6)
-      const uint2 t = __ldg(reinterpret_cast<const uint2 *>(TL + (unsigned)(r * q.v_pitch + xs)));
-      w.a0 = w.b0 = t.x;
-      w.a1 = w.b1 = t.y;
-      w.a2 = w.b2 = 0;
-      w.sa = w.sb = 0;
-      return;
-    }
-    const int by = r >> q.bs_shift;
-    if (by != cur_by) {
-      cur_by = by;
-      const int plane = q.BY * q.BX;
-      const short *m = mvp + by * q.BX + (xs >> q.bs_shift);
-      const int mx0 = in_pic ? (int)__ldg(m + MV_PREV_X * plane) : 0;
-      const int mx1 = in_pic ? (int)__ldg(m + MV_NEXT_X * plane) : 0;
+  __device__ __forceinline__ void new_block_row(int by) {
+    cur_by = by;
+    const int plane = q.BY * q.BX;
+    const short *m = q.mv + (long long)pair * 4 * plane + by * q.BX + (xs >> q.bs_shift);
+    int mx0 = 0, mx1 = 0;
+    my0 = my1 = 0;
+    if (in_pic) {  // lanes outside the picture read column 0 undisplaced (values never used)
+      mx0 = __ldg(m + MV_PREV_X * plane);
       my0 = __ldg(m + MV_PREV_Y * plane);
+      mx1 = __ldg(m + MV_NEXT_X * plane);
       my1 = __ldg(m + MV_NEXT_Y * plane);
-      col0 = xs + mx0;
-      col1 = xs + mx1;
-      xin0 = col0 >= 0 && col0 + 8 <= q.Xa;
-      xin1 = col1 >= 0 && col1 + 8 <= q.Xa;
     }
-    // columns inside the picture: V(y, x) = U[clamp(y)][x] (the border quirks need x < 0 or x >= Xd)
+    col0 = xs + mx0;
+    col1 = xs + mx1;
+    xin0 = col0 >= 0 && col0 + 8 <= q.Xa;
+    xin1 = col1 >= 0 && col1 + 8 <= q.Xa;
+    const int y0 = by << q.bs_shift, y1 = min(y0 + q.bsa, q.cy) - 1;
+    const bool noclamp = y0 + my0 >= 0 && y1 + my0 < q.Ya && y0 + my1 >= 0 && y1 + my1 < q.Ya;
+    fastrow = __all_sync(FULL, xin0 && xin1 && noclamp);
+    const int o0 = my0 * q.v_pitch + col0, o1 = my1 * q.v_pitch + col1;  // pitch % 4 == 0
+    sa = 8 * (o0 & 3);
+    sb = 8 * (o1 & 3);
+    pa = reinterpret_cast<const unsigned *>(V0() + (o0 & ~3));
+    pb = reinterpret_cast<const unsigned *>(V1() + (o1 & ~3));
+  }
+
+  // One row, any case.  Columns inside the picture: V(y, x) = U[clamp(y)][x] (the border quirks
+  // of texture::fill_border need x < 0 or x >= Xd); otherwise the closed-form border rule.
+  __device__ __forceinline__ void fetch_row_general(int r, unsigned *a, unsigned *b) {
     if (xin0) {
       const unsigned off = (unsigned)(min(max(r + my0, 0), q.Ya - 1) * q.v_pitch + col0);
-      const unsigned *a4 = reinterpret_cast<const unsigned *>(V0 + (off & ~3u));
-      w.a0 = __ldg(a4);
-      w.a1 = __ldg(a4 + 1);
-      w.a2 = __ldg(a4 + 2);
-      w.sa = 8 * (int)(off & 3u);
+      const unsigned *a4 = reinterpret_cast<const unsigned *>(V0() + (off & ~3u));
+      a[0] = __ldg(a4);
+      a[1] = __ldg(a4 + 1);
+      a[2] = __ldg(a4 + 2);
     } else {
-      const uint2 t = bref_row8(V0, q.v_pitch, q.Ya, q.Xa, q.ba, q.padh, r + my0, col0);
-      w.a0 = t.x;
-      w.a1 = t.y;
-      w.a2 = 0;
-      w.sa = 0;
+      const uint2 t = bref_row8(V0(), q.v_pitch, q.Ya, q.Xa, q.ba, q.padh, r + my0, col0);
+      a[0] = t.x;
+      a[1] = t.y;
+      a[2] = 0;
     }
     if (xin1) {
       const unsigned off = (unsigned)(min(max(r + my1, 0), q.Ya - 1) * q.v_pitch + col1);
-      const unsigned *b4 = reinterpret_cast<const unsigned *>(V1 + (off & ~3u));
-      w.b0 = __ldg(b4);
-      w.b1 = __ldg(b4 + 1);
-      w.b2 = __ldg(b4 + 2);
-      w.sb = 8 * (int)(off & 3u);
+      const unsigned *b4 = reinterpret_cast<const unsigned *>(V1() + (off & ~3u));
+      b[0] = __ldg(b4);
+      b[1] = __ldg(b4 + 1);
+      b[2] = __ldg(b4 + 2);
     } else {
-      const uint2 t = bref_row8(V1, q.v_pitch, q.Ya, q.Xa, q.ba, q.padh, r + my1, col1);
-      w.b0 = t.x;
-      w.b1 = t.y;
-      w.b2 = 0;
-      w.sb = 0;
+      const uint2 t = bref_row8(V1(), q.v_pitch, q.Ya, q.Xa, q.ba, q.padh, r + my1, col1);
+      b[0] = t.x;
+      b[1] = t.y;
+      b[2] = 0;
     }
   }
 
-  static __device__ __forceinline__ void combine(const RawRow &w, unsigned &lo, unsigned &hi) {
-    // (r0 + r1) / 2 on bytes; the [0,255] clip of decorrelate.cpp:841-848 is a no-op
-    lo = __vhaddu4(__funnelshift_r(w.a0, w.a1, w.sa), __funnelshift_r(w.b0, w.b1, w.sb));
-    hi = __vhaddu4(__funnelshift_r(w.a1, w.a2, w.sa), __funnelshift_r(w.b1, w.b2, w.sb));
+  // fastrow: every lane's windows of this block row lie inside the picture
+  template <bool PF>
+  __device__ __forceinline__ void fetch2_fast(int r, RawPair &w) {
+    const unsigned pw = (unsigned)q.v_pitch >> 2;
+    const unsigned *a4 = pa + r * pw, *b4 = pb + r * pw;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      w.a[k] = __ldg(a4 + k);
+      w.a[3 + k] = __ldg(a4 + pw + k);
+      w.b[k] = __ldg(b4 + k);
+      w.b[3 + k] = __ldg(b4 + pw + k);
+    }
+    // pull the rows MARCH_PF steps further down into L2 (same vectors assumed: a hint only;
+    // the planes have Ya + 2 rows and the caller stays MARCH_PF steps away from the last row)
+    if (PF) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a4 + 2 * MARCH_PF * pw));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a4 + (2 * MARCH_PF + 1) * pw));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(b4 + 2 * MARCH_PF * pw));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(b4 + (2 * MARCH_PF + 1) * pw));
+    }
+  }
+
+  // Raw words of prediction rows r, r + 1 (r even) for this lane's 8 columns.
+  __device__ __forceinline__ void fetch2(int r, RawPair &w) {
+    if (r >= q.cy) {  // rows below the last whole block: chained state (A.2.6)
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2 *>(TL() + (unsigned)((r + k) * q.v_pitch + xs)));
+        w.a[3 * k] = w.b[3 * k] = t.x;
+        w.a[3 * k + 1] = w.b[3 * k + 1] = t.y;
+        w.a[3 * k + 2] = w.b[3 * k + 2] = 0;
+      }
+      w.sa = w.sb = 0;
+      fastrow = false;
+      return;
+    }
+    const int by = r >> q.bs_shift;
+    if (by != cur_by) new_block_row(by);
+    if (fastrow) {
+      fetch2_fast<false>(r, w);
+      w.sa = sa;
+      w.sb = sb;
+    } else {
+      fetch_row_general(r, w.a, w.b);
+      fetch_row_general(r + 1, w.a + 3, w.b + 3);
+      w.sa = xin0 ? sa : 0;
+      w.sb = xin1 ? sb : 0;
+    }
+  }
+
+  // (r0 + r1) / 2 on bytes; the [0,255] clip of decorrelate.cpp:841-848 is a no-op
+  static __device__ __forceinline__ void combine(const RawPair &w, int k, unsigned &lo, unsigned &hi) {
+    lo = __vhaddu4(__funnelshift_r(w.a[3 * k], w.a[3 * k + 1], w.sa), __funnelshift_r(w.b[3 * k], w.b[3 * k + 1], w.sb));
+    hi = __vhaddu4(__funnelshift_r(w.a[3 * k + 1], w.a[3 * k + 2], w.sa),
+                   __funnelshift_r(w.b[3 * k + 1], w.b[3 * k + 2], w.sb));
+  }
+
+  // the NOUT <= 4 input bytes of this lane in output row e
+  template <int NOUT>
+  __device__ __forceinline__ unsigned load_in(int e) const {
+    if (!owner) return 0;
+    const uint8_t *p = in + (long long)e * OW + (x >> NLEV);
+    if (NOUT == 1) return *p;
+    if (NOUT == 2) return *reinterpret_cast<const unsigned short *>(p);
+    return *reinterpret_cast<const unsigned *>(p);
   }
 
   // NOUT = 8 >> NLEV consecutive LL samples of output row e (component resolution)
   template <int NOUT>
   __device__ __forceinline__ void out_row(int e, const int *p) {
-    if (e < og0 || e >= og1 || !owner) return;
-    const long long idx = (long long)e * OW + (x >> NLEV);
+    if (e < og0 || e >= og1) return;
+    unsigned sw[2] = {0, 0}, ow[2] = {0, 0}, pw[2] = {0, 0};
+    if (NOUT == 8) {
+      if (owner) {
+        const uint2 t = *reinterpret_cast<const uint2 *>(in + (long long)e * OW + x);
+        sw[0] = t.x;
+        sw[1] = t.y;
+      }
+    } else {
+      sw[0] = in_pre_row == e ? in_pre : load_in<NOUT>(e);
+      if (e + 1 < og1) {  // the next output row's input is in flight until it is needed
+        in_pre = load_in<NOUT>(e + 1);
+        in_pre_row = e + 1;
+      }
+    }
+    if (!owner) return;
 #pragma unroll
     for (int k = 0; k < NOUT; k++) {
-      const int s = in[idx + k];
+      const int s = (sw[k >> 2] >> (8 * (k & 3))) & 0xff;
       int o;
       if (!q.synth) {
         int rr = s - p[k];
         rr = rr < -128 ? -128 : (rr > 127 ? 127 : rr);
         o = rr + 128;
-        if (do_hist) {
+        if (EXTRA && do_hist) {
           atomicAdd(&h_pred[s], 1);
           atomicAdd(&h_res[o], 1);
         }
@@ -220,22 +318,117 @@ struct Marcher {
         o = s - 128 + p[k];
         o = o < 0 ? 0 : (o > 255 ? 255 : o);
       }
-      out[idx + k] = (uint8_t)o;
-      if (pout) pout[idx + k] = (uint8_t)p[k];
+      ow[k >> 2] |= (unsigned)o << (8 * (k & 3));
+      pw[k >> 2] |= (unsigned)(p[k] & 0xff) << (8 * (k & 3));
+    }
+    const long long idx = (long long)e * OW + (x >> NLEV);
+    uint8_t *po = pout();
+    if (NOUT == 1) {
+      out[idx] = (uint8_t)ow[0];
+      if (po) po[idx] = (uint8_t)pw[0];
+    } else if (NOUT == 2) {
+      *reinterpret_cast<unsigned short *>(out + idx) = (unsigned short)ow[0];
+      if (po) *reinterpret_cast<unsigned short *>(po + idx) = (unsigned short)pw[0];
+    } else if (NOUT == 4) {
+      *reinterpret_cast<unsigned *>(out + idx) = ow[0];
+      if (po) *reinterpret_cast<unsigned *>(po + idx) = pw[0];
+    } else {
+      *reinterpret_cast<uint2 *>(out + idx) = make_uint2(ow[0], ow[1]);
+      if (po) *reinterpret_cast<uint2 *>(po + idx) = make_uint2(pw[0], pw[1]);
     }
   }
 
-  __device__ void run(int seg) {
-    const int half1 = q.Ya >> 1, half2 = q.Ya >> 2, half3 = q.Ya >> 3;
+  // One step t of the pipeline: prediction rows 2t, 2t+1 enter level 1; every level emits the
+  // row it completes into the next one.  SP = true handles the first outputs of a line and the
+  // virtual steps at its end; PH = t & 3 when known at compile time (-1 otherwise); FAST_FETCH:
+  // the rows of step t + 1 lie in the current block row and that block row is `fastrow`.
+  template <bool SP, int PH, bool FAST_FETCH>
+  __device__ __forceinline__ void step(int t) {
+    int xe[4] = {0, 0, 0, 0}, xo[4] = {0, 0, 0, 0};
+    if (!SP || t < half1) {
+      unsigned lo0, hi0, lo1, hi1;
+      combine(nx, 0, lo0, hi0);
+      combine(nx, 1, lo1, hi1);
+      // rows of the next step are in flight while this one is computed
+      if (FAST_FETCH) fetch2_fast<true>(2 * t + 2, nx);
+      else if (!SP || t < t_fetch) fetch2(2 * t + 2, nx);
+      hpass_u8(lo0, hi0, xe, first, last);
+      hpass_u8(lo1, hi1, xo, first, last);
+    }
+    int a[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = vstep<SP>(s1[i], t, half1, xe[i], xo[i]);
+    const int e1 = t - 1;  // LL1 row just completed
+    if (NLEV == 1) {
+      out_row<4>(e1, a);
+      return;
+    }
+    const bool e1_odd = PH >= 0 ? !(PH & 1) : (e1 & 1);
+    if (!e1_odd) {  // even row of the level-1 image: keep its row-passed form
+      hpass<4>(a, st1, first, last);
+      return;
+    }
+    int x2o[2];
+    hpass<4>(a, x2o, first, last);
+    const int j = (e1 - 1) >> 1;
+#pragma unroll 1
+    for (int rep = 0; rep < (SP ? 2 : 1); rep++) {  // rep 1: virtual step after the last real one
+      if (rep == 1 && j != half2 - 1) break;
+      const int jj = j + rep;
+      int b[2];
+#pragma unroll
+      for (int i = 0; i < 2; i++) b[i] = vstep<SP>(s2[i], jj, half2, st1[i], x2o[i]);
+      const int e2 = jj - 1;  // LL2 row just completed
+      if (NLEV == 2) {
+        out_row<2>(e2, b);
+        continue;
+      }
+      const bool e2_odd = (PH >= 0 && !SP) ? (PH == 2) : (e2 & 1);
+      if (!e2_odd) {
+        hpass<2>(b, st2, first, last);
+        continue;
+      }
+      int x3o[1];
+      hpass<2>(b, x3o, first, last);
+      const int i3 = (e2 - 1) >> 1;
+#pragma unroll 1
+      for (int rep3 = 0; rep3 < (SP ? 2 : 1); rep3++) {
+        if (rep3 == 1 && i3 != half3 - 1) break;
+        const int ii = i3 + rep3;
+        int cc[1];
+        cc[0] = vstep<SP>(s3[0], ii, half3, st2[0], x3o[0]);
+        out_row<1>(ii - 1, cc);
+      }
+    }
+  }
+
+  __device__ void run() {
+    half1 = q.Ya >> 1;
+    half2 = q.Ya >> 2;
+    half3 = q.Ya >> 3;
     cur_by = -1;
-    my0 = my1 = col0 = col1 = 0;
+    in_pre = 0;
+    in_pre_row = -1 << 30;
+    my0 = my1 = col0 = col1 = sa = sb = 0;
     xin0 = xin1 = true;
+    fastrow = false;
+    pa = pb = nullptr;
     if (NLEV == 0) {
       for (int r = og0; r < og1; r++) {
-        RawRow w;
-        fetch(r, w);
         unsigned lo, hi;
-        combine(w, lo, hi);
+        if (r >= q.cy) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2 *>(TL() + (unsigned)(r * q.v_pitch + xs)));
+          lo = t.x;
+          hi = t.y;
+        } else {
+          const int by = r >> q.bs_shift;
+          if (by != cur_by) new_block_row(by);
+          fetch_row_general(r, nx.a, nx.b);
+          nx.a[3] = nx.a[4] = nx.a[5] = nx.b[3] = nx.b[4] = nx.b[5] = 0;
+          nx.sa = xin0 ? sa : 0;
+          nx.sb = xin1 ? sb : 0;
+          combine(nx, 0, lo, hi);
+        }
         int p[8];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -258,82 +451,37 @@ struct Marcher {
       t_last = 4 * (og1 - 1) + 10;
     }
     t_last = min(t_last, half1);
-    VState s1[4], s2[2], s3[1];
-    int st1[2], st2[1];
+    t_fetch = min(t_last, half1 - 1);  // last step that reads rows
 #pragma unroll
     for (int i = 0; i < 4; i++) s1[i].e = s1[i].o = s1[i].hp = 0;
     s2[0] = s2[1] = s3[0] = s1[0];
     st1[0] = st1[1] = st2[0] = 0;
-
-    RawRow n0, n1;
-    fetch(2 * t0, n0);
-    fetch(2 * t0 + 1, n1);
-    const int t_fetch = min(t_last, half1 - 1);  // last step that reads rows
+    fetch2(2 * t0, nx);
+    // Steps 0..10 of a line produce the first output of some level (SP).  Groups of four
+    // regular steps starting at a multiple of four run unrolled: their rows 8u .. 8u+7 lie in one
+    // block row (block sizes are multiples of 8 rows), only the fetch for step 4u+4 can enter a
+    // new one.
+    const bool can4 = q.bs_shift >= 3;
 #pragma unroll 1
-    for (int t = t0; t <= t_last; t++) {
-      int xe[4] = {0, 0, 0, 0}, xo[4] = {0, 0, 0, 0};
-      if (t < half1) {
-        unsigned lo0, hi0, lo1, hi1;
-        combine(n0, lo0, hi0);
-        combine(n1, lo1, hi1);
-        if (t < t_fetch) {  // rows of the next step are in flight while this one is computed
-          fetch(2 * t + 2, n0);
-          fetch(2 * t + 3, n1);
-        }
-        hpass_u8(lo0, hi0, xe, first, last);
-        hpass_u8(lo1, hi1, xo, first, last);
-      }
-      int a[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = vstep(s1[i], t, half1, xe[i], xo[i]);
-      const int e1 = t - 1;  // LL1 row just completed
-      if (NLEV == 1) {
-        out_row<4>(e1, a);
-        continue;
-      }
-      if (!(e1 & 1)) {  // even row of the level-1 image: keep its row-passed form
-        hpass<4>(a, st1, first, last);
-        continue;
-      }
-      int x2o[2];
-      hpass<4>(a, x2o, first, last);
-      const int j = (e1 - 1) >> 1;
-#pragma unroll 1
-      for (int rep = 0; rep < 2; rep++) {  // rep 1: virtual step after the last real one
-        if (rep == 1 && j != half2 - 1) break;
-        const int jj = j + rep;
-        int b[2];
-#pragma unroll
-        for (int i = 0; i < 2; i++) b[i] = vstep(s2[i], jj, half2, st1[i], x2o[i]);
-        const int e2 = jj - 1;  // LL2 row just completed
-        if (NLEV == 2) {
-          out_row<2>(e2, b);
-          continue;
-        }
-        if (!(e2 & 1)) {
-          hpass<2>(b, st2, first, last);
-          continue;
-        }
-        int x3o[1];
-        hpass<2>(b, x3o, first, last);
-        const int i3 = (e2 - 1) >> 1;
-#pragma unroll 1
-        for (int rep3 = 0; rep3 < 2; rep3++) {
-          if (rep3 == 1 && i3 != half3 - 1) break;
-          const int ii = i3 + rep3;
-          int cc[1];
-          cc[0] = vstep(s3[0], ii, half3, st2[0], x3o[0]);
-          out_row<1>(ii - 1, cc);
-        }
+    for (int t = t0; t <= t_last;) {
+      if (can4 && fastrow && !(t & 3) && t > 10 && t + 3 + MARCH_PF < half1) {
+        step<false, 0, true>(t);
+        step<false, 1, true>(t + 1);
+        step<false, 2, true>(t + 2);
+        step<false, 3, false>(t + 3);
+        t += 4;
+      } else {
+        step<true, -1, false>(t);
+        t++;
       }
     }
   }
 };
 
-template <int NLEV>
+template <int NLEV, bool EXTRA>
 __device__ __forceinline__ void mc_march(const MarchParams &q, int pair, int c, int strip, int seg, int *h_pred,
                                          int *h_res, bool do_hist) {
-  Marcher<NLEV> m(q);
+  Marcher<NLEV, EXTRA> m(q);
   const int lane = threadIdx.x & 31;
   m.pair = pair;
   m.c = c;
@@ -349,34 +497,29 @@ __device__ __forceinline__ void mc_march(const MarchParams &q, int pair, int c, 
   m.og0 = (int)(((long long)seg * q.seg_p) >> NLEV);
   m.og1 = min(OH, (int)(((long long)(seg + 1) * q.seg_p) >> NLEV));
   if (m.og0 >= m.og1) return;
-  m.V0 = q.v + ((long long)(q.f0 + pair) * 3 + c) * q.v_plane_stride;
-  m.V1 = m.V0 + 3 * q.v_plane_stride;
-  m.TL = q.tail ? q.tail + ((long long)pair * 3 + c) * q.tail_plane_stride : nullptr;
-  m.mvp = q.mv + (long long)pair * 4 * q.BY * q.BX;
   const long long coff = c == 0 ? 0 : (long long)q.X * q.Y + (long long)(c - 1) * (q.X / 2) * (q.Y / 2);
   m.in = q.in + (long long)pair * q.in_stride + coff;
   m.out = q.out + (long long)pair * q.out_stride + coff;
-  m.pout = q.prediction ? q.prediction + (long long)pair * q.pred_stride + coff : nullptr;
   m.h_pred = h_pred;
   m.h_res = h_res;
   m.is_I = q.synth && q.types[pair] == 'I';
-  m.run(seg);
+  m.run();
 }
 
 // grid (ceil(nstrips * nsegs / 4), nc * pairs), 128 threads: one warp = one (strip, segment) of
 // component c0 + blockIdx.y % nc (luma and chroma have different level counts: two launches)
-template <int NLEV>
-__global__ void __launch_bounds__(128, 4) k_mc_march(MarchParams q, int c0, int nc) {
-  __shared__ int h_pred[256], h_res[256];
+template <int NLEV, bool EXTRA>
+__global__ void __launch_bounds__(128, 5) k_mc_march(MarchParams q, int c0, int nc) {
+  __shared__ int h_pred[EXTRA ? 256 : 1], h_res[EXTRA ? 256 : 1];
   const int pair = blockIdx.y / nc, c = c0 + blockIdx.y % nc;
-  const bool do_hist = q.hist && c == 0 && !q.synth;
+  const bool do_hist = EXTRA && q.hist && c == 0 && !q.synth;
   if (do_hist) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) h_pred[i] = h_res[i] = 0;
     __syncthreads();
   }
   const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int strip = idx % q.nstrips, seg = idx / q.nstrips;
-  if (seg < q.nsegs) mc_march<NLEV>(q, pair, c, strip, seg, h_pred, h_res, do_hist);
+  if (seg < q.nsegs) mc_march<NLEV, EXTRA>(q, pair, c, strip, seg, h_pred, h_res, do_hist);
   if (do_hist) {
     __syncthreads();
     int *hist = q.hist + (long long)pair * q.hist_stride;
@@ -391,7 +534,8 @@ template <int NLEV>
 static void launch_march_n(const Launch &L, const MarchParams &q, int npairs, int c0, int nc) {
   dim3 grid((q.nstrips * q.nsegs + 3) / 4, nc * npairs);
   ProfScope ps_(L, KC_RESIDUE);
-  k_mc_march<NLEV><<<grid, 128, 0, L.stream>>>(q, c0, nc);
+  if (q.hist || q.prediction) k_mc_march<NLEV, true><<<grid, 128, 0, L.stream>>>(q, c0, nc);
+  else k_mc_march<NLEV, false><<<grid, 128, 0, L.stream>>>(q, c0, nc);
   COUNT(L);
 }
 
