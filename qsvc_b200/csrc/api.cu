@@ -246,7 +246,7 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
                           const uint8_t *odd, long long odd_stride, int n_pairs, int X, int Y,
                           int bs, int sr, int a, int L, bool pr, int first_global, short *mv_out) {
   const int BY = Y / bs, BX = X / bs;
-  const int B = sr, Bc = B + 2;
+  const int B = sr, Bc = (B + 2 + 7) & ~7;  // fill ring + >= 2 zero cells; multiple of 8: 16-byte aligned rows
   const long long field = 4LL * BY * BX;
   const int n_search = 1 + L + a;
   Launch Lh = c->L();
@@ -682,13 +682,18 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
     }
   }
   // 'I': high = raw odd frame, motion_out = 0; 'B': motion_out = motion_in
-  for (int i = 0; i < n_pairs; i++) {
+  for (int i = 0; i < n_pairs;) {  // runs of equal frame types
+    int j = i;
+    while (j < n_pairs && (*types_out)[j] == (*types_out)[i]) j++;
     if ((*types_out)[i] == 'I') {
-      launch_copy_bytes(Lh, out + (long long)i * out_stride, in + (long long)i * in_stride, (size_t)fb);
-      if (mv_out) CU(cudaMemsetAsync(mv_out + (long long)i * field, 0, field * sizeof(short), c->stream));
+      launch_copy_strided(Lh, out + (long long)i * out_stride, out_stride, in + (long long)i * in_stride, in_stride,
+                          (size_t)fb, j - i);
+      if (mv_out) CU(cudaMemsetAsync(mv_out + (long long)i * field, 0, (size_t)(j - i) * field * sizeof(short), c->stream));
     } else if (mv_out && mv_out != mv_in) {
-      launch_copy_bytes(Lh, mv_out + (long long)i * field, mv_in + (long long)i * field, field * sizeof(short));
+      launch_copy_bytes(Lh, mv_out + (long long)i * field, mv_in + (long long)i * field,
+                        (size_t)(j - i) * field * sizeof(short));
     }
+    i = j;
   }
   CU(cudaGetLastError());
   if (rc == 1)
@@ -718,6 +723,13 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
   CU(cudaMemsetAsync(res.raw, 0, res.bytes, c->stream));
   int *d_reach;
   TRY(s.get(256, (void **)&d_reach));
+  if (BY == 0 || BX == 0 || uf == 0.0f) {
+    // update_factor == 0 (analyze.py's default): every contribution is aux + (+-0) with aux
+    // already in [0,255], and the chroma up/down pair is exact: the tool is a copy (A.4)
+    launch_copy_strided(Lh, out, out_stride, in, in_stride, (size_t)fb, n_pairs + 1);
+    CU(cudaGetLastError());
+    return QSVC_OK;
+  }
   for (int k = 0; k <= n_pairs; k++) {
     const uint8_t *frame = in + (long long)k * in_stride;
     uint8_t *dst = out + (long long)k * out_stride;

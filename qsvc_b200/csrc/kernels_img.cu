@@ -37,7 +37,19 @@ __global__ void k_load_u8(Plane dst, int slot0, const uint8_t *__restrict__ src,
   for (int y = blockIdx.y; y < h; y += gridDim.y) {
     short *row = dst.row(slot0 + s, y);
     const uint8_t *srow = f + (long long)y * w;
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x)
+    // 8 samples per thread when both rows allow 64-bit loads / 128-bit stores
+    const bool vec = ((((uintptr_t)row) & 15) | (((uintptr_t)srow) & 7)) == 0;
+    const int nv = vec ? (w >> 3) : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+      const uint2 b = reinterpret_cast<const uint2 *>(srow)[i];
+      uint4 o;
+      o.x = __byte_perm(b.x, 0, 0x4140);
+      o.y = __byte_perm(b.x, 0, 0x4342);
+      o.z = __byte_perm(b.y, 0, 0x4140);
+      o.w = __byte_perm(b.y, 0, 0x4342);
+      reinterpret_cast<uint4 *>(row)[i] = o;
+    }
+    for (int x = (nv << 3) + blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x)
       row[x] = srow[x];
   }
 }
@@ -45,7 +57,7 @@ __global__ void k_load_u8(Plane dst, int slot0, const uint8_t *__restrict__ src,
 void launch_load_u8(const Launch &L, Plane dst, int slot0, int nslots, const uint8_t *src,
                     long long frame_stride, long long comp_off, int f0, int fstep, int h, int w) {
   if (nslots <= 0 || h <= 0 || w <= 0) return;
-  dim3 grid((w + 255) / 256, h < 1024 ? h : 1024, nslots);
+  dim3 grid((w / 8 + 255) / 256 > 0 ? (w / 8 + 255) / 256 : 1, h < 1024 ? h : 1024, nslots);
   ProfScope ps_(L, KC_IMG);
   k_load_u8<<<grid, 256, 0, L.stream>>>(dst, slot0, src, frame_stride, comp_off, f0, fstep, h, w);
   COUNT(L);

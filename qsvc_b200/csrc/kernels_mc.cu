@@ -162,6 +162,40 @@ void launch_copy_bytes(const Launch &L, void *dst, const void *src, size_t n) {
   COUNT(L);
 }
 
+// `count` blocks of `n` bytes, block k at dst + k*dst_stride / src + k*src_stride (one launch)
+__global__ void k_copy_strided(uint8_t *dst, long long dst_stride, const uint8_t *src, long long src_stride,
+                               size_t n) {
+  uint8_t *d = dst + (long long)blockIdx.y * dst_stride;
+  const uint8_t *s = src + (long long)blockIdx.y * src_stride;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  if ((((uintptr_t)d | (uintptr_t)s) & 15) == 0) {
+    size_t n16 = n / 16;
+    const uint4 *s4 = (const uint4 *)s;
+    uint4 *d4 = (uint4 *)d;
+    for (size_t k = i; k < n16; k += stride) d4[k] = s4[k];
+    for (size_t k = n16 * 16 + i; k < n; k += stride) d[k] = s[k];
+  } else {
+    for (size_t k = i; k < n; k += stride) d[k] = s[k];
+  }
+}
+
+void launch_copy_strided(const Launch &L, void *dst, long long dst_stride, const void *src,
+                         long long src_stride, size_t n, int count) {
+  if (!n || count <= 0) return;
+  size_t blocks = (n / 16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  for (int k0 = 0; k0 < count; k0 += 65535) {
+    const int m = count - k0 < 65535 ? count - k0 : 65535;
+    ProfScope ps_(L, KC_IMG);
+    k_copy_strided<<<dim3((unsigned)blocks, (unsigned)m), 256, 0, L.stream>>>(
+        (uint8_t *)dst + (long long)k0 * dst_stride, dst_stride, (const uint8_t *)src + (long long)k0 * src_stride,
+        src_stride, n);
+    COUNT(L);
+  }
+}
+
 __global__ void k_load_residue(Plane dst, int slot, const uint8_t *__restrict__ src, int h, int w) {
   for (int y = blockIdx.y; y < h; y += gridDim.y) {
     short *row = dst.row(slot, y);

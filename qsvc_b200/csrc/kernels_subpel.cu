@@ -725,6 +725,36 @@ __device__ __forceinline__ int level_cell(const SubpelParams &q, const B0View &v
   return b0_cell(v, slot, y, x);
 }
 
+// H x WW window of the level-l image of `slot` at (y0, x0) into dst (row stride WW): one warp
+// per row, the row-invariant part of level_cell hoisted.
+template <int H, int WW>
+__device__ __forceinline__ void load_window(const SubpelParams &q, const B0View &v, int slot, int y0, int x0,
+                                            short *dst) {
+  const int Yl = q.Y << q.l, Xl = q.X << q.l;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int yy = warp; yy < H; yy += 8) {
+    const int y = y0 + yy;
+    short *d = dst + yy * WW;
+    if (y < 0 || y >= Yl) {
+      for (int xx = lane; xx < WW; xx += 32) d[xx] = (short)b0_cell(v, slot, y, x0 + xx);
+      continue;
+    }
+    const short *top = q.strip_top + (long long)slot * q.strip_top_stride + (long long)y * Xl;
+    const short *left = q.strip_left + (long long)slot * q.strip_left_stride + (long long)(y - q.clean) * q.clean;
+    const uint8_t *vb = q.v + (long long)slot * q.v_slot_stride + (long long)y * q.v_pitch;
+    const bool in_top = y < q.clean;
+    for (int xx = lane; xx < WW; xx += 32) {
+      const int x = x0 + xx;
+      int val;
+      if (x < 0 || x >= Xl) val = b0_cell(v, slot, y, x);
+      else if (in_top) val = top[x];
+      else if (x < q.clean) val = left[x];
+      else val = vb[x];
+      d[xx] = (short)val;
+    }
+  }
+}
+
 template <int W>
 __global__ void __launch_bounds__(256) k_subpel_strip(SubpelParams q, B0View v) {
   constexpr int RW = W + 2;
@@ -740,14 +770,9 @@ __global__ void __launch_bounds__(256) k_subpel_strip(SubpelParams q, B0View v) 
     subpel_centre(q, pair, by, bx, c);
     const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
     const int py0 = by * W, px0 = bx * W;
-    const int wy0 = py0 + c[MV_PREV_Y] - 1, wx0 = px0 + c[MV_PREV_X] - 1;
-    const int wy1 = py0 + c[MV_NEXT_Y] - 1, wx1 = px0 + c[MV_NEXT_X] - 1;
-    for (int i = threadIdx.x; i < W * W; i += 256) Ps[i] = (short)level_cell(q, v, ps, py0 + i / W, px0 + i % W);
-    for (int i = threadIdx.x; i < RW * RW; i += 256) {
-      const int yy = i / RW, xx = i - yy * RW;
-      Rs0[i] = (short)level_cell(q, v, r0s, wy0 + yy, wx0 + xx);
-      Rs1[i] = (short)level_cell(q, v, r1s, wy1 + yy, wx1 + xx);
-    }
+    load_window<W, W>(q, v, ps, py0, px0, Ps);
+    load_window<RW, RW>(q, v, r0s, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, Rs0);
+    load_window<RW, RW>(q, v, r1s, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, Rs1);
     __syncthreads();
     sad_windows<W>(Ps, Rs0, Rs1, s_part, s_fin);
     if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
@@ -755,28 +780,85 @@ __global__ void __launch_bounds__(256) k_subpel_strip(SubpelParams q, B0View v) 
   }
 }
 
-// Level-1 strips straight from the level-0 buffer (exact lifting formulas).
-// grid (rows of the level-1 image, slots): rows < clean span the whole width, the others
-// only the first `clean` columns.
-__global__ void __launch_bounds__(128) k_strip1(B0View v, short *top, long long top_stride, short *left,
-                                                long long left_stride, int clean) {
-  const int slot = blockIdx.y, y = blockIdx.x;
-  const int X1 = 2 * v.X;
-  const bool in_top = y < clean;
-  const int n = in_top ? X1 : clean;
-  short *dst = in_top ? top + slot * top_stride + (long long)y * X1
-                      : left + slot * left_stride + (long long)(y - clean) * clean;
-  for (int x = threadIdx.x; x < n; x += blockDim.x) dst[x] = (short)b1_inside(v, slot, y, x);
+// Level-1 image cells of the rectangle [Y0, Y1) x [X0, X1) (X0 even) straight from the level-0
+// buffer with the exact lifting formulas (5_3.cpp:81-94; dwt2d.cpp:139-172: columns, then rows),
+// one 32 x 64 tile per CTA in four shared-memory phases: even rows of the column pass, all rows
+// of the column pass, even columns of the row pass, output.  out(y, x) -> dst[(y - Y0) * dpitch + x - X0].
+__global__ void __launch_bounds__(256) k_level1_tile(B0View v, int Y0, int Y1, int X0, int X1, short *dst,
+                                                     long long dst_slot_stride, int dpitch) {
+  constexpr int TR = 32, TC = 64, NC = TC / 2 + 2;  // low columns j0 .. j0+NC-2, high columns j0-1 .. j0+NC-2
+  __shared__ short TE[2][TR / 2 + 2][NC + 1];  // [low | high columns][even-row index][column]
+  __shared__ short TT[2][TR][NC + 1];
+  __shared__ short EE[TR][NC + 1];
+  const int slot = blockIdx.z;
+  const int ya = Y0 + blockIdx.y * TR, yb = min(ya + TR, Y1);
+  const int xa = X0 + blockIdx.x * TC, xb = min(xa + TC, X1);
+  const int X = v.X, Y = v.Y;
+  const int j0 = xa >> 1;               // column jj of the low set is j0 + jj, of the high set X + j0 - 1 + jj
+  const int nj = ((xb - 1) >> 1) - j0 + 2;  // low columns needed: j0 .. (xb-1)/2 + 1
+  const int i0 = ya >> 1, ni = ((yb - 1) >> 1) - i0 + 2;
+  auto lowc = [&](int i, int xp) -> int {  // column xp of buffer row i < Y
+    return xp < X ? (int)v.p.row(slot, i)[xp] : b0_high(v, slot, i, xp);
+  };
+  // phase A: even rows of the column pass
+  for (int t = threadIdx.x; t < 2 * ni * (nj + 1); t += 256) {
+    const int set = t / (ni * (nj + 1)), r = t % (ni * (nj + 1)), ii = r / (nj + 1), jj = r % (nj + 1);
+    const int i = i0 + ii;
+    const int xp = set ? X + j0 - 1 + jj : j0 + jj;
+    int val = 0;
+    if (i < Y && xp >= 0 && xp < 2 * X && (set || xp < X)) {
+      const int hh = i == 0 ? tdiv2(b0_high(v, slot, Y, xp))
+                            : tdiv4(b0_high(v, slot, Y + i, xp) + b0_high(v, slot, Y + i - 1, xp));
+      val = (short)(lowc(i, xp) - hh);
+    }
+    TE[set][ii][jj] = (short)val;
+  }
+  __syncthreads();
+  // phase B: all rows of the column pass
+  for (int t = threadIdx.x; t < 2 * (yb - ya) * (nj + 1); t += 256) {
+    const int set = t / ((yb - ya) * (nj + 1)), r = t % ((yb - ya) * (nj + 1)), yy = r / (nj + 1), jj = r % (nj + 1);
+    const int y = ya + yy, i = y >> 1, ii = i - i0;
+    const int xp = set ? X + j0 - 1 + jj : j0 + jj;
+    int val = TE[set][ii][jj];
+    if ((y & 1) && xp >= 0 && xp < 2 * X) {
+      const int h = b0_high(v, slot, Y + i, xp);
+      val = (i < Y - 1) ? (short)(h + tdiv2(val + TE[set][ii + 1][jj])) : (short)(h + val);
+    }
+    TT[set][yy][jj] = (short)val;
+  }
+  __syncthreads();
+  // phase C: even columns of the row pass, j = j0 + jj
+  for (int t = threadIdx.x; t < (yb - ya) * nj; t += 256) {
+    const int yy = t / nj, jj = t % nj, j = j0 + jj;
+    int val = 0;
+    if (j < X) {
+      // high-set index of column X + j is jj + 1, of X + j - 1 is jj
+      const int hh = j == 0 ? tdiv2(TT[1][yy][jj + 1]) : tdiv4(TT[1][yy][jj + 1] + TT[1][yy][jj]);
+      val = (short)(TT[0][yy][jj] - hh);
+    }
+    EE[yy][jj] = (short)val;
+  }
+  __syncthreads();
+  short *d = dst + (long long)slot * dst_slot_stride;
+  for (int t = threadIdx.x; t < (yb - ya) * (xb - xa); t += 256) {
+    const int yy = t / (xb - xa), xx = t % (xb - xa), x = xa + xx, j = x >> 1, jj = j - j0;
+    int val = EE[yy][jj];
+    if (x & 1) {
+      const int h = TT[1][yy][jj + 1];
+      val = (j < X - 1) ? (short)(h + tdiv2(val + EE[yy][jj + 1])) : (short)(h + val);
+    }
+    d[(long long)(ya - Y0 + yy) * dpitch + (x - X0)] = (short)val;
+  }
 }
 
 // Level-2 strips from the level-1 image (level-1 strips where polluted, V_1 bytes elsewhere):
-// zero-high-band synthesis, columns first, then rows.  Same grid shape as k_strip1.
-__global__ void __launch_bounds__(128) k_strip2(int Y, int X, const short *top1, long long top1_stride,
+// zero-high-band synthesis, columns first, then rows.  Flattened over the cells of the region
+// rows [Y0, Y1) x columns [0, W) of the level-2 image.
+__global__ void __launch_bounds__(256) k_strip2(int Y, int X, const short *top1, long long top1_stride,
                                                 const short *left1, long long left1_stride, int clean1,
                                                 const uint8_t *v1, long long v1_slot_stride, int v1_pitch,
-                                                short *top, long long top_stride, short *left,
-                                                long long left_stride, int clean) {
-  const int slot = blockIdx.y, y = blockIdx.x;
+                                                short *dst, long long dst_stride, int Y0, int Y1, int W) {
+  const int slot = blockIdx.y;
   const int X1 = 2 * X, Y2 = 4 * Y, X2 = 4 * X;
   const short *t1 = top1 + slot * top1_stride, *l1 = left1 + slot * left1_stride;
   const uint8_t *b1 = v1 + slot * v1_slot_stride;
@@ -785,19 +867,18 @@ __global__ void __launch_bounds__(128) k_strip2(int Y, int X, const short *top1,
     if (xx < clean1) return l1[(yy - clean1) * clean1 + xx];
     return b1[(long long)yy * v1_pitch + xx];
   };
-  const int ya = y >> 1;
-  const bool vavg = (y & 1) && y != Y2 - 1;
-  auto T2 = [&](int xp) -> int {
-    const int a0 = B1(ya, xp);
-    return vavg ? (int)(short)tdiv2(a0 + B1(ya + 1, xp)) : a0;
-  };
-  const bool in_top = y < clean;
-  const int n = in_top ? X2 : clean;
-  short *dst = in_top ? top + slot * top_stride + (long long)y * X2
-                      : left + slot * left_stride + (long long)(y - clean) * clean;
-  for (int x = threadIdx.x; x < n; x += blockDim.x) {
+  const long long cells = (long long)(Y1 - Y0) * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < cells;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int y = Y0 + (int)(idx / W), x = (int)(idx % W);
+    const int ya = y >> 1;
+    const bool vavg = (y & 1) && y != Y2 - 1;
+    auto T2 = [&](int xp) -> int {
+      const int a0 = B1(ya, xp);
+      return vavg ? (int)(short)tdiv2(a0 + B1(ya + 1, xp)) : a0;
+    };
     const int a0 = T2(x >> 1);
-    dst[x] = (!(x & 1) || x == X2 - 1) ? (short)a0 : (short)tdiv2(a0 + T2((x >> 1) + 1));
+    dst[slot * dst_stride + idx] = (!(x & 1) || x == X2 - 1) ? (short)a0 : (short)tdiv2(a0 + T2((x >> 1) + 1));
   }
 }
 
@@ -818,15 +899,36 @@ void launch_strips(const Launch &L, const SubpelParams &q, int level, int nslots
                    const short *top1, const short *left1, long long top1_stride, long long left1_stride,
                    int clean1, const uint8_t *v1, long long v1_slot_stride, int v1_pitch) {
   if (nslots <= 0) return;
-  dim3 grid(q.Y << level, nslots);
-  ProfScope ps_(L, KC_SEARCH_EXACT);
-  if (level == 1)
-    k_strip1<<<grid, 128, 0, L.stream>>>(make_b0view(q), top, q.strip_top_stride, left, q.strip_left_stride, q.clean);
-  else
-    k_strip2<<<grid, 128, 0, L.stream>>>(q.Y, q.X, top1, top1_stride, left1, left1_stride, clean1, v1,
-                                         v1_slot_stride, v1_pitch, top, q.strip_top_stride, left,
-                                         q.strip_left_stride, q.clean);
-  COUNT(L);
+  const int Yl = q.Y << level, Xl = q.X << level;
+  if (level == 1) {
+    const B0View v = make_b0view(q);
+    {
+      dim3 grid((Xl + 63) / 64, (q.clean + 31) / 32, nslots);
+      ProfScope ps_(L, KC_SEARCH_EXACT);
+      k_level1_tile<<<grid, 256, 0, L.stream>>>(v, 0, q.clean, 0, Xl, top, q.strip_top_stride, Xl);
+      COUNT(L);
+    }
+    if (Yl > q.clean) {
+      dim3 grid((q.clean + 63) / 64, (Yl - q.clean + 31) / 32, nslots);
+      ProfScope ps_(L, KC_SEARCH_EXACT);
+      k_level1_tile<<<grid, 256, 0, L.stream>>>(v, q.clean, Yl, 0, q.clean, left, q.strip_left_stride, q.clean);
+      COUNT(L);
+    }
+    return;
+  }
+  auto run = [&](short *dst, long long dst_stride, int Y0, int Y1, int W) {
+    const long long cells = (long long)(Y1 - Y0) * W;
+    if (cells <= 0) return;
+    long long blocks = (cells + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfScope ps_(L, KC_SEARCH_EXACT);
+    k_strip2<<<dim3((unsigned)blocks, nslots), 256, 0, L.stream>>>(q.Y, q.X, top1, top1_stride, left1, left1_stride,
+                                                                  clean1, v1, v1_slot_stride, v1_pitch, dst,
+                                                                  dst_stride, Y0, Y1, W);
+    COUNT(L);
+  };
+  run(top, q.strip_top_stride, 0, q.clean, Xl);
+  run(left, q.strip_left_stride, q.clean, Yl, q.clean);
 }
 
 template <int W>
