@@ -380,8 +380,16 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       run_search(ME_DESCEND, desp(BY, l), desp(BX, l), sr);
     }
     // byte planes of the level-0 interiors and their zero-high-band interpolations
-    launch_plane_to_u8(Lh, img, 0, nslots, Y, X, v[0], (long long)vbytes[0], pitch[0], d_flags, tiles_x,
-                       tiles_per_slot);
+    if (pr) {
+      // the descent restored the pictures exactly: V_0 is the frames' luma, every tile holds bytes
+      launch_luma_to_plane(Lh, even + (long long)i0 * even_stride, even_stride, m + 1, Y, X, v[0],
+                           (long long)vbytes[0], pitch[0]);
+      launch_luma_to_plane(Lh, odd + (long long)i0 * odd_stride, odd_stride, m, Y, X,
+                           v[0] + (size_t)(m + 1) * vbytes[0], (long long)vbytes[0], pitch[0]);
+    } else {
+      launch_plane_to_u8(Lh, img, 0, nslots, Y, X, v[0], (long long)vbytes[0], pitch[0], d_flags, tiles_x,
+                         tiles_per_slot);
+    }
     for (int l = 1; l <= a; l++)
       launch_upsample2x(Lh, v[l - 1], Y << (l - 1), X << (l - 1), pitch[l - 1], (long long)vbytes[l - 1],
                         v[l], pitch[l], (long long)vbytes[l], nslots);
@@ -419,7 +427,10 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       q.strip_left = sleft[l];
       q.strip_top_stride = (long long)top_sz[l];
       q.strip_left_stride = (long long)left_sz[l];
-      launch_strips(Lh, q, l, nslots, stop[l], sleft[l], stop[1], sleft[1], (long long)top_sz[1],
+      // only the reference roles are border-filled: slots [0, m] and the carried copies
+      launch_strips(Lh, q, l, 0, m + 1, stop[l], sleft[l], stop[1], sleft[1], (long long)top_sz[1],
+                    (long long)left_sz[1], cleanl[1], v[1], (long long)vbytes[1], pitch[1]);
+      launch_strips(Lh, q, l, 2 * m + 1, n_copy, stop[l], sleft[l], stop[1], sleft[1], (long long)top_sz[1],
                     (long long)left_sz[1], cleanl[1], v[1], (long long)vbytes[1], pitch[1]);
       q.v_rows_per_slot = (int)(vbytes[l] / pitch[l]);
       q.use_tma = (c->tma_mode != 0 &&

@@ -110,9 +110,11 @@ bool subpel_make_tensor_maps(const uint8_t *v, int pitch, long long total_rows, 
 bool subpel_supported(int W);
 // int16 strips of the level-l images where they differ from the byte planes (first
 // `clean` rows and columns); level 2 is derived from the level-1 strips and V_1.
-void launch_strips(const Launch &L, const SubpelParams &q, int level, int nslots, short *top, short *left,
+void launch_strips(const Launch &L, const SubpelParams &q, int level, int slot0, int nslots, short *top, short *left,
                    const short *top1, const short *left1, long long top1_stride, long long left1_stride,
                    int clean1, const uint8_t *v1, long long v1_slot_stride, int v1_pitch);
+void launch_luma_to_plane(const Launch &L, const uint8_t *src, long long frame_stride, int nframes, int Y, int X,
+                          uint8_t *dst, long long dst_slot_stride, int pitch);
 int subpel_tma_timeouts();
 void launch_subpel(const Launch &L, const SubpelParams &q, int W, int npairs);
 void launch_plane_to_u8(const Launch &L, Plane src, int slot0, int nslots, int Y, int X,

@@ -61,6 +61,33 @@ void launch_plane_to_u8(const Launch &L, Plane src, int slot0, int nslots, int Y
   COUNT(L);
 }
 
+// V_0 planes straight from the frames' luma (pyramids whose descent restores the picture exactly)
+__global__ void __launch_bounds__(256) k_luma_to_plane(const uint8_t *__restrict__ src, long long frame_stride,
+                                                       int Y, int X, uint8_t *__restrict__ dst,
+                                                       long long dst_slot_stride, int pitch) {
+  const uint8_t *f = src + (long long)blockIdx.z * frame_stride;
+  uint8_t *d = dst + (long long)blockIdx.z * dst_slot_stride;
+  for (int y = blockIdx.y; y < Y; y += gridDim.y) {
+    const uint8_t *srow = f + (long long)y * X;
+    uint8_t *drow = d + (long long)y * pitch;
+    const bool vec = (((uintptr_t)srow | (uintptr_t)drow) & 15) == 0;
+    const int nv = vec ? (X >> 4) : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x)
+      reinterpret_cast<uint4 *>(drow)[i] = reinterpret_cast<const uint4 *>(srow)[i];
+    for (int x = (nv << 4) + blockIdx.x * blockDim.x + threadIdx.x; x < X; x += gridDim.x * blockDim.x)
+      drow[x] = srow[x];
+  }
+}
+
+void launch_luma_to_plane(const Launch &L, const uint8_t *src, long long frame_stride, int nframes, int Y, int X,
+                          uint8_t *dst, long long dst_slot_stride, int pitch) {
+  if (nframes <= 0) return;
+  dim3 grid((X / 16 + 255) / 256 > 0 ? (X / 16 + 255) / 256 : 1, Y < 512 ? Y : 512, nframes);
+  ProfScope ps_(L, KC_IMG);
+  k_luma_to_plane<<<grid, 256, 0, L.stream>>>(src, frame_stride, Y, X, dst, dst_slot_stride, pitch);
+  COUNT(L);
+}
+
 // out (2n x 2m) = rows(cols(in (n x m))) of the zero-high-band 5/3 synthesis on bytes
 // (5_3.cpp:81-94 with h = 0, dwt2d.cpp:139-172: columns first, then rows).
 // One thread: 4 input pixels of input rows i and i+1 -> 8 output pixels of rows 2i, 2i+1.
@@ -727,7 +754,9 @@ __device__ __forceinline__ int level_cell(const SubpelParams &q, const B0View &v
 
 // H x WW window of the level-l image of `slot` at (y0, x0) into dst (row stride WW): one warp
 // per row, the row-invariant part of level_cell hoisted.
-template <int H, int WW>
+// STRIPS = false: the image has no polluted strips (predicted frames: never border-filled) and the
+// window lies inside the picture.
+template <int H, int WW, bool STRIPS>
 __device__ __forceinline__ void load_window(const SubpelParams &q, const B0View &v, int slot, int y0, int x0,
                                             short *dst) {
   const int Yl = q.Y << q.l, Xl = q.X << q.l;
@@ -735,6 +764,11 @@ __device__ __forceinline__ void load_window(const SubpelParams &q, const B0View 
   for (int yy = warp; yy < H; yy += 8) {
     const int y = y0 + yy;
     short *d = dst + yy * WW;
+    if (!STRIPS) {
+      const uint8_t *vb = q.v + (long long)slot * q.v_slot_stride + (long long)y * q.v_pitch + x0;
+      for (int xx = lane; xx < WW; xx += 32) d[xx] = vb[xx];
+      continue;
+    }
     if (y < 0 || y >= Yl) {
       for (int xx = lane; xx < WW; xx += 32) d[xx] = (short)b0_cell(v, slot, y, x0 + xx);
       continue;
@@ -770,9 +804,9 @@ __global__ void __launch_bounds__(256) k_subpel_strip(SubpelParams q, B0View v) 
     subpel_centre(q, pair, by, bx, c);
     const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
     const int py0 = by * W, px0 = bx * W;
-    load_window<W, W>(q, v, ps, py0, px0, Ps);
-    load_window<RW, RW>(q, v, r0s, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, Rs0);
-    load_window<RW, RW>(q, v, r1s, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, Rs1);
+    load_window<W, W, false>(q, v, ps, py0, px0, Ps);
+    load_window<RW, RW, true>(q, v, r0s, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, Rs0);
+    load_window<RW, RW, true>(q, v, r1s, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, Rs1);
     __syncthreads();
     sad_windows<W>(Ps, Rs0, Rs1, s_part, s_fin);
     if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
@@ -784,13 +818,13 @@ __global__ void __launch_bounds__(256) k_subpel_strip(SubpelParams q, B0View v) 
 // buffer with the exact lifting formulas (5_3.cpp:81-94; dwt2d.cpp:139-172: columns, then rows),
 // one 32 x 64 tile per CTA in four shared-memory phases: even rows of the column pass, all rows
 // of the column pass, even columns of the row pass, output.  out(y, x) -> dst[(y - Y0) * dpitch + x - X0].
-__global__ void __launch_bounds__(256) k_level1_tile(B0View v, int Y0, int Y1, int X0, int X1, short *dst,
+__global__ void __launch_bounds__(256) k_level1_tile(B0View v, int slot0, int Y0, int Y1, int X0, int X1, short *dst,
                                                      long long dst_slot_stride, int dpitch) {
   constexpr int TR = 32, TC = 64, NC = TC / 2 + 2;  // low columns j0 .. j0+NC-2, high columns j0-1 .. j0+NC-2
   __shared__ short TE[2][TR / 2 + 2][NC + 1];  // [low | high columns][even-row index][column]
   __shared__ short TT[2][TR][NC + 1];
   __shared__ short EE[TR][NC + 1];
-  const int slot = blockIdx.z;
+  const int slot = slot0 + blockIdx.z;
   const int ya = Y0 + blockIdx.y * TR, yb = min(ya + TR, Y1);
   const int xa = X0 + blockIdx.x * TC, xb = min(xa + TC, X1);
   const int X = v.X, Y = v.Y;
@@ -857,8 +891,8 @@ __global__ void __launch_bounds__(256) k_level1_tile(B0View v, int Y0, int Y1, i
 __global__ void __launch_bounds__(256) k_strip2(int Y, int X, const short *top1, long long top1_stride,
                                                 const short *left1, long long left1_stride, int clean1,
                                                 const uint8_t *v1, long long v1_slot_stride, int v1_pitch,
-                                                short *dst, long long dst_stride, int Y0, int Y1, int W) {
-  const int slot = blockIdx.y;
+                                                short *dst, long long dst_stride, int slot0, int Y0, int Y1, int W) {
+  const int slot = slot0 + blockIdx.y;
   const int X1 = 2 * X, Y2 = 4 * Y, X2 = 4 * X;
   const short *t1 = top1 + slot * top1_stride, *l1 = left1 + slot * left1_stride;
   const uint8_t *b1 = v1 + slot * v1_slot_stride;
@@ -895,7 +929,7 @@ static B0View make_b0view(const SubpelParams &q) {
   return v;
 }
 
-void launch_strips(const Launch &L, const SubpelParams &q, int level, int nslots, short *top, short *left,
+void launch_strips(const Launch &L, const SubpelParams &q, int level, int slot0, int nslots, short *top, short *left,
                    const short *top1, const short *left1, long long top1_stride, long long left1_stride,
                    int clean1, const uint8_t *v1, long long v1_slot_stride, int v1_pitch) {
   if (nslots <= 0) return;
@@ -905,13 +939,13 @@ void launch_strips(const Launch &L, const SubpelParams &q, int level, int nslots
     {
       dim3 grid((Xl + 63) / 64, (q.clean + 31) / 32, nslots);
       ProfScope ps_(L, KC_SEARCH_EXACT);
-      k_level1_tile<<<grid, 256, 0, L.stream>>>(v, 0, q.clean, 0, Xl, top, q.strip_top_stride, Xl);
+      k_level1_tile<<<grid, 256, 0, L.stream>>>(v, slot0, 0, q.clean, 0, Xl, top, q.strip_top_stride, Xl);
       COUNT(L);
     }
     if (Yl > q.clean) {
       dim3 grid((q.clean + 63) / 64, (Yl - q.clean + 31) / 32, nslots);
       ProfScope ps_(L, KC_SEARCH_EXACT);
-      k_level1_tile<<<grid, 256, 0, L.stream>>>(v, q.clean, Yl, 0, q.clean, left, q.strip_left_stride, q.clean);
+      k_level1_tile<<<grid, 256, 0, L.stream>>>(v, slot0, q.clean, Yl, 0, q.clean, left, q.strip_left_stride, q.clean);
       COUNT(L);
     }
     return;
@@ -924,7 +958,7 @@ void launch_strips(const Launch &L, const SubpelParams &q, int level, int nslots
     ProfScope ps_(L, KC_SEARCH_EXACT);
     k_strip2<<<dim3((unsigned)blocks, nslots), 256, 0, L.stream>>>(q.Y, q.X, top1, top1_stride, left1, left1_stride,
                                                                   clean1, v1, v1_slot_stride, v1_pitch, dst,
-                                                                  dst_stride, Y0, Y1, W);
+                                                                  dst_stride, slot0, Y0, Y1, W);
     COUNT(L);
   };
   run(top, q.strip_top_stride, 0, q.clean, Xl);
