@@ -73,6 +73,21 @@ int qsvc_set_me_mode(qsvc_ctx *ctx, int mode);
  * int16 planes, 2 byte-plane fused path or fail, 0 automatic. */
 int qsvc_set_mc_mode(qsvc_ctx *ctx, int mode);
 
+/* GOP shards of a picture whose height is not a multiple of the block size (1080 lines, block 16)
+ * are coupled through the prediction buffer of decorrelate / correlate: its rows below the last
+ * whole block are never rewritten by predict() and carry the previous pair's in-place analysis
+ * (decorrelate.cpp:562-567,852-861).  The state is
+ * 3 components x (Y<<a - (Y/bs)*(bs<<a)) rows x (X<<a) bytes.  When a callback is installed,
+ * every decorrelate / correlate level calls it twice on the calling thread:
+ *   phase 0: `state` is zero-filled (what a fresh process starts from); a shard that is not the
+ *            first writes the state received from its left neighbour and returns 1 (0: keep zeros);
+ *   phase 1: `state` holds the state after this shard's last pair, to be passed to the right.
+ * `level` is the temporal level of a resident analysis / synthesis (0 for the per-tool calls),
+ * `synthesis` is 1 for correlate.  A negative return value aborts the call (QSVC_EINVAL). */
+typedef int (*qsvc_tail_fn)(void *user, int level, int synthesis, int phase, uint8_t *state,
+                            long long bytes);
+int qsvc_set_tail_exchange(qsvc_ctx *ctx, qsvc_tail_fn fn, void *user);
+
 /* Replaces `motion_estimate` main(), reference motion_estimate.cpp:490-912
  * (search: :70-184, pyramid driver: :260-413).
  * first_pair_is_global_first: 1 when even[0] is the first frame the reference

@@ -40,6 +40,8 @@ class LevelOut(C.Structure):
                 ("frame_types", C.c_void_p), ("low", u8p)]
 
 _i = C.c_int
+# qsvc_tail_fn: (user, level, synthesis, phase, state, bytes) -> int
+TAIL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_longlong)
 
 # name -> (restype, argtypes); every symbol include/qsvc_b200.h declares
 SIGNATURES = {
@@ -52,6 +54,7 @@ SIGNATURES = {
     "qsvc_timer_start": (_i, [C.c_void_p]),
     "qsvc_timer_stop": (_i, [C.c_void_p, C.POINTER(C.c_float)]),
     "qsvc_synchronize": (_i, [C.c_void_p]),
+    "qsvc_set_tail_exchange": (_i, [C.c_void_p, TAIL_FN, C.c_void_p]),
     "qsvc_set_me_mode": (_i, [C.c_void_p, _i]),
     "qsvc_set_mc_mode": (_i, [C.c_void_p, _i]),
     "qsvc_profile_enable": (_i, [C.c_void_p, _i]),
@@ -82,7 +85,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compiles the CUDA sources for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc"))]
     srcs.append(os.path.join(_HERE, "..", "include", "qsvc_b200.h"))
     stale = force or not os.path.exists(SO_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)

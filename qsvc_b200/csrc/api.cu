@@ -68,6 +68,9 @@ struct qsvc_ctx {
   long long launches = 0;
   Profiler prof;
   std::vector<PoolBlock> pool;
+  qsvc_tail_fn tail_fn = nullptr;  // GOP-shard exchange of the prediction tail state (A.2.6)
+  void *tail_user = nullptr;
+  int cur_level = 0;  // temporal level of the running resident analysis / synthesis
   int tma_mode = 1;  // 0: plain loads in the sub-pixel fast path (env QSVC_TMA=0)
   int mc_mode = 0;  // same three values for the decorrelate / correlate path
   int mc_march = 1;  // 1: line-based fused decorrelate/correlate (kernels_mcmarch.cu), 0: tile kernels
@@ -624,6 +627,8 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
   }
   const int padh = heap_row_shorts(Xa, ba) - (Xa + 2 * ba);
 
+  if (!fused && c->tail_fn && Y % bs != 0)
+    return fail(QSVC_EINVAL, "the prediction tail exchange needs the byte-plane path (X %% 8 == 0, X %% block_size == 0)");
   if (fused) {
     TRY(mc_fused_core(c, analysis, even, even_stride, in, in_stride, mv_in, n_pairs, X, Y, bs, sr, a,
                       types_in, out, out_stride, prediction_out, need_hist ? d_hist : nullptr, HS));
@@ -922,6 +927,12 @@ int qsvc_set_mc_mode(qsvc_ctx *c, int mode) {
   c->mc_mode = mode;
   return QSVC_OK;
 }
+int qsvc_set_tail_exchange(qsvc_ctx *c, qsvc_tail_fn fn, void *user) {
+  if (!c) return fail(QSVC_EINVAL, "null context");
+  c->tail_fn = fn;
+  c->tail_user = user;
+  return QSVC_OK;
+}
 int qsvc_set_me_mode(qsvc_ctx *c, int mode) {
   if (!c || mode < 0 || mode > 2) return fail(QSVC_EINVAL, "bad me_mode");
   c->me_mode = mode;
@@ -1154,6 +1165,7 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
     TRY(pool_alloc(c, (size_t)fb * (n + 1), (void **)&lv.low));
     // split (split.cpp:229-341) is index arithmetic: even k = frame 2k, odd i = frame 2i+1
     const uint8_t *even = low, *odd = low + fb;
+    c->cur_level = t;
     TRY(me_level(c, even, 2 * fb, odd, 2 * fb, n, X, Y, bs, p->border_size, sr, p->subpixel_accuracy,
                  p->first_gop_is_global_first, lv.motion));
     TRY(mc_level(c, 1, even, 2 * fb, odd, 2 * fb, lv.motion, n, X, Y, bs, p->block_overlaping, sr,
@@ -1184,6 +1196,7 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
     sr = std::min(sr * 2, 128);       // analyze.py:144-147
     bs = std::max(bs / 2, bs_min);    // analyze.py:149-151
   }
+  c->cur_level = 0;
   CU(cudaEventRecord(c->ev3, c->stream));
   CU(cudaEventSynchronize(c->ev3));
   CU(cudaEventElapsedTime(&c->total_ms, c->ev2, c->ev3));
@@ -1266,6 +1279,7 @@ int qsvc_resident_synthesize(qsvc_ctx *c, const qsvc_analyze_params *p) {
     int sr = p->search_range;
     for (int j = 1; j < t; j++) sr = std::min(sr * 2, 128);
     uint8_t *dst;  // low_{t-1}: 2n+1 frames, even_t at even positions, odd_t at odd positions
+    c->cur_level = t;
     TRY(pool_alloc(c, (size_t)fb * (2 * n + 1), (void **)&dst));
     TRY(update_level(c, 1, lv.low, fb, lv.high, fb, lv.motion, lv.types.c_str(), n, X, Y,
                      lv.block_size, p->update_factor, dst, 2 * fb));

@@ -117,6 +117,29 @@ class Context:
         """0 automatic, 1 literal decorrelate/correlate path, 2 byte-plane fused path or fail."""
         check(self._L.qsvc_set_mc_mode(self._h, mode))
 
+    def set_tail_exchange(self, fn=None):
+        """Installs (or clears) the GOP-shard exchange of the prediction tail state
+        (include/qsvc_b200.h): fn(level, synthesis, phase, state) with
+        `state` a writable uint8 array; phase 0 returns True after filling in the left
+        neighbour's state, phase 1 receives the state to pass to the right."""
+        if fn is None:
+            self._tail_cb = None
+            check(self._L.qsvc_set_tail_exchange(self._h, _lib.TAIL_FN(), None))
+            return
+
+        def cb(_user, level, synthesis, phase, state, nbytes):
+            try:
+                a = np.ctypeslib.as_array(state, shape=(int(nbytes),))
+                r = fn(int(level), int(synthesis), int(phase), a)
+                return 1 if r else 0
+            except Exception:  # noqa: BLE001 -- must not propagate through the C frame
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        self._tail_cb = _lib.TAIL_FN(cb)  # keep the trampoline alive
+        check(self._L.qsvc_set_tail_exchange(self._h, self._tail_cb, None))
+
     def profile_enable(self, on=True):
         check(self._L.qsvc_profile_enable(self._h, 1 if on else 0))
 

@@ -3,12 +3,19 @@
 GPU g of N takes GOPs [g0, g1), i.e. input frames [g0*G, g1*G] inclusive (the
 boundary frame is read by both neighbours), runs every temporal level locally
 and returns its per-level outputs; the host concatenates them in GOP order into
-the reference's file layout, dropping the duplicated boundary low frame.
+the reference's file layout, dropping the duplicated boundary frame.
 
-Exact when update_factor == 0 and the picture height/width are multiples of the
-block size.  Otherwise a neighbour exchange would be needed (update of the
-boundary frame; chained prediction tail rows) and the functions
-below refuse unless `allow_inexact=True`.
+What couples neighbouring shards, and how it is handled:
+  * picture height not a multiple of the block size (1080 lines, block 16): the
+    prediction buffer of decorrelate / correlate carries its uncovered rows from
+    pair to pair.  Every shard receives that state from its left
+    neighbour and passes its own to the right, once per temporal level (a point-to-
+    point message of 3 * rows * (X << a) bytes; `TailRelay` over torch.distributed,
+    `LocalTailRelay` when the shards run one after the other on one GPU);
+  * update_factor != 0: the boundary frame receives updates from both sides in a
+    fixed order (SURVEY.md 8e item 1).  Not built: refused unless allow_inexact;
+  * X % block_size != 0 with Y % block_size != 0: the byte-plane path does not apply
+    and the literal path has no exchange hook: refused.
 """
 from __future__ import annotations
 
@@ -32,25 +39,80 @@ def shard_frames(low0: np.ndarray, TRLs: int, g0: int, g1: int) -> np.ndarray:
     return low0[g0 * G : g1 * G + 1]
 
 
+def needs_tail_exchange(Y, block_size, world):
+    return world > 1 and Y % block_size != 0
+
+
 def check_exact(X, Y, block_size, update_factor, world, allow_inexact=False):
     if world <= 1 or allow_inexact:
         return
     if update_factor != 0:
         raise ValueError("GOP sharding with update_factor != 0 needs the boundary-frame "
                          "exchange of SURVEY.md 8e(1); run on one GPU or pass allow_inexact")
-    if Y % block_size or X % block_size:
-        raise ValueError("GOP sharding with a picture size that is not a multiple of the block "
-                         "size needs the chained tail rows of SURVEY.md A.2.6; run on one GPU "
-                         "or pass allow_inexact")
+    if Y % block_size and (X % block_size or X % 8):
+        raise ValueError("GOP sharding with uncovered rows AND columns has no tail exchange "
+                         "(literal decorrelate path); run on one GPU or pass allow_inexact")
+
+
+class LocalTailRelay:
+    """Tail-state hand-over between shards that run one after the other in this
+    process (one GPU working through a long sequence GOP range by GOP range)."""
+
+    def __init__(self):
+        self.state = {}
+        self.first = True
+
+    def next_shard(self):
+        self.first = False
+
+    def __call__(self, level, synthesis, phase, state):
+        key = (level, synthesis)
+        if phase == 0:
+            if self.first or key not in self.state:
+                return False
+            state[:] = self.state[key]
+            return True
+        self.state[key] = state.copy()
+        return False
+
+
+class TailRelay:
+    """Tail-state hand-over over torch.distributed point-to-point messages: receive from
+    the nearest rank on the left that has work, send to the nearest on the right."""
+
+    def __init__(self, rank, ranges):
+        import torch.distributed as dist
+        active = [r for r, (a, b) in enumerate(ranges) if b > a]
+        i = active.index(rank)
+        self.left = active[i - 1] if i > 0 else None
+        self.right = active[i + 1] if i + 1 < len(active) else None
+        self.cuda = dist.get_backend() == "nccl"
+
+    def __call__(self, level, synthesis, phase, state):
+        import torch
+        import torch.distributed as dist
+        if phase == 0:
+            if self.left is None:
+                return False
+            t = torch.empty(state.shape[0], dtype=torch.uint8, device="cuda" if self.cuda else "cpu")
+            dist.recv(t, src=self.left)
+            state[:] = t.cpu().numpy()
+            return True
+        if self.right is not None:
+            t = torch.from_numpy(state.copy())
+            dist.send(t.cuda() if self.cuda else t, dst=self.right)
+        return False
 
 
 def analyze_shard(ctx, low0, X, Y, GOPs, TRLs, rank, world, block_size=32, search_range=4,
                   subpixel_accuracy=0, update_factor=0.0, always_B=0, block_size_min=32,
-                  allow_inexact=False, analyze_fn=None):
+                  allow_inexact=False, analyze_fn=None, relay=None):
     """Runs this rank's GOP range.  `analyze_fn(frames, n_gops, first_global)` defaults
-    to ctx.analyze (the CUDA path); tests may inject another callable."""
+    to ctx.analyze (the CUDA path); tests may inject another callable.  `relay` is the
+    tail-state hand-over (default: TailRelay when the geometry needs one)."""
     check_exact(X, Y, block_size, update_factor, world, allow_inexact)
-    g0, g1 = partition(GOPs, world)[rank]
+    ranges = partition(GOPs, world)
+    g0, g1 = ranges[rank]
     if g1 == g0:
         return None
     frames = shard_frames(low0, TRLs, g0, g1)
@@ -59,7 +121,15 @@ def analyze_shard(ctx, low0, X, Y, GOPs, TRLs, rank, world, block_size=32, searc
             return ctx.analyze(fr, X, Y, n_gops, TRLs, block_size, search_range,
                                subpixel_accuracy, update_factor, always_B,
                                block_size_min=block_size_min, first_global=first_global)
-    return analyze_fn(frames, g1 - g0, g0 == 0)
+    if relay is None and needs_tail_exchange(Y, block_size, world) and ctx is not None:
+        relay = TailRelay(rank, ranges)
+    if relay is not None and ctx is not None:
+        ctx.set_tail_exchange(relay)
+    try:
+        return analyze_fn(frames, g1 - g0, g0 == 0)
+    finally:
+        if relay is not None and ctx is not None:
+            ctx.set_tail_exchange(None)
 
 
 def gather(parts, TRLs: int):
@@ -84,3 +154,58 @@ def analyze_distributed(ctx, low0, X, Y, GOPs, TRLs, **kw):
     parts = [None] * world if rank == 0 else None
     dist.gather_object(local, parts, dst=0)
     return gather(parts, TRLs) if rank == 0 else None
+
+
+# ------------------------------------------------------------------ synthesis
+
+def shard_subbands(subbands, TRLs: int, g0: int, g1: int):
+    """The slices of high_t / motion_t / frame_types_t / low_{TRLs-1} that belong to GOPs
+    [g0, g1): level t has 2^(TRLs-1-t) pairs per GOP, low_{TRLs-1} one frame per GOP + 1."""
+    out = {}
+    for t in range(1, TRLs):
+        k = 2 ** (TRLs - 1 - t)
+        out[f"high_{t}"] = subbands[f"high_{t}"][g0 * k : g1 * k]
+        out[f"motion_{t}"] = subbands[f"motion_{t}"][g0 * k : g1 * k]
+        out[f"frame_types_{t}"] = bytes(subbands[f"frame_types_{t}"])[g0 * k : g1 * k]
+    out[f"low_{TRLs - 1}"] = subbands[f"low_{TRLs - 1}"][g0 : g1 + 1]
+    return out
+
+
+def synthesize_shard(ctx, subbands, X, Y, GOPs, TRLs, rank, world, block_size=16, search_range=4,
+                     subpixel_accuracy=0, update_factor=0.0, allow_inexact=False,
+                     synthesize_fn=None, relay=None):
+    """Reconstructs this rank's GOP range: low_0 frames [g0*G, g1*G] inclusive."""
+    check_exact(X, Y, block_size, update_factor, world, allow_inexact)
+    ranges = partition(GOPs, world)
+    g0, g1 = ranges[rank]
+    if g1 == g0:
+        return None
+    sub = shard_subbands(subbands, TRLs, g0, g1)
+    if synthesize_fn is None:
+        def synthesize_fn(sb, n_gops):
+            return ctx.synthesize(sb, X, Y, n_gops, TRLs, block_size, search_range,
+                                  subpixel_accuracy, update_factor)
+    if relay is None and needs_tail_exchange(Y, block_size, world) and ctx is not None:
+        relay = TailRelay(rank, ranges)
+    if relay is not None and ctx is not None:
+        ctx.set_tail_exchange(relay)
+    try:
+        return synthesize_fn(sub, g1 - g0)
+    finally:
+        if relay is not None and ctx is not None:
+            ctx.set_tail_exchange(None)
+
+
+def gather_frames(parts):
+    """Concatenates reconstructed GOP ranges, dropping each duplicated boundary frame."""
+    parts = [p for p in parts if p is not None]
+    return np.concatenate([p if i == 0 else p[1:] for i, p in enumerate(parts)], axis=0)
+
+
+def synthesize_distributed(ctx, subbands, X, Y, GOPs, TRLs, **kw):
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = synthesize_shard(ctx, subbands, X, Y, GOPs, TRLs, rank, world, **kw)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(local, parts, dst=0)
+    return gather_frames(parts) if rank == 0 else None

@@ -151,6 +151,44 @@ def test_mc_literal_and_fused_paths_agree_with_oracle(ctx, mode, X, Y, GOPs, TRL
         ctx.set_mc_mode(0)
 
 
+def test_gop_shards_with_tail_exchange_match_the_whole_sequence(ctx):
+    """Height % block_size != 0: GOP shards that hand the
+    prediction tail state from left to right reproduce the single-process result, analysis
+    and synthesis; without the hand-over the later shard's bottom rows differ."""
+    from qsvc_b200 import shard
+    X, Y, GOPs, TRLs, bs, sr, a = 128, 72, 2, 4, 16, 4, 2
+    clip = yuv.synthetic_clip(X, Y, GOPs * 2 ** (TRLs - 1) + 1, 23, max_shift=12)
+    ref = orc.analyze(clip, X, Y, TRLs, bs, sr, a, 0.0, block_size_min=bs)
+    kw = dict(block_size=bs, search_range=sr, subpixel_accuracy=a, update_factor=0.0, block_size_min=bs)
+
+    def run(relay):
+        parts = []
+        for r in range(2):
+            parts.append(shard.analyze_shard(ctx, clip, X, Y, GOPs, TRLs, r, 2, relay=relay, **kw))
+            if hasattr(relay, "next_shard"):
+                relay.next_shard()
+        return shard.gather(parts, TRLs)
+
+    got = run(shard.LocalTailRelay())
+    for k, v in got.items():
+        assert (np.array_equal(ref[k], v) if not isinstance(v, bytes) else ref[k] == v), k
+    naive = run(lambda level, synthesis, phase, state: False)
+    assert any(not np.array_equal(naive[f"high_{t}"], ref[f"high_{t}"]) for t in range(1, TRLs))
+
+    sub = {f"low_{TRLs-1}": ref[f"low_{TRLs-1}"]}
+    for t in range(1, TRLs):
+        sub[f"high_{t}"], sub[f"motion_{t}"] = ref[f"high_{t}"], ref[f"motion_filtered_{t}"]
+        sub[f"frame_types_{t}"] = ref[f"frame_types_{t}"]
+    whole = ctx.synthesize(sub, X, Y, GOPs, TRLs, bs, sr, a, 0.0)
+    relay = shard.LocalTailRelay()
+    parts = []
+    for r in range(2):
+        parts.append(shard.synthesize_shard(ctx, sub, X, Y, GOPs, TRLs, r, 2, block_size=bs, search_range=sr,
+                                            subpixel_accuracy=a, update_factor=0.0, relay=relay))
+        relay.next_shard()
+    assert np.array_equal(shard.gather_frames(parts), whole)
+
+
 def test_first_pair_flag_for_gop_shards(ctx):
     """A later GOP shard must start from the carried (non-restored) reference[0]
     when the pyramid is not perfectly reconstructing."""

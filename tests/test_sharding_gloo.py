@@ -57,5 +57,80 @@ def test_sharding_refuses_inexact_configurations():
     with pytest.raises(ValueError):
         shard.check_exact(64, 48, 16, 0.25, world=2)
     with pytest.raises(ValueError):
-        shard.check_exact(64, 40, 16, 0.0, world=2)
+        shard.check_exact(60, 40, 16, 0.0, world=2)   # uncovered rows and columns: no exchange hook
+    shard.check_exact(64, 40, 16, 0.0, world=2)       # uncovered rows only: tail exchange
     shard.check_exact(64, 40, 16, 0.25, world=1)
+    assert shard.needs_tail_exchange(1080, 16, 2) and not shard.needs_tail_exchange(2160, 16, 8)
+
+
+class _FakeCtx:
+    """Stands in for mctf.Context: drives the installed tail callback the way the library
+    does (phase 0 before the first pair of a level, phase 1 after the last one)."""
+
+    def __init__(self, rank):
+        self.rank, self.fn, self.seen = rank, None, []
+
+    def set_tail_exchange(self, fn):
+        self.fn = fn
+
+    def run_levels(self, synthesis):
+        levels = range(TRLs - 1, 0, -1) if synthesis else range(1, TRLs)
+        for t in levels:
+            st = np.zeros(24, np.uint8)
+            got = self.fn(t, synthesis, 0, st)
+            self.seen.append((t, bool(got), st.copy()))
+            st[:] = 100 * self.rank + 10 * synthesis + t
+            self.fn(t, synthesis, 1, st)
+
+
+def _relay_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = _FakeCtx(rank)
+    clip = np.zeros((GOPs * 2 ** (TRLs - 1) + 1, 8), np.uint8)
+
+    def fn(frames, n_gops, first_global):
+        ctx.run_levels(0)
+        return {"rank": rank, "first": first_global, "frames": len(frames)}
+
+    out = shard.analyze_shard(ctx, clip, 64, 40, GOPs, TRLs, rank, world, block_size=16, update_factor=0.0,
+                              analyze_fn=fn)
+    assert ctx.fn is None  # callback removed again
+    sub = {f"high_{t}": np.zeros((GOPs * 2 ** (TRLs - 1 - t), 8), np.uint8) for t in range(1, TRLs)}
+    sub.update({f"motion_{t}": np.zeros((GOPs * 2 ** (TRLs - 1 - t), 4, 1, 1), np.int16) for t in range(1, TRLs)})
+    sub.update({f"frame_types_{t}": b"B" * (GOPs * 2 ** (TRLs - 1 - t)) for t in range(1, TRLs)})
+    sub[f"low_{TRLs - 1}"] = np.arange(GOPs + 1, dtype=np.uint8).reshape(-1, 1).repeat(8, 1)
+
+    def sfn(sb, n_gops):
+        ctx.run_levels(1)
+        G = 2 ** (TRLs - 1)
+        assert sb[f"low_{TRLs - 1}"].shape[0] == n_gops + 1 and sb["high_1"].shape[0] == n_gops * G // 2
+        first = int(sb[f"low_{TRLs - 1}"][0, 0]) * G
+        return np.arange(first, first + n_gops * G + 1, dtype=np.uint8).reshape(-1, 1)
+
+    rec = shard.synthesize_distributed(ctx, sub, 64, 40, GOPs, TRLs, block_size=16, update_factor=0.0,
+                                       synthesize_fn=sfn)
+    q.put((rank, out, ctx.seen, None if rec is None else rec[:, 0].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tail_relay_passes_state_left_to_right():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_relay_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((r[0], r) for r in (q.get(timeout=120), q.get(timeout=120)))
+    for p in procs:
+        p.join(timeout=60)
+    # rank 0 starts every level from zeros; rank 1 from what rank 0 ended with
+    assert all(not got and not st.any() for (_, got, st) in res[0][2])
+    for (t, got, st), syn in zip(res[1][2], [0] * (TRLs - 1) + [1] * (TRLs - 1)):
+        assert got and (st == 10 * syn + t).all()
+    assert res[0][1]["first"] and not res[1][1]["first"]
+    assert res[0][3] == list(range(GOPs * 2 ** (TRLs - 1) + 1))  # gathered frames, no duplicates
