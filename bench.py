@@ -244,6 +244,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device (qsvc_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL's own log lines (version banner, NCCL_DEBUG=INFO) must not share stdout with the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
