@@ -437,9 +437,15 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
                     (long long)left_sz[1], cleanl[1], v[1], (long long)vbytes[1], pitch[1]);
       q.v_rows_per_slot = (int)(vbytes[l] / pitch[l]);
       q.use_tma = (c->tma_mode != 0 &&
-                   subpel_make_tensor_maps(v[l], pitch[l], (long long)q.v_rows_per_slot * nslots, bs << l, q.tm_p, q.tm_r))
+                   subpel_make_tensor_maps(v[l], pitch[l], (long long)q.v_rows_per_slot * nslots, bs << l,
+                                           (bs << l) + 32, q.tm_p, q.tm_r))
                       ? 1
                       : 0;
+      q.check_tiles = pr ? 0 : 1;
+      {
+        static const int dbg = getenv("QSVC_SUBPEL_DEBUG") ? atoi(getenv("QSVC_SUBPEL_DEBUG")) : 0;
+        q.debug = dbg;
+      }
       launch_subpel(Lh, q, bs << l, m);
       j++;
     }

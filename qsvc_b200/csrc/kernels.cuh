@@ -101,11 +101,13 @@ struct SubpelParams {
   long long strip_top_stride, strip_left_stride;
   int clean;             // min((2B + 2) << (l - 1), Y << l, X << l)
   int v_rows_per_slot;   // v_slot_stride / v_pitch
-  int use_tma;           // tm_p / tm_r hold valid CUtensorMap objects
+  int use_tma;           // tm_p / tm_r hold valid CUtensorMap objects; 1: windows at 16-byte aligned columns, 2: at their own column
+  int debug;             // env QSVC_SUBPEL_DEBUG: 1 = fast blocks go to the strip kernel, 2 = strip blocks go to the exact generator
+  int check_tiles;       // 0: every tile of every slot is known to hold bytes (tile_bad not consulted)
   alignas(64) unsigned char tm_p[128];
   alignas(64) unsigned char tm_r[128];
 };
-bool subpel_make_tensor_maps(const uint8_t *v, int pitch, long long total_rows, int W, void *tm_p,
+bool subpel_make_tensor_maps(const uint8_t *v, int pitch, long long total_rows, int W, int box_w, void *tm_p,
                              void *tm_r);
 bool subpel_supported(int W);
 // int16 strips of the level-l images where they differ from the byte planes (first

@@ -197,19 +197,23 @@ __device__ __forceinline__ int classify_block(const SubpelParams &q, int l, int 
   for (int d = 0; d < 2; d++)
     fast = fast && wy[d] >= q.clean && wx[d] >= q.clean && wy[d] + W + 2 <= Yl && wx[d] + W + 2 <= Xl;
   int bad = 0;
-  for (int img = 0; img < 3; img++) {
-    const int slot = img == 0 ? r0s : (img == 1 ? r1s : ps);
-    const int y0 = img == 2 ? py0 : wy[img], x0 = img == 2 ? px0 : wx[img];
-    const int span = img == 2 ? W : W + 2;
-    const int pyl = max(y0 >> l, 0), pyh = min(((y0 + span - 1) >> l) + 1, q.Y - 1);
-    const int pxl = max(x0 >> l, 0), pxh = min(((x0 + span - 1) >> l) + 1, q.X - 1);
-    if (pyl > pyh || pxl > pxh) continue;
-    const int ty0 = pyl >> 4, nty = (pyh >> 4) - ty0 + 1, tx0 = pxl >> 4, ntx = (pxh >> 4) - tx0 + 1;
-    const uint8_t *map = q.tile_bad + (long long)slot * q.tiles_per_slot;
-    for (int i = threadIdx.x; i < nty * ntx; i += NT)
-      bad |= map[(ty0 + i / ntx) * q.tiles_x + tx0 + i % ntx];
+  if (q.check_tiles) {
+    for (int img = 0; img < 3; img++) {
+      const int slot = img == 0 ? r0s : (img == 1 ? r1s : ps);
+      const int y0 = img == 2 ? py0 : wy[img], x0 = img == 2 ? px0 : wx[img];
+      const int span = img == 2 ? W : W + 2;
+      const int pyl = max(y0 >> l, 0), pyh = min(((y0 + span - 1) >> l) + 1, q.Y - 1);
+      const int pxl = max(x0 >> l, 0), pxh = min(((x0 + span - 1) >> l) + 1, q.X - 1);
+      if (pyl > pyh || pxl > pxh) continue;
+      const int ty0 = pyl >> 4, nty = (pyh >> 4) - ty0 + 1, tx0 = pxl >> 4, ntx = (pxh >> 4) - tx0 + 1;
+      const uint8_t *map = q.tile_bad + (long long)slot * q.tiles_per_slot;
+      for (int i = threadIdx.x; i < nty * ntx; i += NT)
+        bad |= map[(ty0 + i / ntx) * q.tiles_x + tx0 + i % ntx];
+    }
   }
   bad = __syncthreads_or(bad);
+  if (q.debug & 1) fast = false;               // debug: no block takes the TMA kernel
+  if ((q.debug & 2) && !fast) bad = 1;         // debug: the strip kernel is bypassed
   return bad ? 2 : (fast ? 0 : 1);
 }
 
@@ -349,28 +353,120 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, in
       : "memory");
 }
 
+// ---- packed-byte SAD core shared by the TMA kernel and the strip kernel ----
+// 2*W threads per block: thread = (direction d, row group g of RPT = W/4 block rows, word column
+// j of W/4).  A thread keeps its RPT block words in registers, walks the RPT + 2 window rows
+// below them once and accumulates the nine window shifts with VABSDIFF4.U8.ACC.  S = byte
+// offset of window column 0 inside word 0 of the row pointer (0 when the window was staged
+// aligned); EX adds the sums of a second byte window (the "excess" of int16 samples outside
+// [0,255], see k_subpel_strip) under the same shifts.
+template <int S>
+__device__ __forceinline__ void shifted3(const unsigned *rw, unsigned sh[3]) {
+  const unsigned w0 = rw[0], w1 = rw[1];
+  if (S == 0) {
+    sh[0] = w0;
+    sh[1] = __funnelshift_r(w0, w1, 8);
+    sh[2] = __funnelshift_r(w0, w1, 16);
+  } else if (S == 1) {
+    sh[0] = __funnelshift_r(w0, w1, 8);
+    sh[1] = __funnelshift_r(w0, w1, 16);
+    sh[2] = __funnelshift_r(w0, w1, 24);
+  } else if (S == 2) {
+    sh[0] = __funnelshift_r(w0, w1, 16);
+    sh[1] = __funnelshift_r(w0, w1, 24);
+    sh[2] = w1;
+  } else {
+    const unsigned w2 = rw[2];
+    sh[0] = __funnelshift_r(w0, w1, 24);
+    sh[1] = w1;
+    sh[2] = __funnelshift_r(w1, w2, 8);
+  }
+}
+
+template <int W, int S, bool EX>
+__device__ __forceinline__ void sad_rows(const unsigned *P4, const unsigned *R4, const unsigned *E4, int rp,
+                                         unsigned acc[9]) {
+  constexpr int WPR = W / 4, RPT = W / 4;
+  unsigned p[RPT];
+#pragma unroll
+  for (int r = 0; r < RPT; r++) p[r] = P4[r * WPR];
+#pragma unroll
+  for (int rr = 0; rr < RPT + 2; rr++) {
+    unsigned sh[3], se[3];
+    shifted3<S>(R4 + rr * rp, sh);
+    if (EX) shifted3<S>(E4 + rr * rp, se);
+#pragma unroll
+    for (int wdy = -1; wdy <= 1; wdy++) {
+      const int r = rr - 1 - wdy;  // block row paired with window row rr under vertical shift wdy
+      if (r >= 0 && r < RPT) {
+#pragma unroll
+        for (int wdx = -1; wdx <= 1; wdx++) {
+          const int a = (wdy + 1) * 3 + wdx + 1;
+          acc[a] = __vsadu4(p[r], sh[wdx + 1]) + acc[a];
+          if (EX) acc[a] = __vsadu4(se[wdx + 1], 0u) + acc[a];
+        }
+      }
+    }
+  }
+}
+
+// Warp sums -> block sums per direction -> arg-min with the reference's `<=` rule -> vectors.
+// s_err: [2 * W / 32][9]; one direction per warp (W >= 32).
 template <int W>
-__global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_tma(SubpelParams q,
-                                                                const __grid_constant__ CUtensorMap tmP,
-                                                                const __grid_constant__ CUtensorMap tmR) {
-  constexpr int WPR = W / 4;            // P words per row
-  constexpr int RPT = 8;                // block rows per thread
-  constexpr int NT = WPR * (W / RPT);
-  constexpr int TP = (W + 32) / 4;      // TMA landing pitch in words (box inner dim W + 32 bytes)
-  constexpr int TBYTES = (W + 32) * (W + 2);
+__device__ __forceinline__ void sad_finish(const SubpelParams &q, const unsigned acc[9], int (*s_err)[9], int pair,
+                                           int by, int bx, const short c[4]) {
+  constexpr int WPD = W / 32;  // warps per direction
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const unsigned v = __reduce_add_sync(0xffffffffu, acc[k]);
+    if (lane == 0) s_err[warp][k] = (int)v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    // candidate k of direction d tests the window shift sgn * (dy, dx)
+    const int d = threadIdx.x, sgn = d ? -1 : 1;
+    int best = 0, min_error = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const int slot = (sgn * c_cand9[k][0] + 1) * 3 + sgn * c_cand9[k][1] + 1;
+      int e = 0;
+#pragma unroll
+      for (int w = 0; w < WPD; w++) e += s_err[d * WPD + w][slot];
+      if (k == 0 || e <= min_error) {
+        min_error = e;
+        best = k;
+      }
+    }
+    const long long plane = (long long)q.BY * q.BX, dst = (long long)by * q.BX + bx;
+    short *mvo = q.mv_out + (long long)pair * 4 * plane;
+    mvo[(2 * d) * plane + dst] = (short)(c[2 * d] + sgn * c_cand9[best][1]);
+    mvo[(2 * d + 1) * plane + dst] = (short)(c[2 * d + 1] + sgn * c_cand9[best][0]);
+  }
+}
+
+// ---- fast path, TMA ----
+// The predicted block and the two (W+2)-row windows are fetched by three
+// cp.async.bulk.tensor.2d loads (UTMALDG) on one mbarrier.  ALIGNED = 1: windows are fetched
+// from the 16-byte aligned column below wx (W + 32 bytes wide) and the SAD loop absorbs the
+// byte offset (four instantiations).  ALIGNED = 0 would start the box at wx itself (W + 16
+// bytes): measured on B200, a u8 box at a column that is not a multiple of 16 raises
+// "illegal instruction", so only ALIGNED = 1 is instantiated.
+template <int W, int ALIGNED>
+__global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __grid_constant__ CUtensorMap tmP,
+                                                      const __grid_constant__ CUtensorMap tmR) {
+  constexpr int WPR = W / 4, RPT = W / 4, NT = 2 * W;
+  constexpr int BOXW = ALIGNED ? W + 32 : W + 16;  // TMA landing pitch in bytes
+  constexpr int TP = BOXW / 4;
+  constexpr int TBYTES = BOXW * (W + 2);
   constexpr int TB = (TBYTES + 127) & ~127;
-  constexpr int RS = WPR + 2;           // re-aligned window pitch in words (8 * RS % 32 == 16)
-  constexpr int NWARP = (NT + 31) / 32;
   __shared__ __align__(128) unsigned char sP[W * W];
   __shared__ __align__(128) unsigned char sT[2][TB];
-  __shared__ unsigned sR[2][(W + 2) * RS];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ int s_err[NWARP][18];
-  __shared__ int s_fin[18];
+  __shared__ int s_err[NT / 32][9];
 
   const int bx = blockIdx.x, by = blockIdx.y, pair = blockIdx.z;
   const int l = q.l;
-  const int Yl = q.Y << l, Xl = q.X << l;
   short c[4];
   subpel_centre(q, pair, by, bx, c);
   const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
@@ -390,14 +486,12 @@ __global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_tma(SubpelParams q
     }
   }
   if (threadIdx.x == 0) {
-    // TMA needs 16-byte aligned inner coordinates: fetch from wx & ~15, W + 32 bytes wide
-    // (bytes beyond the plane pitch are zero-filled and never used)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)),
                  "r"(W * W + 2 * TBYTES)
                  : "memory");
     tma_load_2d(sP, &tmP, px0, ps * q.v_rows_per_slot + py0, &bar);
-    tma_load_2d(sT[0], &tmR, wx[0] & ~15, r0s * q.v_rows_per_slot + wy[0], &bar);
-    tma_load_2d(sT[1], &tmR, wx[1] & ~15, r1s * q.v_rows_per_slot + wy[1], &bar);
+    tma_load_2d(sT[0], &tmR, ALIGNED ? (wx[0] & ~15) : wx[0], r0s * q.v_rows_per_slot + wy[0], &bar);
+    tma_load_2d(sT[1], &tmR, ALIGNED ? (wx[1] & ~15) : wx[1], r1s * q.v_rows_per_slot + wy[1], &bar);
   }
   {
     unsigned done = 0;
@@ -417,77 +511,25 @@ __global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_tma(SubpelParams q
       }
     }
   }
-  // re-align the windows so that window column 0 sits on a word boundary: thread =
-  // (row of a pass, word column); the threads of column 0 also produce word WPR
-  {
-    const int w = threadIdx.x % WPR, r0 = threadIdx.x / WPR;  // WPR is a power of two
-    constexpr int RSTEP = NT / WPR;
+  const int d = threadIdx.x / W, t = threadIdx.x % W;  // one direction per warp
+  const int j = t % WPR, g = t / WPR;
+  const unsigned *P4 = reinterpret_cast<const unsigned *>(sP) + (g * RPT) * WPR + j;
+  const unsigned *R4 = reinterpret_cast<const unsigned *>(sT[d]) + (g * RPT) * TP + j;
+  unsigned acc[9];
 #pragma unroll
-    for (int d = 0; d < 2; d++) {
-      const unsigned *T4 = reinterpret_cast<const unsigned *>(sT[d]) + ((wx[d] & 15) >> 2);
-      const int sa = 8 * (wx[d] & 3);
-      for (int y = r0; y < W + 2; y += RSTEP) {
-        const unsigned *t = T4 + y * TP + w;
-        sR[d][y * RS + w] = __funnelshift_r(t[0], t[1], sa);
-        if (w == 0) sR[d][y * RS + WPR] = __funnelshift_r(t[WPR], t[WPR + 1], sa);
-      }
+  for (int k = 0; k < 9; k++) acc[k] = 0;
+  if (ALIGNED) {
+    R4 += (wx[d] & 15) >> 2;
+    switch (wx[d] & 3) {
+      case 0: sad_rows<W, 0, false>(P4, R4, nullptr, TP, acc); break;
+      case 1: sad_rows<W, 1, false>(P4, R4, nullptr, TP, acc); break;
+      case 2: sad_rows<W, 2, false>(P4, R4, nullptr, TP, acc); break;
+      default: sad_rows<W, 3, false>(P4, R4, nullptr, TP, acc); break;
     }
+  } else {
+    sad_rows<W, 0, false>(P4, R4, nullptr, TP, acc);
   }
-  __syncthreads();
-
-  const int j = threadIdx.x % WPR, g = threadIdx.x / WPR;
-  unsigned p[RPT];
-  {
-    const unsigned *P4 = reinterpret_cast<const unsigned *>(sP) + (g * RPT) * WPR + j;
-#pragma unroll
-    for (int r = 0; r < RPT; r++) p[r] = P4[r * WPR];
-  }
-  unsigned acc[18];
-#pragma unroll
-  for (int k = 0; k < 18; k++) acc[k] = 0;
-#pragma unroll
-  for (int d = 0; d < 2; d++) {
-    const unsigned *R4 = sR[d] + (g * RPT) * RS + j;
-#pragma unroll
-    for (int rr = 0; rr < RPT + 2; rr++) {
-      const unsigned w0 = R4[rr * RS], w1 = R4[rr * RS + 1];
-      unsigned sh[3];
-      sh[0] = w0;                           // window column shift -1
-      sh[1] = __funnelshift_r(w0, w1, 8);   //                      0
-      sh[2] = __funnelshift_r(w0, w1, 16);  //                     +1
-#pragma unroll
-      for (int wdy = -1; wdy <= 1; wdy++) {
-        const int r = rr - 1 - wdy;  // block row paired with window row rr under vertical shift wdy
-        if (r >= 0 && r < RPT) {
-#pragma unroll
-          for (int wdx = -1; wdx <= 1; wdx++) {
-            const int a = d * 9 + (wdy + 1) * 3 + wdx + 1;
-            acc[a] = __vsadu4(p[r], sh[wdx + 1]) + acc[a];
-          }
-        }
-      }
-    }
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int k = 0; k < 18; k++) {
-    unsigned v = __reduce_add_sync(0xffffffffu, acc[k]);
-    if (lane == 0) s_err[warp][k] = (int)v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 18) {
-    // candidate k of direction dd tests the window shift sgn * (dy, dx)
-    constexpr int DY[9] = {-1, -1, 1, 1, -1, 1, 0, 0, 0};
-    constexpr int DX[9] = {-1, 1, -1, 1, 0, 0, 1, -1, 0};
-    const int dd = threadIdx.x / 9, k = threadIdx.x % 9;
-    const int sgn = dd ? -1 : 1;
-    const int slot = dd * 9 + (sgn * DY[k] + 1) * 3 + sgn * DX[k] + 1;
-    int e = 0;
-    for (int w = 0; w < NWARP; w++) e += s_err[w][slot];
-    s_fin[threadIdx.x] = e;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
+  sad_finish<W>(q, acc, s_err, pair, by, bx, c);
 }
 
 // ------------------------------------------------------------ exact path
@@ -789,27 +831,93 @@ __device__ __forceinline__ void load_window(const SubpelParams &q, const B0View 
   }
 }
 
+// Blocks whose windows touch the polluted strips or leave the picture.  The predicted block is
+// always bytes (predicted frames are never border-filled and the block has no non-byte tile), so
+// for a window sample r of any value |p - r| = |p - clamp(r, 0, 255)| + excess(r) with
+// excess(r) = r - 255 above, -r below, 0 inside.  The kernel stages the clamped windows and their
+// excess as byte windows (column 0 word-aligned) and runs the packed-byte SAD core on both;
+// a sample with excess > 255 (the malloc size field) sends the block to the exact generator.
 template <int W>
-__global__ void __launch_bounds__(256) k_subpel_strip(SubpelParams q, B0View v) {
-  constexpr int RW = W + 2;
-  extern __shared__ short sm[];
-  short *Ps = sm, *Rs0 = Ps + W * W, *Rs1 = Rs0 + RW * RW;
-  __shared__ int s_part[8][18];
-  __shared__ int s_fin[18];
+__global__ void __launch_bounds__(2 * W) k_subpel_strip(SubpelParams q, B0View v) {
+  constexpr int WPR = W / 4, RPT = W / 4, NT = 2 * W;
+  constexpr int RW = W + 2, TP = (W + 4) / 4;  // window rows, words per staged row (odd pitch: no bank conflicts)
+  __shared__ __align__(16) unsigned sP[W * WPR];
+  __shared__ unsigned sC[2][RW * TP];
+  __shared__ unsigned sE[2][RW * TP];
+  __shared__ int s_err[NT / 32][9];
+  const int Yl = q.Y << q.l, Xl = q.X << q.l;
   const int total = *q.slow_count;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int id = q.slow_list[item];
     const int bx = id % q.BX, by = (id / q.BX) % q.BY, pair = id / (q.BX * q.BY);
     short c[4];
     subpel_centre(q, pair, by, bx, c);
-    const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
+    const int rs[2] = {q.slots[3 * pair], q.slots[3 * pair + 1]};
+    const int ps = q.slots[3 * pair + 2];
     const int py0 = by * W, px0 = bx * W;
-    load_window<W, W, false>(q, v, ps, py0, px0, Ps);
-    load_window<RW, RW, true>(q, v, r0s, py0 + c[MV_PREV_Y] - 1, px0 + c[MV_PREV_X] - 1, Rs0);
-    load_window<RW, RW, true>(q, v, r1s, py0 + c[MV_NEXT_Y] - 1, px0 + c[MV_NEXT_X] - 1, Rs1);
-    __syncthreads();
-    sad_windows<W>(Ps, Rs0, Rs1, s_part, s_fin);
-    if (threadIdx.x == 0) subpel_store(q, pair, by, bx, c, s_fin);
+    const int wy[2] = {py0 + c[MV_PREV_Y] - 1, py0 + c[MV_NEXT_Y] - 1};
+    const int wx[2] = {px0 + c[MV_PREV_X] - 1, px0 + c[MV_NEXT_X] - 1};
+    {  // predicted block: inside the picture, 16-byte aligned rows
+      const uint8_t *vp = q.v + (long long)ps * q.v_slot_stride + (long long)py0 * q.v_pitch + px0;
+      for (int i = threadIdx.x; i < W * (W / 16); i += NT) {
+        const int y = i / (W / 16), w = i % (W / 16);
+        reinterpret_cast<uint4 *>(sP)[i] = __ldg(reinterpret_cast<const uint4 *>(vp + (long long)y * q.v_pitch) + w);
+      }
+    }
+    int flags = 0;  // 1: some excess is non-zero, 2: some excess does not fit a byte
+    for (int i = threadIdx.x; i < 2 * RW * TP; i += NT) {
+      const int d = i / (RW * TP), r = i - d * (RW * TP), yy = r / TP, w = r - yy * TP;
+      const int slot = rs[d], y = wy[d] + yy, x = wx[d] + 4 * w;
+      unsigned cw = 0, ew = 0;
+      const bool row_in = y >= 0 && y < Yl, cols_in = x >= 0 && x + 3 < Xl;
+      if (row_in && y >= q.clean && x >= q.clean && x + 3 < Xl) {
+        // byte plane: unaligned word = two aligned words + funnel shift
+        const uint8_t *vb = q.v + (long long)slot * q.v_slot_stride + (long long)y * q.v_pitch + x;
+        const unsigned *a4 = reinterpret_cast<const unsigned *>(vb - ((uintptr_t)vb & 3));
+        const unsigned sa = 8 * (unsigned)((uintptr_t)vb & 3);
+        const unsigned lo = __ldg(a4);
+        cw = sa ? __funnelshift_r(lo, __ldg(a4 + 1), sa) : lo;
+      } else {
+        int s4[4];
+        if (row_in && cols_in && (y < q.clean || x + 3 < q.clean)) {
+          const short *src = y < q.clean
+                                 ? q.strip_top + (long long)slot * q.strip_top_stride + (long long)y * Xl + x
+                                 : q.strip_left + (long long)slot * q.strip_left_stride +
+                                       (long long)(y - q.clean) * q.clean + x;
+#pragma unroll
+          for (int k = 0; k < 4; k++) s4[k] = src[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) s4[k] = level_cell(q, v, slot, y, x + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int cl = min(max(s4[k], 0), 255);
+          const int ex = abs(s4[k] - cl);
+          // columns >= W + 2 of the staged row are never read by the SAD core
+          if (4 * w + k < RW) flags |= (ex != 0) | ((ex > 255) << 1);
+          cw |= (unsigned)cl << (8 * k);
+          ew |= (unsigned)(ex & 255) << (8 * k);
+        }
+      }
+      sC[d][r] = cw;
+      sE[d][r] = ew;
+    }
+    const int any_ex = __syncthreads_or(flags);  // (a boolean) also publishes the staged windows
+    if (any_ex && __syncthreads_or(flags & 2)) {
+      queue_block(q, 2, pair, by, bx);
+    } else {
+      const int d = threadIdx.x / W, t = threadIdx.x % W;
+      const int j = t % WPR, g = t / WPR;
+      const unsigned *P4 = sP + (g * RPT) * WPR + j;
+      const unsigned *R4 = sC[d] + (g * RPT) * TP + j, *E4 = sE[d] + (g * RPT) * TP + j;
+      unsigned acc[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) acc[k] = 0;
+      if (any_ex) sad_rows<W, 0, true>(P4, R4, E4, TP, acc);
+      else sad_rows<W, 0, false>(P4, R4, E4, TP, acc);
+      sad_finish<W>(q, acc, s_err, pair, by, bx, c);
+    }
     __syncthreads();
   }
 }
@@ -1000,28 +1108,22 @@ __global__ void __launch_bounds__(256) k_subpel_exact(SubpelParams q, B0View v) 
 
 template <int W>
 static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) {
-  constexpr int NT = (W / 4) * (W / 8);
   dim3 grid(q.BX, q.BY, npairs);
   {
     ProfScope ps_(L, KC_SEARCH);
+    const CUtensorMap &tp = *reinterpret_cast<const CUtensorMap *>(q.tm_p);
+    const CUtensorMap &tr = *reinterpret_cast<const CUtensorMap *>(q.tm_r);
     if (q.use_tma)
-      k_subpel_tma<W><<<grid, NT, 0, L.stream>>>(q, *reinterpret_cast<const CUtensorMap *>(q.tm_p),
-                                                       *reinterpret_cast<const CUtensorMap *>(q.tm_r));
+      k_subpel_tma<W, 1><<<grid, 2 * W, 0, L.stream>>>(q, tp, tr);
     else
-      k_subpel_fast<W><<<grid, NT, 0, L.stream>>>(q);
+      k_subpel_fast<W><<<grid, (W / 4) * (W / 8), 0, L.stream>>>(q);
     COUNT(L);
   }
   B0View v = make_b0view(q);
   const int RW = W + 2, TW = W / 2 + 4;
   {
-    size_t smem1 = ((size_t)W * W + 2 * (size_t)RW * RW) * sizeof(short);
-    static size_t s_attr1 = 0;
-    if (smem1 > 48 * 1024 && smem1 > s_attr1) {
-      cudaFuncSetAttribute(k_subpel_strip<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-      s_attr1 = smem1;
-    }
     ProfScope ps_(L, KC_SEARCH_EXACT);
-    k_subpel_strip<W><<<148 * 6, 256, smem1, L.stream>>>(q, v);
+    k_subpel_strip<W><<<148 * 8, 2 * W, 0, L.stream>>>(q, v);
     COUNT(L);
   }
   size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW + (size_t)TW * TW + 2 * (size_t)RW * TW + 4 * (size_t)TW * TW) *
@@ -1050,9 +1152,10 @@ void launch_subpel(const Launch &L, const SubpelParams &q, int W, int npairs) {
 
 // Tensor maps over the V_l planes of all slots seen as one tall 2-D u8 tensor
 // (pitch bytes wide, nslots * rows_per_slot rows): box W x W for the predicted block
-// and (W+32) x (W+2) for the windows (fetched from a 16-byte aligned column).  Encoded through the driver entry point so the
+// and box_w x (W+2) for the windows (W + 32 when fetched from a 16-byte aligned column, W + 16
+// when fetched at the window's own column).  Encoded through the driver entry point so the
 // library does not link against libcuda.
-bool subpel_make_tensor_maps(const uint8_t *v, int pitch, long long total_rows, int W, void *tm_p,
+bool subpel_make_tensor_maps(const uint8_t *v, int pitch, long long total_rows, int W, int box_w, void *tm_p,
                              void *tm_r) {
   typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -1075,7 +1178,7 @@ bool subpel_make_tensor_maps(const uint8_t *v, int pitch, long long total_rows, 
   cuuint64_t gstride[1] = {(cuuint64_t)pitch};
   cuuint32_t estr[2] = {1, 1};
   cuuint32_t boxp[2] = {(cuuint32_t)W, (cuuint32_t)W};
-  cuuint32_t boxr[2] = {(cuuint32_t)(W + 32), (cuuint32_t)(W + 2)};
+  cuuint32_t boxr[2] = {(cuuint32_t)box_w, (cuuint32_t)(W + 2)};
   CUresult a = encode((CUtensorMap *)tm_p, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)v, gdim, gstride, boxp, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
