@@ -103,6 +103,7 @@ struct SubpelParams {
   int v_rows_per_slot;   // v_slot_stride / v_pitch
   int use_tma;           // tm_p / tm_r hold valid CUtensorMap objects; 1: windows at 16-byte aligned columns, 2: at their own column
   int debug;             // env QSVC_SUBPEL_DEBUG: 1 = fast blocks go to the strip kernel, 2 = strip blocks go to the exact generator
+  int npairs, pair_group;  // TMA kernel: block order (launch_subpel fills these)
   int check_tiles;       // 0: every tile of every slot is known to hold bytes (tile_bad not consulted)
   alignas(64) unsigned char tm_p[128];
   alignas(64) unsigned char tm_r[128];

@@ -265,10 +265,11 @@ struct Marcher {
   }
 
   // (r0 + r1) / 2 on bytes; the [0,255] clip of decorrelate.cpp:841-848 is a no-op
-  static __device__ __forceinline__ void combine(const RawPair &w, int k, unsigned &lo, unsigned &hi) {
-    lo = __vhaddu4(__funnelshift_r(w.a[3 * k], w.a[3 * k + 1], w.sa), __funnelshift_r(w.b[3 * k], w.b[3 * k + 1], w.sb));
-    hi = __vhaddu4(__funnelshift_r(w.a[3 * k + 1], w.a[3 * k + 2], w.sa),
-                   __funnelshift_r(w.b[3 * k + 1], w.b[3 * k + 2], w.sb));
+  static __device__ __forceinline__ void combine(const RawPair &w, int sa_, int sb_, int k, unsigned &lo,
+                                                 unsigned &hi) {
+    lo = __vhaddu4(__funnelshift_r(w.a[3 * k], w.a[3 * k + 1], sa_), __funnelshift_r(w.b[3 * k], w.b[3 * k + 1], sb_));
+    hi = __vhaddu4(__funnelshift_r(w.a[3 * k + 1], w.a[3 * k + 2], sa_),
+                   __funnelshift_r(w.b[3 * k + 1], w.b[3 * k + 2], sb_));
   }
 
   // the NOUT <= 4 input bytes of this lane in output row e
@@ -347,8 +348,8 @@ struct Marcher {
     int xe[4] = {0, 0, 0, 0}, xo[4] = {0, 0, 0, 0};
     if (!SP || t < half1) {
       unsigned lo0, hi0, lo1, hi1;
-      combine(nx, 0, lo0, hi0);
-      combine(nx, 1, lo1, hi1);
+      combine(nx, nx.sa, nx.sb, 0, lo0, hi0);
+      combine(nx, nx.sa, nx.sb, 1, lo1, hi1);
       // rows of the next step are in flight while this one is computed
       if (FAST_FETCH) fetch2_fast<true>(2 * t + 2, nx);
       else if (!SP || t < t_fetch) fetch2(2 * t + 2, nx);
@@ -427,7 +428,7 @@ struct Marcher {
           nx.a[3] = nx.a[4] = nx.a[5] = nx.b[3] = nx.b[4] = nx.b[5] = 0;
           nx.sa = xin0 ? sa : 0;
           nx.sb = xin1 ? sb : 0;
-          combine(nx, 0, lo, hi);
+          combine(nx, nx.sa, nx.sb, 0, lo, hi);
         }
         int p[8];
 #pragma unroll
@@ -506,18 +507,26 @@ __device__ __forceinline__ void mc_march(const MarchParams &q, int pair, int c, 
   m.run();
 }
 
-// grid (ceil(nstrips * nsegs / 4), nc * pairs), 128 threads: one warp = one (strip, segment) of
-// component c0 + blockIdx.y % nc (luma and chroma have different level counts: two launches)
+// 128 threads: one warp = one (strip, segment) of component c0 + .. % nc (luma and chroma have
+// different level counts: two launches).  A (pair, component) plane takes nb CTAs in
+// segment-major order.  Block order inside a group of G consecutive pairs (blockIdx.z = group):
+// chunks of KC CTAs (about one segment) -> pair of the group -> component -> CTA of the chunk, so
+// that the even frame shared by pairs i-1 (NEXT) and i (PREV) is fetched from DRAM once.
 template <int NLEV, bool EXTRA>
-__global__ void __launch_bounds__(128, 5) k_mc_march(MarchParams q, int c0, int nc) {
+__global__ void __launch_bounds__(128, 5) k_mc_march(MarchParams q, int c0, int nc, int npairs, int G, int KC,
+                                                     int nb) {
   __shared__ int h_pred[EXTRA ? 256 : 1], h_res[EXTRA ? 256 : 1];
-  const int pair = blockIdx.y / nc, c = c0 + blockIdx.y % nc;
+  const int per_chunk = G * nc * KC;
+  const int chunk = blockIdx.x / per_chunk, rem = blockIdx.x - chunk * per_chunk;
+  const int pgc = rem / KC, k = chunk * KC + (rem - pgc * KC);
+  const int pair = blockIdx.z * G + pgc / nc, c = c0 + pgc % nc;
+  if (pair >= npairs || k >= nb) return;
   const bool do_hist = EXTRA && q.hist && c == 0 && !q.synth;
   if (do_hist) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) h_pred[i] = h_res[i] = 0;
     __syncthreads();
   }
-  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int idx = k * 4 + (threadIdx.x >> 5);
   const int strip = idx % q.nstrips, seg = idx / q.nstrips;
   if (seg < q.nsegs) mc_march<NLEV, EXTRA>(q, pair, c, strip, seg, h_pred, h_res, do_hist);
   if (do_hist) {
@@ -532,10 +541,13 @@ __global__ void __launch_bounds__(128, 5) k_mc_march(MarchParams q, int c0, int 
 
 template <int NLEV>
 static void launch_march_n(const Launch &L, const MarchParams &q, int npairs, int c0, int nc) {
-  dim3 grid((q.nstrips * q.nsegs + 3) / 4, nc * npairs);
+  const int nb = (q.nstrips * q.nsegs + 3) / 4, KC = (q.nstrips + 3) / 4;
+  const int G = npairs < 4 ? npairs : 4;
+  const int nchunks = (nb + KC - 1) / KC;
+  dim3 grid(G * nc * KC * nchunks, 1, (npairs + G - 1) / G);
   ProfScope ps_(L, KC_RESIDUE);
-  if (q.hist || q.prediction) k_mc_march<NLEV, true><<<grid, 128, 0, L.stream>>>(q, c0, nc);
-  else k_mc_march<NLEV, false><<<grid, 128, 0, L.stream>>>(q, c0, nc);
+  if (q.hist || q.prediction) k_mc_march<NLEV, true><<<grid, 128, 0, L.stream>>>(q, c0, nc, npairs, G, KC, nb);
+  else k_mc_march<NLEV, false><<<grid, 128, 0, L.stream>>>(q, c0, nc, npairs, G, KC, nb);
   COUNT(L);
 }
 

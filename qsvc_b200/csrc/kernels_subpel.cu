@@ -452,6 +452,25 @@ __device__ __forceinline__ void sad_finish(const SubpelParams &q, const unsigned
 // byte offset (four instantiations).  ALIGNED = 0 would start the box at wx itself (W + 16
 // bytes): measured on B200, a u8 box at a column that is not a multiple of 16 raises
 // "illegal instruction", so only ALIGNED = 1 is instantiated.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar) {
+  unsigned done = 0;
+  const unsigned addr = smem_u32(bar);
+  unsigned long long t0 = 0;
+  for (int spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr)
+        : "memory");
+    if (!done && (spin & 1023) == 1023) {  // never hang the GPU: give up after 50 ms
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 50000000ull) { atomicAdd(&g_tma_timeouts, 1); break; }
+    }
+  }
+}
+
 template <int W, int ALIGNED>
 __global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __grid_constant__ CUtensorMap tmP,
                                                       const __grid_constant__ CUtensorMap tmR) {
@@ -464,53 +483,91 @@ __global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __gr
   __shared__ __align__(128) unsigned char sT[2][TB];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ int s_err[NT / 32][9];
+  __shared__ int s_blk[8];  // doubled + clamped centre vectors, R0 / R1 / P slots
 
-  const int bx = blockIdx.x, by = blockIdx.y, pair = blockIdx.z;
-  const int l = q.l;
-  short c[4];
-  subpel_centre(q, pair, by, bx, c);
-  const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
+  // block order: bx fastest, then the pairs of a group, then by, then the groups -- pair i's
+  // PREV window and pair i-1's NEXT window come from the same even frame and now meet in L2
+  const int bx = blockIdx.x, by = blockIdx.y / q.pair_group;
+  const int pair = blockIdx.z * q.pair_group + blockIdx.y % q.pair_group;
+  if (pair >= q.npairs) return;
+  const int l = q.l, Yl = q.Y << l, Xl = q.X << l;
   const int py0 = by * W, px0 = bx * W;
-  const int wy[2] = {py0 + c[MV_PREV_Y] - 1, py0 + c[MV_NEXT_Y] - 1};
-  const int wx[2] = {px0 + c[MV_PREV_X] - 1, px0 + c[MV_NEXT_X] - 1};
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  {
-    const int kind = classify_block<W, NT>(q, l, r0s, r1s, ps, py0, px0, wy, wx);  // contains a block barrier
-    if (kind) {
-      queue_block(q, kind, pair, by, bx);
-      return;
+  const int lane = threadIdx.x & 31;
+  int blk[7] = {0, 0, 0, 0, 0, 0, 0};
+  bool fast;
+  auto geometry = [&](int wy[2], int wx[2]) {
+    wy[0] = py0 + blk[MV_PREV_Y] - 1;
+    wy[1] = py0 + blk[MV_NEXT_Y] - 1;
+    wx[0] = px0 + blk[MV_PREV_X] - 1;
+    wx[1] = px0 + blk[MV_NEXT_X] - 1;
+    bool f = true;
+#pragma unroll
+    for (int d = 0; d < 2; d++)
+      f = f && wy[d] >= q.clean && wx[d] >= q.clean && wy[d] + W + 2 <= Yl && wx[d] + W + 2 <= Xl;
+    return f && !(q.debug & 1);
+  };
+  int wy[2], wx[2];
+  if (threadIdx.x < 32) {
+    // warp 0: one global load per lane (four vector components, three slots), shared by
+    // shuffles; lane 0 starts the TMA loads before anybody else has looked at the block
+    const long long plane = (long long)q.BY * q.BX;
+    int v = 0;
+    if (lane < 4) {
+      short m = q.mv_in[(long long)pair * 4 * plane + lane * plane + (long long)by * q.BX + bx];
+      m = (short)(m * 2);
+      if (m > q.lim) m = (short)q.lim;
+      if (m < -q.lim) m = (short)(-q.lim);
+      v = m;
+    } else if (lane < 7) {
+      v = q.slots[3 * pair + lane - 4];
     }
-  }
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)),
-                 "r"(W * W + 2 * TBYTES)
-                 : "memory");
-    tma_load_2d(sP, &tmP, px0, ps * q.v_rows_per_slot + py0, &bar);
-    tma_load_2d(sT[0], &tmR, ALIGNED ? (wx[0] & ~15) : wx[0], r0s * q.v_rows_per_slot + wy[0], &bar);
-    tma_load_2d(sT[1], &tmR, ALIGNED ? (wx[1] & ~15) : wx[1], r1s * q.v_rows_per_slot + wy[1], &bar);
-  }
-  {
-    unsigned done = 0;
-    const unsigned addr = smem_u32(&bar);
-    unsigned long long t0 = 0;
-    for (int spin = 0; !done; spin++) {
-      asm volatile(
-          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
-          : "=r"(done)
-          : "r"(addr)
-          : "memory");
-      if (!done && (spin & 1023) == 1023) {  // never hang the GPU: give up after 50 ms
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 50000000ull) { atomicAdd(&g_tma_timeouts, 1); break; }
+#pragma unroll
+    for (int k = 0; k < 7; k++) blk[k] = __shfl_sync(0xffffffffu, v, k);
+    fast = geometry(wy, wx);
+    if (lane < 7) s_blk[lane] = v;
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (fast) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)),
+                     "r"(W * W + 2 * TBYTES)
+                     : "memory");
+        tma_load_2d(sP, &tmP, px0, blk[6] * q.v_rows_per_slot + py0, &bar);
+        tma_load_2d(sT[0], &tmR, ALIGNED ? (wx[0] & ~15) : wx[0], blk[4] * q.v_rows_per_slot + wy[0], &bar);
+        tma_load_2d(sT[1], &tmR, ALIGNED ? (wx[1] & ~15) : wx[1], blk[5] * q.v_rows_per_slot + wy[1], &bar);
       }
     }
   }
+  __syncthreads();
+  if (threadIdx.x >= 32) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) blk[k] = s_blk[k];
+    fast = geometry(wy, wx);
+  }
+  int bad = 0;
+  if (q.check_tiles) {
+    // 16x16 level-0 tiles under the three images' footprints: at most 4 x 4 each
+    if (threadIdx.x < 48) {
+      const int img = threadIdx.x >> 4, ty = (threadIdx.x >> 2) & 3, tx = threadIdx.x & 3;
+      const int slot = blk[4 + img];
+      const int y0 = img == 2 ? py0 : wy[img], x0 = img == 2 ? px0 : wx[img];
+      const int span = img == 2 ? W : W + 2;
+      const int pyl = max(y0 >> l, 0), pyh = min(((y0 + span - 1) >> l) + 1, q.Y - 1);
+      const int pxl = max(x0 >> l, 0), pxh = min(((x0 + span - 1) >> l) + 1, q.X - 1);
+      const int tyy = (pyl >> 4) + ty, txx = (pxl >> 4) + tx;
+      if (pyl <= pyh && pxl <= pxh && tyy <= (pyh >> 4) && txx <= (pxh >> 4))
+        bad = q.tile_bad[(long long)slot * q.tiles_per_slot + tyy * q.tiles_x + txx];
+    }
+    bad = __syncthreads_or(bad);
+  }
+  if ((q.debug & 2) && !fast) bad = 1;  // debug: the strip kernel is bypassed
+  if (bad || !fast) {
+    if (fast) mbar_wait(&bar);  // the loads in flight must land before the block retires
+    queue_block(q, bad ? 2 : 1, pair, by, bx);
+    return;
+  }
+  mbar_wait(&bar);
   const int d = threadIdx.x / W, t = threadIdx.x % W;  // one direction per warp
   const int j = t % WPR, g = t / WPR;
   const unsigned *P4 = reinterpret_cast<const unsigned *>(sP) + (g * RPT) * WPR + j;
@@ -529,6 +586,7 @@ __global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __gr
   } else {
     sad_rows<W, 0, false>(P4, R4, nullptr, TP, acc);
   }
+  short c[4] = {(short)blk[0], (short)blk[1], (short)blk[2], (short)blk[3]};
   sad_finish<W>(q, acc, s_err, pair, by, bx, c);
 }
 
@@ -1111,10 +1169,14 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
   dim3 grid(q.BX, q.BY, npairs);
   {
     ProfScope ps_(L, KC_SEARCH);
+    SubpelParams qg = q;
+    qg.npairs = npairs;
+    qg.pair_group = npairs < 8 ? npairs : 8;
+    const dim3 ggrid(q.BX, q.BY * qg.pair_group, (npairs + qg.pair_group - 1) / qg.pair_group);
     const CUtensorMap &tp = *reinterpret_cast<const CUtensorMap *>(q.tm_p);
     const CUtensorMap &tr = *reinterpret_cast<const CUtensorMap *>(q.tm_r);
     if (q.use_tma)
-      k_subpel_tma<W, 1><<<grid, 2 * W, 0, L.stream>>>(q, tp, tr);
+      k_subpel_tma<W, 1><<<ggrid, 2 * W, 0, L.stream>>>(qg, tp, tr);
     else
       k_subpel_fast<W><<<grid, (W / 4) * (W / 8), 0, L.stream>>>(q);
     COUNT(L);
