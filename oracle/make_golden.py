@@ -17,25 +17,27 @@ sys.path.insert(0, ROOT)
 from oracle import run_ref  # noqa: E402
 from qsvc_b200 import yuv  # noqa: E402
 
-# name: X, Y, GOPs, TRLs, bs, sr, a, uf, always_B, flat_every, seed
+# name: X, Y, GOPs, TRLs, bs, sr, a, uf, always_B, flat_every, seed[, block_overlaping]
 CASES = {
     "ib_types_a0":   (64, 48, 2, 3, 16, 4, 0, 0.25, 0, 2, 21),   # IBIB frame types, update 1/4
     "quarter_pel":   (64, 48, 1, 4, 16, 8, 2, 0.3, 0, 0, 22),    # border pollution, size-field reads
     "ragged_height": (64, 40, 2, 4, 16, 4, 1, 0.0, 0, 0, 23),    # Y % bs != 0: chained tail rows
     "odd_pyramid":   (64, 60, 2, 3, 8, 32, 0, 0.0, 1, 0, 24),    # non-invertible pyramid descent
+    "obmc_half_pel": (64, 48, 1, 3, 16, 4, 1, 0.25, 0, 0, 25, 2),  # block_overlaping=2: per-block DWT + scatter
 }
 
 
-def make(name, X, Y, GOPs, TRLs, bs, sr, a, uf, always_B, flat, seed):
+def make(name, X, Y, GOPs, TRLs, bs, sr, a, uf, always_B, flat, seed, ov=0):
     frames = GOPs * 2 ** (TRLs - 1) + 1
     clip = yuv.synthetic_clip(X, Y, frames, seed, max_shift=min(24, 3 * sr), flat_every=flat)
     d = tempfile.mkdtemp(prefix="golden_")
     try:
         yuv.write_frames(os.path.join(d, "low_0"), clip)
-        sched = run_ref.analyze(d, X, Y, GOPs, TRLs, bs, sr, a, uf, always_B, block_size_min=bs)
+        sched = run_ref.analyze(d, X, Y, GOPs, TRLs, bs, sr, a, uf, always_B, block_overlaping=ov, block_size_min=bs)
         out = {"low_0": clip,
                "params": np.array([X, Y, GOPs, TRLs, bs, sr, a, always_B], np.int64),
-               "update_factor": np.array([uf], np.float64)}
+               "update_factor": np.array([uf], np.float64),
+               "block_overlaping": np.array([ov], np.int64)}
         for s in sched:
             t, n = s["t"], s["pictures"] // 2
             out[f"motion_{t}"] = yuv.read_motion(os.path.join(d, f"motion_{t}"), X, Y, bs, n)
@@ -52,7 +54,7 @@ def make(name, X, Y, GOPs, TRLs, bs, sr, a, uf, always_B, flat, seed):
             os.remove(os.path.join(d, f"odd_{t}"))
         for t in range(0, TRLs - 1):
             os.remove(os.path.join(d, f"low_{t}"))
-        run_ref.synthesize(d, X, Y, GOPs, TRLs, bs, sr, a, uf)
+        run_ref.synthesize(d, X, Y, GOPs, TRLs, bs, sr, a, uf, block_overlaping=ov)
         for t in range(1, TRLs):
             out[f"syn_even_{t}"] = yuv.read_frames(os.path.join(d, f"even_{t}"), X, Y)
             out[f"syn_odd_{t}"] = yuv.read_frames(os.path.join(d, f"odd_{t}"), X, Y)
@@ -67,5 +69,7 @@ def make(name, X, Y, GOPs, TRLs, bs, sr, a, uf, always_B, flat, seed):
 
 if __name__ == "__main__":
     assert run_ref.build(), "oracle/_ref is missing and /root/reference is not available"
+    only = sys.argv[1:]
     for k, v in CASES.items():
-        make(k, *v)
+        if not only or k in only:
+            make(k, *v)

@@ -613,8 +613,21 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
                     uint8_t *out, long long out_stride, std::string *types_out, short *mv_out,
                     uint8_t *prediction_out) {
   TRY(check_geometry(X, Y, bs, a));
-  if (ov != 0)
-    return fail(QSVC_EINVAL, "block_overlaping=%d: the OBMC path (decorrelate.cpp:110-172) is not implemented", ov);
+  if (ov < 0) return fail(QSVC_EINVAL, "bad block_overlaping");
+  int ov_levels = 0;
+  if (ov > 0) {
+    // decorrelate.cpp:84-88: levels of the per-block transform.  Areas no block covers would keep
+    // the previous pair's transformed leftovers and then go through the picture synthesis (A.2.6);
+    // that history is not reproduced for the overlapped mode: refuse such geometries.
+    if (X % bs != 0 || Y % bs != 0)
+      return fail(QSVC_EINVAL, "block_overlaping > 0 needs pictures that are multiples of the block size");
+    if (!predict_obmc_supported(bs << a, ov << a))
+      return fail(QSVC_EINVAL, "block_overlaping=%d: extended block does not fit shared memory", ov);
+    ov_levels = (int)rint(log((double)(ov << a)) / log(2.0));
+    if (ov_levels < 0) ov_levels = 0;
+    if (((bs << a) >> ov_levels) == 0)
+      return fail(QSVC_EINVAL, "block_overlaping=%d: more transform levels than the block has", ov);
+  }
   const int BY = Y / bs, BX = X / bs;
   const long long field = 4LL * BY * BX;
   const long long fb = frame_bytes(X, Y);
@@ -663,8 +676,14 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
     q.Xa = Xa;
     q.ba = ba;
     q.padh = padh;
-    launch_predict(Lh, q);
-    launch_clip_uncovered(Lh, pred.p, Ya, Xa, BY * bsa, BX * bsa);
+    if (ov > 0) {
+      launch_predict_obmc(Lh, q, ov << a, ov_levels);
+      dwt_synthesize(Lh, pred.p, 0, 3, Ya, Xa, ov_levels);
+      launch_clip_uncovered(Lh, pred.p, Ya, Xa, 0, 0);  // decorrelate.cpp:841-848 over the whole picture
+    } else {
+      launch_predict(Lh, q);
+      launch_clip_uncovered(Lh, pred.p, Ya, Xa, BY * bsa, BX * bsa);
+    }
     dwt_analyze(Lh, pred.p, 0, 3, Ya, Xa, a);
     dwt_analyze(Lh, pred.p, 1, 2, Y, X, 1);
     ResidueParams r;

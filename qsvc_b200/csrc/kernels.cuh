@@ -139,6 +139,9 @@ struct PredictParams {
   int padh;           // (malloc chunk - row bytes)/2 in shorts (heap alias rule)
 };
 void launch_predict(const Launch &L, const PredictParams &q);
+// block_overlaping > 0: per-block analysis + sub-band scatter (the caller synthesises the picture)
+bool predict_obmc_supported(int bsa, int ova);
+void launch_predict_obmc(const Launch &L, const PredictParams &q, int ova, int levels);
 // clip to [0,255] everything outside the covered area [0,cy) x [0,cx)
 void launch_clip_uncovered(const Launch &L, Plane pred, int Ya, int Xa, int cy, int cx);
 

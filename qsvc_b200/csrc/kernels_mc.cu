@@ -1,6 +1,6 @@
 // kernels_mc.cu -- motion-compensated predict / update lifting steps.
 //
-// Reference: decorrelate.cpp:69-108 (predict, block_overlaping == 0),
+// Reference: decorrelate.cpp:69-189 (predict, with and without block_overlaping),
 // :841-848 (clip), :920-929 / :1009-1022 / :1038-1066 (residue, re-bias,
 // inverse), :799-816 / :940-953 (histograms); update.cpp:71-148 (update).
 #include "kernels.cuh"
@@ -37,6 +37,82 @@ void launch_predict(const Launch &L, const PredictParams &q) {
   dim3 grid((cx + 1023) / 1024, cy < 2048 ? cy : 2048, 3);
   ProfScope ps_(L, KC_PREDICT);
   k_predict<<<grid, 256, 0, L.stream>>>(q);
+  COUNT(L);
+}
+
+// predict() with block_overlaping > 0 (decorrelate.cpp:84-88, 99-172): every block is
+// predicted with a margin of `ova` samples, analysed `levels` levels on its own (in-place
+// Mallat layout of an N x N block, N = bsa + 2*ova), and the inner (bsa >> l)^2 part of each
+// sub-band is scattered into the picture-sized Mallat layout; the caller then synthesises the
+// whole picture `levels` levels.  One CTA per (block, component); the block ping-pongs between
+// two shared-memory buffers (rows: A -> B, columns: B -> A), so after each level it is back in A.
+__global__ void __launch_bounds__(256) k_predict_obmc(PredictParams q, int ova, int levels) {
+  extern __shared__ short obmc_sm[];
+  const int N = q.bsa + 2 * ova;
+  short *A = obmc_sm, *B = obmc_sm + N * N;
+  const int xb = blockIdx.x, yb = blockIdx.y, c = blockIdx.z;
+  const long long plane = (long long)q.BY * q.BX, b = (long long)yb * q.BX + xb;
+  const short *U0 = q.ref.row(q.r0_slot * 3 + c, 0);
+  const short *U1 = q.ref.row(q.r1_slot * 3 + c, 0);
+  const int y0 = yb * q.bsa + q.mv[MV_PREV_Y * plane + b], x0 = xb * q.bsa + q.mv[MV_PREV_X * plane + b];
+  const int y1 = yb * q.bsa + q.mv[MV_NEXT_Y * plane + b], x1 = xb * q.bsa + q.mv[MV_NEXT_X * plane + b];
+  for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
+    const int y = i / N - ova, x = i % N - ova;
+    const int v = (int)bordered_ref(U0, q.ref.S, q.Ya, q.Xa, q.ba, q.padh, y0 + y, x0 + x) +
+                  (int)bordered_ref(U1, q.ref.S, q.Ya, q.Xa, q.ba, q.padh, y1 + y, x1 + x);
+    A[i] = (short)tdiv2(v);
+  }
+  __syncthreads();
+  int n = N;
+  for (int lv = 0; lv < levels; lv++) {
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+      const int y = i / n, j = i % n;
+      B[y * N + j] = l53_ana_out(A + y * N, 1, j, n);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+      const int j = i / n, x = i % n;
+      A[j * N + x] = l53_ana_out(B + x, N, j, n);
+    }
+    __syncthreads();
+    n >>= 1;
+    if (n == 0) n = 1;
+  }
+  for (int l = 1; l <= levels; l++) {
+    const int s = q.bsa >> l, o_lo = ova >> l, o_hi = (q.bsa + 3 * ova) >> l;
+    const int Yl = q.Ya >> l, Xl = q.Xa >> l;
+    for (int i = threadIdx.x; i < s * s; i += blockDim.x) {
+      const int y = i / s, x = i % s;
+      q.pred.row(c, yb * s + y)[Xl + xb * s + x] = A[(o_lo + y) * N + o_hi + x];
+      q.pred.row(c, Yl + yb * s + y)[xb * s + x] = A[(o_hi + y) * N + o_lo + x];
+      q.pred.row(c, Yl + yb * s + y)[Xl + xb * s + x] = A[(o_hi + y) * N + o_hi + x];
+    }
+  }
+  {
+    const int s = q.bsa >> levels, o = ova >> levels;
+    for (int i = threadIdx.x; i < s * s; i += blockDim.x) {
+      const int y = i / s, x = i % s;
+      q.pred.row(c, yb * s + y)[xb * s + x] = A[(o + y) * N + o + x];
+    }
+  }
+}
+
+bool predict_obmc_supported(int bsa, int ova) {
+  const long long N = bsa + 2LL * ova;
+  return 2 * N * N * (long long)sizeof(short) <= 200 * 1024;
+}
+
+void launch_predict_obmc(const Launch &L, const PredictParams &q, int ova, int levels) {
+  if (q.BY <= 0 || q.BX <= 0) return;
+  const int N = q.bsa + 2 * ova;
+  const size_t smem = 2 * (size_t)N * N * sizeof(short);
+  static size_t s_attr = 0;
+  if (smem > 48 * 1024 && smem > s_attr) {
+    cudaFuncSetAttribute(k_predict_obmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    s_attr = smem;
+  }
+  ProfScope ps_(L, KC_PREDICT);
+  k_predict_obmc<<<dim3(q.BX, q.BY, 3), 256, smem, L.stream>>>(q, ova, levels);
   COUNT(L);
 }
 

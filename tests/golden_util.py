@@ -13,7 +13,8 @@ def load(name):
     X, Y, GOPs, TRLs, bs, sr, a, always_B = (int(v) for v in z["params"])
     g = {k: z[k] for k in z.files}
     g.update(X=X, Y=Y, GOPs=GOPs, TRLs=TRLs, bs=bs, sr=sr, a=a, always_B=always_B,
-             uf=float(z["update_factor"][0]))
+             uf=float(z["update_factor"][0]),
+             ov=int(z["block_overlaping"][0]) if "block_overlaping" in z.files else 0)
     return g
 
 

@@ -20,7 +20,8 @@ MCTF = os.path.join(ROOT, "bin", "mctf")
 def test_api_matches_golden(ctx, name):
     g = load(name)
     X, Y, bs, a, uf, T = g["X"], g["Y"], g["bs"], g["a"], g["uf"], g["TRLs"]
-    got = ctx.analyze(g["low_0"], X, Y, g["GOPs"], T, bs, g["sr"], a, uf, g["always_B"], block_size_min=bs)
+    got = ctx.analyze(g["low_0"], X, Y, g["GOPs"], T, bs, g["sr"], a, uf, g["always_B"],
+                      block_overlaping=g["ov"], block_size_min=bs)
     sub = {f"low_{T-1}": got[f"low_{T-1}"]}
     for t in range(1, T):
         for n in ("motion", "motion_filtered", "high", "low"):
@@ -28,7 +29,7 @@ def test_api_matches_golden(ctx, name):
         assert got[f"frame_types_{t}"] == bytes(g[f"frame_types_{t}"])
         sub[f"high_{t}"], sub[f"motion_{t}"] = got[f"high_{t}"], got[f"motion_filtered_{t}"]
         sub[f"frame_types_{t}"] = got[f"frame_types_{t}"]
-    rec = ctx.synthesize(sub, X, Y, g["GOPs"], T, bs, g["sr"], a, uf)
+    rec = ctx.synthesize(sub, X, Y, g["GOPs"], T, bs, g["sr"], a, uf, g["ov"])
     assert np.array_equal(rec, g["syn_low_0"])
 
 
@@ -38,7 +39,7 @@ def _mctf(args, cwd):
     assert r.returncode == 0, r.stderr.decode()[-2000:]
 
 
-@pytest.mark.parametrize("name", ["ib_types_a0", "quarter_pel"])
+@pytest.mark.parametrize("name", ["ib_types_a0", "quarter_pel", "obmc_half_pel"])
 def test_cli_tool_chain_matches_golden(tmp_path, name):
     """bin/mctf analyze (fused) and the per-step tools (analyze_step) write the same
     files the reference chain writes; bin/mctf synthesize reconstructs its low_0."""
@@ -46,16 +47,17 @@ def test_cli_tool_chain_matches_golden(tmp_path, name):
     X, Y, bs, a, uf, T, GOPs = g["X"], g["Y"], g["bs"], g["a"], g["uf"], g["TRLs"], g["GOPs"]
     common = [f"--pixels_in_x={X}", f"--pixels_in_y={Y}", f"--block_size={bs}",
               f"--subpixel_accuracy={a}", f"--update_factor={uf}"]
+    ovf = [f"--block_overlaping={g['ov']}"] if g["ov"] else []
     d1, d2 = tmp_path / "fused", tmp_path / "steps"
     for d in (d1, d2):
         d.mkdir()
         yuv.write_frames(str(d / "low_0"), g["low_0"])
     _mctf(["analyze", f"--GOPs={GOPs}", f"--TRLs={T}", f"--search_range={g['sr']}",
-           f"--block_size_min={bs}", f"--always_B={g['always_B']}"] + common, str(d1))
+           f"--block_size_min={bs}", f"--always_B={g['always_B']}"] + ovf + common, str(d1))
     pictures = GOPs * 2 ** (T - 1) + 1
     for t, sr in schedule(g):
         _mctf(["analyze_step", f"--pictures={pictures}", f"--search_range={sr}",
-               f"--temporal_subband={t}", f"--always_B={g['always_B']}"] + common, str(d2))
+               f"--temporal_subband={t}", f"--always_B={g['always_B']}"] + ovf + common, str(d2))
         pictures = (pictures + 1) // 2
     for d in (d1, d2):
         for t in range(1, T):
@@ -73,7 +75,7 @@ def test_cli_tool_chain_matches_golden(tmp_path, name):
     _mctf(["synthesize", f"--GOPs={GOPs}", f"--TRLs={T}", f"--search_range={g['sr']}",
            f"--block_size={lists}", f"--pixels_in_x={','.join([str(X)] * (T + 1))}",
            f"--pixels_in_y={','.join([str(Y)] * (T + 1))}",
-           f"--subpixel_accuracy={','.join([str(a)] * (T + 1))}", f"--update_factor={uf}"], str(d2))
+           f"--subpixel_accuracy={','.join([str(a)] * (T + 1))}", f"--update_factor={uf}"] + ovf, str(d2))
     assert np.array_equal(yuv.read_frames(str(d2 / "low_0"), X, Y), g["syn_low_0"])
 
 

@@ -151,6 +151,48 @@ def test_mc_literal_and_fused_paths_agree_with_oracle(ctx, mode, X, Y, GOPs, TRL
         ctx.set_mc_mode(0)
 
 
+#             X    Y  bs sr  a  ov
+OBMC_CASES = [
+    (96, 64, 16, 4, 0, 2),     # one transform level on 20 x 20 blocks
+    (64, 48, 16, 4, 1, 2),     # half-pel: two levels on 40 x 40 blocks
+    (64, 64, 16, 4, 2, 4),     # quarter-pel, overlap 4: four levels on 96 x 96 blocks
+    (64, 48, 16, 8, 1, 3),     # overlap that is not a power of two (odd sub-band sizes)
+    (128, 64, 32, 4, 1, 2),    # 32 x 32 blocks
+]
+
+
+@pytest.mark.parametrize("X,Y,bs,sr,a,ov", OBMC_CASES)
+def test_overlapped_block_prediction_matches_oracle(ctx, X, Y, bs, sr, a, ov):
+    """decorrelate / correlate with --block_overlaping > 0 (decorrelate.cpp:84-88, 99-172):
+    per-block 5/3 analysis of the extended block, sub-band scatter, picture synthesis."""
+    clip = yuv.synthetic_clip(X, Y, 5, 29, max_shift=min(24, 3 * sr))
+    even, odd = clip[0::2], clip[1::2]
+    mv = orc.motion_estimate(even, odd, X, Y, bs, sr, a)
+    high_o, types_o, mvf_o, pred_o, rc = orc.decorrelate(even, odd, mv, X, Y, bs, sr, a, ov)
+    assert rc == 0
+    high_g, types_g, mvf_g, pred_g = ctx.decorrelate(even, odd, mv, X, Y, bs, sr, a, block_overlaping=ov,
+                                                     want_prediction=True)
+    assert types_g == types_o
+    bad = np.argwhere(pred_g != pred_o)
+    assert bad.size == 0, f"prediction: {len(bad)} differ, first {bad[:4].tolist()}"
+    assert np.array_equal(high_g, high_o) and np.array_equal(mvf_g, mvf_o)
+    odd_o, _ = orc.correlate(even, high_o, mvf_o, types_o, X, Y, bs, sr, a, ov)
+    odd_g, _ = ctx.correlate(even, high_o, mvf_o, types_o, X, Y, bs, sr, a, block_overlaping=ov)
+    assert np.array_equal(odd_g, odd_o)
+
+
+def test_overlapped_prediction_refuses_ragged_pictures(ctx):
+    """Areas no block covers would carry the previous pair's leftovers through the picture
+    synthesis; the library refuses instead of inventing them."""
+    from qsvc_b200._lib import QsvcError, QSVC_EINVAL
+    X, Y, bs = 64, 40, 16
+    clip = yuv.synthetic_clip(X, Y, 3, 1)
+    mv = np.zeros((1, 4, Y // bs, X // bs), np.int16)
+    with pytest.raises(QsvcError) as e:
+        ctx.decorrelate(clip[0::2], clip[1::2], mv, X, Y, bs, 4, 0, block_overlaping=2)
+    assert e.value.code == QSVC_EINVAL
+
+
 def test_gop_shards_with_tail_exchange_match_the_whole_sequence(ctx):
     """Height % block_size != 0: GOP shards that hand the
     prediction tail state from left to right reproduce the single-process result, analysis

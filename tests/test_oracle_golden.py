@@ -16,7 +16,7 @@ def test_oracle_analysis_matches_reference(name):
         even, odd = low[0::2], low[1::2]
         mv = orc.motion_estimate(even, odd, X, Y, bs, sr, a)
         assert np.array_equal(mv, g[f"motion_{t}"]), f"motion_{t}"
-        high, types, mvf, pred, rc = orc.decorrelate(even, odd, mv, X, Y, bs, sr, a, 0, g["always_B"])
+        high, types, mvf, pred, rc = orc.decorrelate(even, odd, mv, X, Y, bs, sr, a, g["ov"], g["always_B"])
         assert rc == 0
         assert types == bytes(g[f"frame_types_{t}"])
         assert np.array_equal(pred, g[f"prediction_even_{t}"]), f"prediction_even_{t}"
@@ -36,7 +36,7 @@ def test_oracle_synthesis_matches_reference(name):
         mv = g[f"motion_filtered_{t}"]
         even = orc.update(low, g[f"high_{t}"], mv, types, X, Y, bs, uf, inverse=True)
         assert np.array_equal(even, g[f"syn_even_{t}"]), f"even_{t}"
-        odd, _ = orc.correlate(even, g[f"high_{t}"], mv, types, X, Y, bs, sr, a)
+        odd, _ = orc.correlate(even, g[f"high_{t}"], mv, types, X, Y, bs, sr, a, g["ov"])
         assert np.array_equal(odd, g[f"syn_odd_{t}"]), f"odd_{t}"
         low = np.empty((2 * odd.shape[0] + 1, even.shape[1]), np.uint8)
         low[0::2], low[1::2] = even, odd
