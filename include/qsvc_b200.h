@@ -121,6 +121,26 @@ int qsvc_update(qsvc_ctx *ctx, int inverse, const uint8_t *frames_in, const uint
                 const int16_t *motion, const char *frame_types, int n_pairs, int pixels_in_x,
                 int pixels_in_y, int block_size, float update_factor, uint8_t *frames_out);
 
+/* Motion-field (de)correlation: the step after the analysis / before the synthesis on the motion
+ * side (motion_compress.py:141-182, motion_expand.py:147-179).  Fields are n_fields x
+ * [PREV.X, PREV.Y, NEXT.X, NEXT.Y][blocks_in_y][blocks_in_x] int16.
+ *
+ * Replaces `bidirectional_motion_decorrelate` (inverse=0: NEXT -= PREV) and
+ * `bidirectional_motion_correlate` (inverse=1: NEXT += PREV) main(), reference
+ * bidirectional_motion_decorrelate.cpp:25-52,177-215. */
+int qsvc_bidirectional_motion_decorrelate(qsvc_ctx *ctx, int inverse, const int16_t *fields_in,
+                                          int n_fields, int blocks_in_y, int blocks_in_x,
+                                          int16_t *fields_out);
+/* Replaces `interlevel_motion_decorrelate` (inverse=0: residue = predicted - reference/2) and
+ * `interlevel_motion_correlate` (inverse=1: predicted = residue + reference/2) main(), reference
+ * interlevel_motion_decorrelate.cpp:32-69,250-297: field k pairs with reference field k/2
+ * (the level above); `reference` may be NULL with n_reference = 0 (the tool falls back to
+ * /dev/zero when the file is missing); a reference shorter than (n_fields+1)/2 fields repeats
+ * its last field (what the reader's buffer still holds after a short fread). */
+int qsvc_interlevel_motion_decorrelate(qsvc_ctx *ctx, int inverse, const int16_t *fields_in,
+                                       int n_fields, const int16_t *reference, int n_reference,
+                                       int blocks_in_y, int blocks_in_x, int16_t *fields_out);
+
 /* Whole-sequence temporal analysis with the frames kept resident in HBM between
  * levels: the device-side equivalent of analyze.py:107-153 driving
  * analyze_step.py:115-232 (split -> motion_estimate -> decorrelate -> update per
@@ -149,6 +169,10 @@ int qsvc_resident_analyze(qsvc_ctx *ctx, const qsvc_analyze_params *params);
  * low n_pairs(t)+1 frames. */
 int qsvc_resident_fetch(qsvc_ctx *ctx, int level, uint8_t *high, int16_t *motion,
                         int16_t *motion_filtered, char *frame_types, uint8_t *low);
+/* motion_residue_<level> of the resident analysis, computed on the device from the resident
+ * motion_filtered fields the way motion_compress.py:141-182 chains the two tools: interlevel
+ * against level+1 for level < TRLs-1, bidirectional for the top level. */
+int qsvc_resident_fetch_motion_residue(qsvc_ctx *ctx, int level, int16_t *motion_residue);
 /* Work done by the last qsvc_resident_analyze: SAD operations issued by the
  * search kernels and device milliseconds spent in them (summed over levels). */
 int qsvc_resident_stats(qsvc_ctx *ctx, double *sad_ops, float *search_ms, float *total_ms);

@@ -909,3 +909,42 @@ int orc_bordered_view(const uint8_t *luma, int y_img, int x_img, int y_alloc, in
   arena_free(&A);
   return 0;
 }
+
+/* ------------------------------------------------ motion-field (de)correlation */
+
+/* bidirectional_motion_decorrelate.cpp:25-52 (kernel), :195-215 (field loop).
+ * analyze != 0: NEXT -= PREV; else NEXT += PREV.  Fields are [2][2][by][bx] shorts in file order. */
+int orc_bidirectional_motion(int analyze, const int16_t *in, int fields, int by, int bx, int16_t *out) {
+  const long plane = (long)by * bx;
+  for (int i = 0; i < fields; i++) {
+    const int16_t *f = in + (long)i * 4 * plane;
+    int16_t *o = out + (long)i * 4 * plane;
+    memcpy(o, f, sizeof(int16_t) * 4 * plane);
+    for (long k = 0; k < 2 * plane; k++) /* X then Y of NEXT against X then Y of PREV */
+      o[2 * plane + k] = (int16_t)(analyze ? f[2 * plane + k] - f[k] : f[2 * plane + k] + f[k]);
+  }
+  return 0;
+}
+
+/* interlevel_motion_decorrelate.cpp:32-69 (kernel), :250-297 (reader loop): one reference field
+ * per iteration (fread past the end leaves the buffer as it was; a missing file is /dev/zero),
+ * then up to two fields of the predicted (analyze) or residue stream, stopping at its end.
+ * ref == NULL: zeros.  Returns the number of fields written. */
+int orc_interlevel_motion(int analyze, const int16_t *in, int n_in, const int16_t *ref, int n_ref,
+                          int fields_in_predicted, int by, int bx, int16_t *out) {
+  const long fsz = 4L * by * bx;
+  int16_t *reference = calloc((size_t)(fsz > 0 ? fsz : 1), sizeof(int16_t));
+  int rd = 0, wr = 0, rr = 0;
+  for (int i = 0; i < fields_in_predicted; i++) {
+    if (ref && rr < n_ref) memcpy(reference, ref + (long)rr++ * fsz, sizeof(int16_t) * fsz);
+    for (int p = 0; p < 2; p++) {
+      if (rd >= n_in) break; /* feof after the failed read */
+      const int16_t *f = in + (long)rd++ * fsz;
+      int16_t *o = out + (long)wr++ * fsz;
+      for (long k = 0; k < fsz; k++)
+        o[k] = (int16_t)(analyze ? f[k] - reference[k] / 2 : f[k] + reference[k] / 2);
+    }
+  }
+  free(reference);
+  return wr;
+}

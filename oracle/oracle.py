@@ -91,6 +91,30 @@ def correlate(even, high, mv, frame_types, X, Y, block_size, search_range, subpi
     return odd, pred
 
 
+def bidirectional_motion(fields, inverse=False):
+    """bidirectional_motion_decorrelate (inverse: _correlate) on (n, 4, by, bx) int16 fields."""
+    fields = np.ascontiguousarray(fields, np.int16)
+    n, _, by, bx = fields.shape
+    out = np.zeros_like(fields)
+    rc = lib().orc_bidirectional_motion(0 if inverse else 1, _p(fields, C.c_int16), n, by, bx, _p(out, C.c_int16))
+    assert rc == 0
+    return out
+
+
+def interlevel_motion(fields, reference=None, fields_in_predicted=None, inverse=False):
+    """interlevel_motion_decorrelate (inverse: _correlate); reference None = /dev/zero."""
+    fields = np.ascontiguousarray(fields, np.int16)
+    n, _, by, bx = fields.shape
+    if reference is not None:
+        reference = np.ascontiguousarray(reference, np.int16)
+    out = np.zeros_like(fields)
+    wr = lib().orc_interlevel_motion(0 if inverse else 1, _p(fields, C.c_int16), n,
+                                     _p(reference, C.c_int16), 0 if reference is None else reference.shape[0],
+                                     n if fields_in_predicted is None else fields_in_predicted, by, bx,
+                                     _p(out, C.c_int16))
+    return out[:wr]
+
+
 def update(frames_in, high, mv, frame_types, X, Y, block_size, update_factor, inverse=False):
     """update (even->low) or, with inverse=True, un_update (low->even)."""
     frames_in = np.ascontiguousarray(frames_in, np.uint8)

@@ -17,7 +17,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_BIN = os.path.join(_HERE, "_ref")
 SEARCH_RANGE_MAX = 128
 
-TOOLS = ("split", "merge", "motion_estimate", "decorrelate", "correlate", "update", "un_update")
+TOOLS = ("split", "merge", "motion_estimate", "decorrelate", "correlate", "update", "un_update",
+         "bidirectional_motion_decorrelate", "bidirectional_motion_correlate",
+         "interlevel_motion_decorrelate", "interlevel_motion_correlate")
 
 
 def available() -> bool:

@@ -1109,6 +1109,51 @@ int qsvc_update(qsvc_ctx *c, int inverse, const uint8_t *in, const uint8_t *high
   return QSVC_OK;
 }
 
+int qsvc_bidirectional_motion_decorrelate(qsvc_ctx *c, int inverse, const int16_t *in, int n_fields, int by, int bx,
+                                          int16_t *out) {
+  ENTER(c);
+  if (n_fields < 0 || by < 0 || bx < 0 || (n_fields > 0 && by > 0 && bx > 0 && (!in || !out)))
+    return fail(QSVC_EINVAL, "bad arguments");
+  const size_t bytes = (size_t)n_fields * 4 * by * bx * sizeof(short);
+  if (!bytes) return QSVC_OK;
+  Scratch s(c);
+  short *d_in, *d_out;
+  TRY(s.get(bytes, (void **)&d_in));
+  TRY(s.get(bytes, (void **)&d_out));
+  CU(cudaMemcpyAsync(d_in, in, bytes, cudaMemcpyHostToDevice, c->stream));
+  launch_mv_bidirectional(c->L(), d_in, d_out, n_fields, by * bx, inverse);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QSVC_OK;
+}
+
+int qsvc_interlevel_motion_decorrelate(qsvc_ctx *c, int inverse, const int16_t *in, int n_fields,
+                                       const int16_t *reference, int n_reference, int by, int bx, int16_t *out) {
+  ENTER(c);
+  if (n_fields < 0 || n_reference < 0 || by < 0 || bx < 0 || (n_reference > 0 && !reference) ||
+      (n_fields > 0 && by > 0 && bx > 0 && (!in || !out)))
+    return fail(QSVC_EINVAL, "bad arguments");
+  const size_t fsz = (size_t)4 * by * bx * sizeof(short), bytes = fsz * n_fields;
+  if (!bytes) return QSVC_OK;
+  // only the reference fields the reader's loop would reach matter
+  const int n_ref = std::min(n_reference, (n_fields + 1) / 2);
+  Scratch s(c);
+  short *d_in, *d_out, *d_ref = nullptr;
+  TRY(s.get(bytes, (void **)&d_in));
+  TRY(s.get(bytes, (void **)&d_out));
+  if (n_ref > 0) {
+    TRY(s.get(fsz * n_ref, (void **)&d_ref));
+    CU(cudaMemcpyAsync(d_ref, reference, fsz * n_ref, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaMemcpyAsync(d_in, in, bytes, cudaMemcpyHostToDevice, c->stream));
+  launch_mv_interlevel(c->L(), d_in, d_ref, d_out, n_fields, n_ref, by * bx, inverse);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QSVC_OK;
+}
+
 // ------------------------------------------------------ resident sequence
 
 int qsvc_resident_load(qsvc_ctx *c, const uint8_t *low0, int n_frames, int X, int Y) {
@@ -1244,6 +1289,33 @@ int qsvc_resident_fetch(qsvc_ctx *c, int t, uint8_t *high, int16_t *motion, int1
   if (low) CU(cudaMemcpyAsync(low, lv.low, (size_t)fb * (lv.n_pairs + 1), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (types) memcpy(types, lv.types.data(), (size_t)lv.n_pairs);
+  return QSVC_OK;
+}
+
+int qsvc_resident_fetch_motion_residue(qsvc_ctx *c, int t, int16_t *residue) {
+  ENTER(c);
+  const int T = (int)c->levels.size();
+  if (t < 1 || t >= T || !residue) return fail(QSVC_EINVAL, "no such level %d", t);
+  LevelResult &lv = c->levels[t];
+  if (!lv.motion_filtered) return fail(QSVC_EINVAL, "level %d holds no motion_filtered fields", t);
+  const int by = c->Y / lv.block_size, bx = c->X / lv.block_size;
+  const size_t bytes = (size_t)lv.n_pairs * 4 * by * bx * sizeof(short);
+  if (!bytes) return QSVC_OK;
+  Scratch s(c);
+  short *d_out;
+  TRY(s.get(bytes, (void **)&d_out));
+  if (t == T - 1) {
+    launch_mv_bidirectional(c->L(), lv.motion_filtered, d_out, lv.n_pairs, by * bx, 0);
+  } else {
+    LevelResult &up = c->levels[t + 1];
+    if (up.block_size != lv.block_size)
+      return fail(QSVC_EINVAL, "levels %d and %d use different block sizes", t, t + 1);
+    launch_mv_interlevel(c->L(), lv.motion_filtered, up.motion_filtered, d_out, lv.n_pairs,
+                         up.motion_filtered ? up.n_pairs : 0, by * bx, 0);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(residue, d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return QSVC_OK;
 }
 

@@ -214,6 +214,57 @@ void launch_mv_hist(const Launch &L, const short *mv, int n, int *hist) {
   COUNT(L);
 }
 
+// Motion-field (de)correlation, the step after the analysis on the motion side.
+// bidirectional (bidirectional_motion_decorrelate.cpp:25-52): NEXT -= PREV (+= when inverse);
+// interlevel (interlevel_motion_decorrelate.cpp:32-69, 250-297): field k of level t is predicted
+// by half of field k/2 of level t+1 (C division: truncation towards zero); a reference file that
+// ends early leaves its last field in the reader's buffer, a missing one reads as zeros.
+// Fields are [PREV.X, PREV.Y, NEXT.X, NEXT.Y][by][bx] int16; results wrap like the reference's shorts.
+__global__ void k_mv_bidirectional(const short *__restrict__ in, short *__restrict__ out, int n_fields, int plane,
+                                   int inverse) {
+  const long long total = (long long)n_fields * 4 * plane;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % (4LL * plane));
+    int v = in[i];
+    if (e >= 2 * plane) v = inverse ? v + in[i - 2 * plane] : v - in[i - 2 * plane];
+    out[i] = (short)v;
+  }
+}
+
+__global__ void k_mv_interlevel(const short *__restrict__ in, const short *__restrict__ ref, short *__restrict__ out,
+                                int n_fields, int n_ref, int plane, int inverse) {
+  const long long fsz = 4LL * plane, total = (long long)n_fields * fsz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long f = i / fsz, e = i - f * fsz;
+    int r = 0;
+    if (n_ref > 0) r = tdiv2(ref[(f / 2 < n_ref ? f / 2 : n_ref - 1) * fsz + e]);
+    out[i] = (short)(inverse ? in[i] + r : in[i] - r);
+  }
+}
+
+void launch_mv_bidirectional(const Launch &L, const short *in, short *out, int n_fields, int plane, int inverse) {
+  const long long total = (long long)n_fields * 4 * plane;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  ProfScope ps_(L, KC_IMG);
+  k_mv_bidirectional<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, L.stream>>>(in, out, n_fields, plane,
+                                                                                        inverse);
+  COUNT(L);
+}
+
+void launch_mv_interlevel(const Launch &L, const short *in, const short *ref, short *out, int n_fields, int n_ref,
+                          int plane, int inverse) {
+  const long long total = (long long)n_fields * 4 * plane;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  ProfScope ps_(L, KC_IMG);
+  k_mv_interlevel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, L.stream>>>(in, ref, out, n_fields,
+                                                                                     n_ref, plane, inverse);
+  COUNT(L);
+}
+
 __global__ void k_copy_bytes(uint8_t *dst, const uint8_t *src, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -201,6 +201,41 @@ class Context:
                                      _u8(pred) if want_prediction else None))
         return odd, pred
 
+    def bidirectional_motion_decorrelate(self, fields, inverse=False):
+        """(n, 4, by, bx) int16 -> same shape: NEXT -= PREV (inverse: += ), the reference's
+        bidirectional_motion_decorrelate / _correlate (bidirectional_motion_decorrelate.cpp:25-52)."""
+        fields = np.ascontiguousarray(fields, np.int16)
+        n, four, by, bx = fields.shape
+        assert four == 4
+        out = np.zeros_like(fields)
+        check(self._L.qsvc_bidirectional_motion_decorrelate(self._h, 1 if inverse else 0, _i16(fields), n,
+                                                            by, bx, _i16(out)))
+        return out
+
+    def interlevel_motion_decorrelate(self, fields, reference=None, inverse=False):
+        """residue[k] = predicted[k] - reference[k // 2] / 2 (inverse: predicted = residue + ...),
+        the reference's interlevel_motion_decorrelate / _correlate
+        (interlevel_motion_decorrelate.cpp:32-69, 250-297); reference None = the tool's /dev/zero."""
+        fields = np.ascontiguousarray(fields, np.int16)
+        n, four, by, bx = fields.shape
+        assert four == 4
+        nref = 0
+        if reference is not None:
+            reference = np.ascontiguousarray(reference, np.int16)
+            nref = reference.shape[0]
+            assert reference.shape[1:] == fields.shape[1:]
+        out = np.zeros_like(fields)
+        check(self._L.qsvc_interlevel_motion_decorrelate(self._h, 1 if inverse else 0, _i16(fields), n,
+                                                         _i16(reference) if nref else None, nref, by, bx,
+                                                         _i16(out)))
+        return out
+
+    def resident_motion_residue(self, t, n_pairs, by, bx):
+        """motion_residue_t of the last resident analysis (motion_compress.py:141-182 on the device)."""
+        out = np.zeros((n_pairs, 4, by, bx), np.int16)
+        check(self._L.qsvc_resident_fetch_motion_residue(self._h, t, _i16(out)))
+        return out
+
     def update(self, frames_in, high, motion, frame_types, X, Y, block_size=16,
                update_factor=0.25, inverse=False):
         frames_in = np.ascontiguousarray(frames_in, np.uint8)

@@ -5,6 +5,8 @@
 
 Tools: split merge motion_estimate decorrelate correlate update un_update
        analyze_step analyze synthesize_step synthesize
+       bidirectional_motion_decorrelate bidirectional_motion_correlate
+       interlevel_motion_decorrelate interlevel_motion_correlate
 Flag names, short forms and defaults follow the reference's getopt_long tables
 (motion_estimate.cpp:500-530, decorrelate.cpp:209-251, update.cpp:170-205,
 split.cpp:50-71) and MCTF_parser.py; unambiguous prefixes are accepted like
@@ -340,7 +342,69 @@ def t_synthesize_step(argv):
     return 255 if rc else 0
 
 
+def _read_fields(tool, fn, by, bx):
+    """Every whole field of a motion file, (n, 4, by, bx) int16."""
+    if not os.path.exists(fn):
+        _abort(tool, f'unable to read "{fn}"')
+    data = np.fromfile(fn, dtype="<i2")
+    fsz = 4 * by * bx
+    n = data.size // fsz if fsz else 0
+    return data[: n * fsz].reshape(n, 4, by, bx)
+
+
+def t_bidirectional(argv, inverse=False):
+    """bidirectional_motion_decorrelate.cpp:64-215 (flags :82-91)."""
+    tool = "bidirectional_motion_correlate" if inverse else "bidirectional_motion_decorrelate"
+    p = _Parser(tool)
+    p.opt("blocks_in_x", "x", 11, int)
+    p.opt("blocks_in_y", "y", 9, int)
+    p.opt("fields", "f", 1, int)
+    p.opt("input_fn", "i", "/dev/zero")
+    p.opt("output_fn", "o", "/dev/zero")
+    a = p.parse(argv)
+    if a.input_fn == "/dev/zero":
+        fields = np.zeros((a.fields, 4, a.blocks_in_y, a.blocks_in_x), np.int16)
+    else:
+        fields = _read_fields(tool, a.input_fn, a.blocks_in_y, a.blocks_in_x)[: a.fields]
+    with _ctx() as c:
+        out = c.bidirectional_motion_decorrelate(fields, inverse=inverse)
+    if a.output_fn != "/dev/zero":
+        yuv.write_motion(a.output_fn, out)
+    return 0
+
+
+def t_interlevel(argv, inverse=False):
+    """interlevel_motion_decorrelate.cpp:77-297 (flags :143-152): the loop reads one reference
+    field per iteration and up to two predicted (or residue) fields with it."""
+    tool = "interlevel_motion_correlate" if inverse else "interlevel_motion_decorrelate"
+    p = _Parser(tool)
+    p.opt("blocks_in_x", "x", 11, int)
+    p.opt("blocks_in_y", "y", 9, int)
+    p.opt("fields_in_predicted", "f", 1, int)
+    p.opt("predicted_fn", "p", "/dev/zero")
+    p.opt("reference_fn", "r", "/dev/zero")
+    p.opt("residue_fn", "e", "/dev/zero")
+    a = p.parse(argv)
+    src_fn, dst_fn = (a.residue_fn, a.predicted_fn) if inverse else (a.predicted_fn, a.residue_fn)
+    if src_fn == "/dev/zero":
+        fields = np.zeros((2 * a.fields_in_predicted, 4, a.blocks_in_y, a.blocks_in_x), np.int16)
+    else:
+        fields = _read_fields(tool, src_fn, a.blocks_in_y, a.blocks_in_x)[: 2 * a.fields_in_predicted]
+    ref = None  # a missing reference file reads as zeros (:229-238)
+    if a.reference_fn != "/dev/zero" and os.path.exists(a.reference_fn):
+        ref = _read_fields(tool, a.reference_fn, a.blocks_in_y, a.blocks_in_x)[: a.fields_in_predicted]
+    with _ctx() as c:
+        out = c.interlevel_motion_decorrelate(fields, ref, inverse=inverse)
+    if dst_fn != "/dev/zero":
+        yuv.write_motion(dst_fn, out)
+    return 0
+
+
 TOOLS = {
+    "bidirectional_motion_decorrelate": t_bidirectional,
+    "bidirectional_motion_correlate": lambda argv: t_bidirectional(argv, inverse=True),
+    "interlevel_motion_decorrelate": t_interlevel,
+    "interlevel_motion_correlate": lambda argv: t_interlevel(argv, inverse=True),
     "split": t_split,
     "merge": lambda argv: t_split(argv, inverse=True),
     "motion_estimate": t_motion_estimate,
