@@ -393,9 +393,16 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       launch_plane_to_u8(Lh, img, 0, nslots, Y, X, v[0], (long long)vbytes[0], pitch[0], d_flags, tiles_x,
                          tiles_per_slot);
     }
-    for (int l = 1; l <= a; l++)
-      launch_upsample2x(Lh, v[l - 1], Y << (l - 1), X << (l - 1), pitch[l - 1], (long long)vbytes[l - 1],
-                        v[l], pitch[l], (long long)vbytes[l], nslots);
+    if (a == 2) {  // V_1 and V_2 from one read of V_0
+      uint8_t *const outs[3] = {v[1], v[2], nullptr};
+      const int ps[3] = {pitch[1], pitch[2], 0};
+      const long long st[3] = {(long long)vbytes[1], (long long)vbytes[2], 0};
+      launch_upsample_chain(Lh, v[0], Y, X, pitch[0], (long long)vbytes[0], 2, outs, ps, st, nslots);
+    } else {
+      for (int l = 1; l <= a; l++)
+        launch_upsample2x(Lh, v[l - 1], Y << (l - 1), X << (l - 1), pitch[l - 1], (long long)vbytes[l - 1],
+                          v[l], pitch[l], (long long)vbytes[l], nslots);
+    }
     for (int l = 1; l <= a; l++) {
       CU(cudaMemsetAsync(d_slow, 0, sizeof(int), c->stream));
       SubpelParams q;

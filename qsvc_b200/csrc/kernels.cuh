@@ -126,6 +126,11 @@ void launch_plane_to_u8(const Launch &L, Plane src, int slot0, int nslots, int Y
 void launch_upsample2x(const Launch &L, const uint8_t *in, int n, int m, int pitch_in,
                        long long in_slot_stride, uint8_t *out, int pitch_out,
                        long long out_slot_stride, int nslots);
+// nst (2 or 3) chained x2 up-samplings in one kernel; outs[k] (k < nst) = plane after k + 1 stages
+// or nullptr when nobody reads it (the last one is mandatory); (m << 1) % 8 == 0
+void launch_upsample_chain(const Launch &L, const uint8_t *in, int n, int m, int pitch_in, long long in_slot_stride,
+                           int nst, uint8_t *const outs[3], const int pitches[3], const long long strides[3],
+                           int nslots);
 int run_int_peak(cudaStream_t stream, unsigned *d_out, int blocks, int iters, bool packed);
 
 // ---- motion compensation (kernels_mc.cu) ----

@@ -150,6 +150,102 @@ void launch_upsample2x(const Launch &L, const uint8_t *in, int n, int m, int pit
   COUNT(L);
 }
 
+// NST consecutive x2 up-samplings in one pass over the input: the CTA stages a (TH+1) x (TW+1)
+// input tile (one halo sample to the right and below, clamped at the picture edge = the
+// "last odd sample = last sample" rule), runs every stage but the last into shared memory and
+// streams the last one to global memory; intermediate planes are written only where a consumer
+// exists (outs[k] != nullptr).  Same arithmetic as k_upsample2x per stage, so the results are
+// identical to chaining it; the traffic is one read of the input and one write per wanted plane.
+struct UpChainOut {
+  uint8_t *p[3];          // plane of stage k + 1 (k = 0 .. NST-1), nullptr: not materialised
+  int pitch[3];
+  long long slot_stride[3];
+};
+
+// eight samples (columns 8q .. 8q+7) of row y of the next stage from the stage buffer `src`
+__device__ __forceinline__ uint2 up_row8(const uint8_t *src, int sp, int y, int q) {
+  const uint8_t *r0 = src + (y >> 1) * sp + 4 * q;
+  unsigned a = *reinterpret_cast<const unsigned *>(r0), an = r0[4];
+  if (y & 1) {
+    const uint8_t *r1 = r0 + sp;
+    a = __vhaddu4(a, *reinterpret_cast<const unsigned *>(r1));
+    an = (an + r1[4]) >> 1;
+  }
+  const unsigned sft = __funnelshift_r(a, an, 8), h = __vhaddu4(a, sft);
+  return make_uint2(__byte_perm(a, h, 0x5140), __byte_perm(a, h, 0x7362));
+}
+
+template <int NST>
+__global__ void __launch_bounds__(256) k_upsample_chain(const uint8_t *__restrict__ in, int n, int m, int pitch_in,
+                                                        long long in_slot_stride, UpChainOut o) {
+  constexpr int TH = 64 >> NST, TW = 256 >> NST;  // input tile; the last stage emits 64 x 256
+  constexpr int P0 = TW + 16, P1 = 2 * TW + 16, P2 = 4 * TW + 16;  // stage buffer pitches (bytes, % 4 == 0)
+  __shared__ __align__(16) uint8_t s0[(TH + 1) * P0];
+  __shared__ __align__(16) uint8_t s1[(2 * TH + 1) * P1];
+  __shared__ __align__(16) uint8_t s2[NST == 3 ? (4 * TH + 1) * P2 : 16];
+  const int slot = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+  const uint8_t *src = in + (long long)slot * in_slot_stride;
+  for (int i = threadIdx.x; i < (TH + 1) * P0; i += 256) {
+    const int r = i / P0, c = i - r * P0;
+    const int y = min(y0 + r, n - 1), x = min(x0 + c, m - 1);
+    s0[i] = c <= TW ? src[(long long)y * pitch_in + x] : (uint8_t)0;
+  }
+  __syncthreads();
+  const uint8_t *cur = s0;
+  int cp = P0;
+#pragma unroll
+  for (int k = 0; k < NST; k++) {
+    const int rows = TH << (k + 1), cols = TW << (k + 1);  // this stage's tile (without halo)
+    const int gy0 = y0 << (k + 1), gx0 = x0 << (k + 1), gn = n << (k + 1), gm = m << (k + 1);
+    uint8_t *g = o.p[k] ? o.p[k] + (long long)slot * o.slot_stride[k] : nullptr;
+    if (k < NST - 1) {
+      uint8_t *nxt = k == 0 ? s1 : s2;
+      const int np = k == 0 ? P1 : P2;
+      const int qn = cols / 8 + 1;  // one more group: the halo column
+      for (int i = threadIdx.x; i < (rows + 1) * qn; i += 256) {
+        const int y = i / qn, q = i - y * qn;
+        const uint2 v = up_row8(cur, cp, y, q);
+        *reinterpret_cast<uint2 *>(nxt + y * np + 8 * q) = v;
+        if (g && y < rows && q < qn - 1 && gy0 + y < gn && gx0 + 8 * q < gm)
+          *reinterpret_cast<uint2 *>(g + (long long)(gy0 + y) * o.pitch[k] + gx0 + 8 * q) = v;
+      }
+      __syncthreads();
+      cur = nxt;
+      cp = np;
+    } else {
+      const int qn = cols / 8;
+      for (int i = threadIdx.x; i < rows * qn; i += 256) {
+        const int y = i / qn, q = i - y * qn;
+        if (gy0 + y < gn && gx0 + 8 * q < gm)
+          *reinterpret_cast<uint2 *>(g + (long long)(gy0 + y) * o.pitch[k] + gx0 + 8 * q) = up_row8(cur, cp, y, q);
+      }
+    }
+  }
+}
+
+// in (n x m) -> stage planes; outs[k] = plane of size (n << (k+1)) x (m << (k+1)) or nullptr
+// (the last one is mandatory).  m << 1 must be a multiple of 8.
+void launch_upsample_chain(const Launch &L, const uint8_t *in, int n, int m, int pitch_in, long long in_slot_stride,
+                           int nst, uint8_t *const outs[3], const int pitches[3], const long long strides[3],
+                           int nslots) {
+  if (nslots <= 0) return;
+  UpChainOut o;
+  for (int k = 0; k < 3; k++) {
+    o.p[k] = k < nst ? outs[k] : nullptr;
+    o.pitch[k] = k < nst ? pitches[k] : 0;
+    o.slot_stride[k] = k < nst ? strides[k] : 0;
+  }
+  ProfScope ps_(L, KC_IMG);
+  if (nst == 3) {
+    dim3 grid((m + 31) / 32, (n + 7) / 8, nslots);
+    k_upsample_chain<3><<<grid, 256, 0, L.stream>>>(in, n, m, pitch_in, in_slot_stride, o);
+  } else {
+    dim3 grid((m + 63) / 64, (n + 15) / 16, nslots);
+    k_upsample_chain<2><<<grid, 256, 0, L.stream>>>(in, n, m, pitch_in, in_slot_stride, o);
+  }
+  COUNT(L);
+}
+
 // ------------------------------------------------------------- fast path
 
 __device__ __forceinline__ void subpel_centre(const SubpelParams &q, int pair, int by, int bx,
