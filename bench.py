@@ -217,7 +217,7 @@ def main():
         if rank != 0:
             return 0
         procs = min(os.cpu_count() or 1, 32)
-        r = cpu_reference_sample(w, procs)
+        r = cpu_reference_sample(w, procs, pairs_per_proc=2)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
             return 0
@@ -355,33 +355,42 @@ def main():
     # the dominant kernel class of the step, against the bound that applies to it
     share = cls_ms[dominant] / max(1e-9, sum(cls_ms.values()))
     pairs_total = sum(p // 2 for p in _pictures_per_level(w))
-    Ya, Xa = w["Y"] << w["a"], w["X"] << w["a"]
     fbytes = w["X"] * w["Y"] * 3 // 2
-    # algorithmic bytes per pair of the byte-plane MC kernels
-    alg = {"residue": (3 * Ya * Xa + 2 * fbytes) * pairs_total,   # k_ll_residue: 3 P_a planes + odd in + high out
-           "predict": 9 * Ya * Xa * pairs_total,                  # k_predict_u8: 2 reads + 1 write of 3 planes
-           "image": None, "dwt_rows": None, "dwt_cols": None, "update": None}
-    # dram__bytes_read+write of one ncu --set full capture (profiles/r1_summary.md), scaled per pair
-    ncu_traffic_per_pair = {"residue": (6.583642e9 + 0.230740e9) / 64, "predict": (12.688434e9 + 6.315000e9) / 64}
+    field_bytes = 8 * (w["Y"] // w["bs"]) * (w["X"] // w["bs"])
+    # algorithmic bytes of decorrelate per pair = two reference frames and the odd
+    # frame read, the high frame written, one motion field read and written (12.4 MB at 1080p)
+    mc_pair_bytes = 4 * fbytes + 2 * field_bytes
+    kernel_of = {"residue": "k_mc_march", "image": "k_upsample_chain/k_upsample2x (+ plane loads, border fills)",
+                 "predict": "k_predict_u8/k_tail_state", "dwt_rows": "k_dwt_rows", "dwt_cols": "k_dwt_cols"}
+    # dram__bytes_read+write per step of the class's kernels, from the committed ncu capture
+    # (profiles/r1_ncu.json, written by profiles/summarize.py; cfg3 only)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu.json"))).get("dram_bytes_per_step", {})
+    except (OSError, ValueError):
+        pass
     if dominant in ("search", "search_exact"):
-        roof = {"bound": "int-sad", "kernel": dominant, "achieved": rooflines["me_search"]["achieved"],
-                "peak": u8_peak / 1e9, "unit": "G SAD-op/s", "frac": rooflines["me_search"]["frac"],
-                "traffic": None, "share_of_step": share}
+        roof = {"bound": "int-sad", "kernel": "k_subpel_tma/k_subpel_strip/k_subpel_exact/k_search16",
+                "achieved": rooflines["me_search"]["achieved"], "peak": u8_peak / 1e9, "unit": "G SAD-op/s",
+                "frac": rooflines["me_search"]["frac"], "traffic": None, "share_of_step": share}
     else:
-        a_bytes = alg.get(dominant) or mc_bytes_total(w)
+        a_bytes = mc_pair_bytes * pairs_total if dominant in ("residue", "predict") else mc_bytes_total(w)
         ach = a_bytes / (cls_ms[dominant] * 1e-3) / 1e9
-        kname = {"residue": "k_ll_residue", "predict": "k_predict_u8"}.get(dominant, dominant)
-        tr = ncu_traffic_per_pair.get(dominant)
-        roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": tr * pairs_total if (tr and wname == "cfg3") else None,
-                "algorithmic_bytes": a_bytes, "share_of_step": share, "peak_source": hbm_src,
-                "note": "bytes and time summed over the class's launches of one step; the kernel is "
-                        "integer-ALU bound (see profiles/r1_summary.md), the HBM fraction is reported as required"}
+        tr = traffic.get(dominant) if wname == "cfg3" else None
+        roof = {"bound": "hbm", "kernel": kernel_of.get(dominant, dominant), "achieved": ach, "peak": hbm_peak,
+                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": tr,
+                "algorithmic_bytes": a_bytes, "launches": cls_n[dominant], "ms": cls_ms[dominant],
+                "share_of_step": share, "peak_source": hbm_src,
+                "note": "achieved = SURVEY 8(d) algorithmic bytes of the class's launches of one step / their "
+                        "summed device time (CUDA events on the library's stream); traffic = ncu dram bytes "
+                        "of the same launches.  k_mc_march reads the up-sampled reference planes "
+                        "(16x the frame bytes) and is bound by instruction issue, not by HBM: see "
+                        "profiles/r1_summary.md"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            r = cpu_reference_sample(w, min(os.cpu_count() or 1, 32))
+            r = cpu_reference_sample(w, min(os.cpu_count() or 1, 32), pairs_per_proc=2)
             if r:
                 cpu = {"value": r["value"], "unit": "frames/s", "cores": r["procs"],
                        "kind": "reference", "sample": r["sample"]}

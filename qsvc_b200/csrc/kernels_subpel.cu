@@ -162,24 +162,28 @@ struct UpChainOut {
   long long slot_stride[3];
 };
 
-// eight samples (columns 8q .. 8q+7) of row y of the next stage from the stage buffer `src`
-__device__ __forceinline__ uint2 up_row8(const uint8_t *src, int sp, int y, int q) {
-  const uint8_t *r0 = src + (y >> 1) * sp + 4 * q;
-  unsigned a = *reinterpret_cast<const unsigned *>(r0), an = r0[4];
+// sixteen samples (columns 16g .. 16g+15) of row y of the next stage from the stage buffer `src`
+// (row pitch sp, a multiple of 8): source columns 8g .. 8g+8 of source row y/2 (and y/2 + 1)
+__device__ __forceinline__ uint4 up_row16(const uint8_t *src, int sp, int y, int g) {
+  const uint8_t *r0 = src + (y >> 1) * sp + 8 * g;
+  uint2 a = *reinterpret_cast<const uint2 *>(r0);
+  unsigned an = r0[8];
   if (y & 1) {
-    const uint8_t *r1 = r0 + sp;
-    a = __vhaddu4(a, *reinterpret_cast<const unsigned *>(r1));
-    an = (an + r1[4]) >> 1;
+    const uint2 b = *reinterpret_cast<const uint2 *>(r0 + sp);
+    a.x = __vhaddu4(a.x, b.x);
+    a.y = __vhaddu4(a.y, b.y);
+    an = (an + r0[sp + 8]) >> 1;
   }
-  const unsigned sft = __funnelshift_r(a, an, 8), h = __vhaddu4(a, sft);
-  return make_uint2(__byte_perm(a, h, 0x5140), __byte_perm(a, h, 0x7362));
+  const unsigned h0 = __vhaddu4(a.x, __funnelshift_r(a.x, a.y, 8)), h1 = __vhaddu4(a.y, __funnelshift_r(a.y, an, 8));
+  return make_uint4(__byte_perm(a.x, h0, 0x5140), __byte_perm(a.x, h0, 0x7362), __byte_perm(a.y, h1, 0x5140),
+                    __byte_perm(a.y, h1, 0x7362));
 }
 
 template <int NST>
 __global__ void __launch_bounds__(256) k_upsample_chain(const uint8_t *__restrict__ in, int n, int m, int pitch_in,
                                                         long long in_slot_stride, UpChainOut o) {
   constexpr int TH = 64 >> NST, TW = 256 >> NST;  // input tile; the last stage emits 64 x 256
-  constexpr int P0 = TW + 16, P1 = 2 * TW + 16, P2 = 4 * TW + 16;  // stage buffer pitches (bytes, % 4 == 0)
+  constexpr int P0 = TW + 16, P1 = 2 * TW + 16, P2 = 4 * TW + 16;  // stage buffer pitches (bytes, % 16 == 0)
   __shared__ __align__(16) uint8_t s0[(TH + 1) * P0];
   __shared__ __align__(16) uint8_t s1[(2 * TH + 1) * P1];
   __shared__ __align__(16) uint8_t s2[NST == 3 ? (4 * TH + 1) * P2 : 16];
@@ -195,29 +199,47 @@ __global__ void __launch_bounds__(256) k_upsample_chain(const uint8_t *__restric
   int cp = P0;
 #pragma unroll
   for (int k = 0; k < NST; k++) {
+    constexpr int dummy = 0;
+    (void)dummy;
     const int rows = TH << (k + 1), cols = TW << (k + 1);  // this stage's tile (without halo)
     const int gy0 = y0 << (k + 1), gx0 = x0 << (k + 1), gn = n << (k + 1), gm = m << (k + 1);
-    uint8_t *g = o.p[k] ? o.p[k] + (long long)slot * o.slot_stride[k] : nullptr;
+    uint8_t *g = o.p[k] ? o.p[k] + (long long)slot * o.slot_stride[k] + (long long)gy0 * o.pitch[k] + gx0 : nullptr;
+    const bool al16 = (o.pitch[k] & 15) == 0 && (gm & 15) == 0;
     if (k < NST - 1) {
       uint8_t *nxt = k == 0 ? s1 : s2;
       const int np = k == 0 ? P1 : P2;
-      const int qn = cols / 8 + 1;  // one more group: the halo column
-      for (int i = threadIdx.x; i < (rows + 1) * qn; i += 256) {
-        const int y = i / qn, q = i - y * qn;
-        const uint2 v = up_row8(cur, cp, y, q);
-        *reinterpret_cast<uint2 *>(nxt + y * np + 8 * q) = v;
-        if (g && y < rows && q < qn - 1 && gy0 + y < gn && gx0 + 8 * q < gm)
-          *reinterpret_cast<uint2 *>(g + (long long)(gy0 + y) * o.pitch[k] + gx0 + 8 * q) = v;
+      const int gr = cols / 16 + 1;  // one more group: the halo column
+      for (int i = threadIdx.x; i < (rows + 1) * gr; i += 256) {
+        const int y = i / gr, q = i - y * gr;
+        const uint4 v = up_row16(cur, cp, y, q);
+        *reinterpret_cast<uint4 *>(nxt + y * np + 16 * q) = v;
+        if (g && y < rows && q < gr - 1 && gy0 + y < gn && gx0 + 16 * q < gm) {
+          uint8_t *d = g + (long long)y * o.pitch[k] + 16 * q;
+          if (al16) {
+            *reinterpret_cast<uint4 *>(d) = v;
+          } else {  // picture width a multiple of 8 only
+            *reinterpret_cast<uint2 *>(d) = make_uint2(v.x, v.y);
+            if (gx0 + 16 * q + 8 < gm) *reinterpret_cast<uint2 *>(d + 8) = make_uint2(v.z, v.w);
+          }
+        }
       }
       __syncthreads();
       cur = nxt;
       cp = np;
     } else {
-      const int qn = cols / 8;
-      for (int i = threadIdx.x; i < rows * qn; i += 256) {
-        const int y = i / qn, q = i - y * qn;
-        if (gy0 + y < gn && gx0 + 8 * q < gm)
-          *reinterpret_cast<uint2 *>(g + (long long)(gy0 + y) * o.pitch[k] + gx0 + 8 * q) = up_row8(cur, cp, y, q);
+      // 256 threads = 16 rows x 16 column groups of 16 bytes; each thread walks down four rows
+      const int q = threadIdx.x & 15;
+      if (gx0 + 16 * q < gm) {
+        for (int y = threadIdx.x >> 4; y < rows && gy0 + y < gn; y += 16) {
+          const uint4 v = up_row16(cur, cp, y, q);
+          uint8_t *d = g + (long long)y * o.pitch[k] + 16 * q;
+          if (al16) {
+            *reinterpret_cast<uint4 *>(d) = v;
+          } else {
+            *reinterpret_cast<uint2 *>(d) = make_uint2(v.x, v.y);
+            if (gx0 + 16 * q + 8 < gm) *reinterpret_cast<uint2 *>(d + 8) = make_uint2(v.z, v.w);
+          }
+        }
       }
     }
   }
