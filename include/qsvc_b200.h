@@ -88,6 +88,24 @@ typedef int (*qsvc_tail_fn)(void *user, int level, int synthesis, int phase, uin
                             long long bytes);
 int qsvc_set_tail_exchange(qsvc_ctx *ctx, qsvc_tail_fn fn, void *user);
 
+/* GOP shards with update_factor != 0: the frame two neighbouring shards
+ * share receives the left shard's NEXT update first and the right shard's PREV update second
+ * (update.cpp:109-140 clamps and truncates every contribution, so the order matters), in
+ * update and in un_update.  When a callback is installed, every update / un_update level calls
+ * it on the calling thread (level / inverse as for the tail exchange):
+ *   phase 0 (right side, before its first frame is updated): `data` = 3 planes of
+ *            pixels_in_y x align8(pixels_in_x) int16 to be filled with what the left neighbour
+ *            passed in its phase 1; return 1 when filled, 0 for the first shard;
+ *   phase 1 (left side, after its last frame received the NEXT update): `data` holds those
+ *            planes, to be passed to the right; return 1 if a right neighbour exists, else 0;
+ *   phase 2 (right side): `data` = the finished shared frame (I420 u8), to be passed to the left;
+ *   phase 3 (left side, only after phase 1 returned 1): fill `data` with that frame, return 1.
+ * The last frame of a shard is processed first, so a chain of shards does not serialise.  The
+ * shards must run concurrently (one context each).  A negative return aborts the call. */
+typedef int (*qsvc_boundary_fn)(void *user, int level, int inverse, int phase, void *data,
+                                long long bytes);
+int qsvc_set_boundary_exchange(qsvc_ctx *ctx, qsvc_boundary_fn fn, void *user);
+
 /* Replaces `motion_estimate` main(), reference motion_estimate.cpp:490-912
  * (search: :70-184, pyramid driver: :260-413).
  * first_pair_is_global_first: 1 when even[0] is the first frame the reference

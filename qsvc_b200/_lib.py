@@ -43,6 +43,9 @@ _i = C.c_int
 # qsvc_tail_fn: (user, level, synthesis, phase, state, bytes) -> int
 TAIL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_longlong)
 
+# qsvc_boundary_fn: (user, level, inverse, phase, data, bytes) -> int
+BOUNDARY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_longlong)
+
 # name -> (restype, argtypes); every symbol include/qsvc_b200.h declares
 SIGNATURES = {
     "qsvc_version": (_i, []),
@@ -55,6 +58,7 @@ SIGNATURES = {
     "qsvc_timer_stop": (_i, [C.c_void_p, C.POINTER(C.c_float)]),
     "qsvc_synchronize": (_i, [C.c_void_p]),
     "qsvc_set_tail_exchange": (_i, [C.c_void_p, TAIL_FN, C.c_void_p]),
+    "qsvc_set_boundary_exchange": (_i, [C.c_void_p, BOUNDARY_FN, C.c_void_p]),
     "qsvc_set_me_mode": (_i, [C.c_void_p, _i]),
     "qsvc_set_mc_mode": (_i, [C.c_void_p, _i]),
     "qsvc_profile_enable": (_i, [C.c_void_p, _i]),

@@ -70,6 +70,8 @@ struct qsvc_ctx {
   std::vector<PoolBlock> pool;
   qsvc_tail_fn tail_fn = nullptr;  // GOP-shard exchange of the prediction tail state (A.2.6)
   void *tail_user = nullptr;
+  qsvc_boundary_fn boundary_fn = nullptr;  // GOP-shard exchange of the boundary frame (update_factor != 0)
+  void *boundary_user = nullptr;
   int cur_level = 0;  // temporal level of the running resident analysis / synthesis
   int tma_mode = 1;  // 0: plain loads in the sub-pixel fast path (env QSVC_TMA=0)
   int mc_mode = 0;  // same three values for the decorrelate / correlate path
@@ -778,14 +780,30 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
     CU(cudaGetLastError());
     return QSVC_OK;
   }
-  for (int k = 0; k <= n_pairs; k++) {
+  // GOP shards: the frame shared with a neighbour receives the left
+  // shard's NEXT update first and the right shard's PREV update second, and every contribution
+  // is clamped and truncated, so the int16 planes travel from left to right between the two
+  // passes and the finished frame travels back.  The last frame is processed first so that a
+  // chain of shards does not serialise on this hand-over.
+  std::vector<uint8_t> h_planes;
+  const bool xch = c->boundary_fn != nullptr && n_pairs > 0;
+  auto boundary = [&](int phase, void *data, long long bytes) -> int {
+    CU(cudaStreamSynchronize(c->stream));
+    const int r = c->boundary_fn(c->boundary_user, c->cur_level, inverse, phase, data, bytes);
+    if (r < 0) return fail(QSVC_EINVAL, "boundary exchange callback failed (phase %d)", phase);
+    return r;
+  };
+  bool last_from_right = false;
+  for (int kk = 0; kk <= n_pairs; kk++) {
+    const int k = xch ? (kk == 0 ? n_pairs : kk - 1) : kk;  // with an exchange: n, 0, 1, .., n-1
     const uint8_t *frame = in + (long long)k * in_stride;
     uint8_t *dst = out + (long long)k * out_stride;
     bool upd_next = k >= 1 && types[k - 1] == 'B';
     bool upd_prev = k < n_pairs && types[k] == 'B';
+    const bool first_xch = xch && k == 0, last_xch = xch && k == n_pairs;
     // update_factor == 0: every contribution is aux + (+-0) with aux already in
     // [0,255], so the scatter is the identity (analyze.py's default)
-    if (!(upd_next || upd_prev) || BY == 0 || BX == 0 || uf == 0.0f) {
+    if (!first_xch && !last_xch && !(upd_next || upd_prev)) {
       // chroma up (zero-high synthesis) and down (analysis) are exact inverses
       launch_copy_bytes(Lh, dst, frame, (size_t)fb);
       continue;
@@ -795,6 +813,16 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
     launch_load_u8(Lh, ref.p, 1, 1, frame, 0, comp_offset(X, Y, 1), 0, 0, Y / 2, X / 2);
     launch_load_u8(Lh, ref.p, 2, 1, frame, 0, comp_offset(X, Y, 2), 0, 0, Y / 2, X / 2);
     dwt_synthesize(Lh, ref.p, 1, 2, Y, X, 1);
+    if (first_xch) {
+      // phase 0: the planes as the left neighbour left them after its NEXT pass (1: filled in)
+      h_planes.resize(ref.bytes);
+      const int got = boundary(0, h_planes.data(), (long long)ref.bytes);
+      if (got < 0) return got;
+      if (got > 0) {
+        CU(cudaMemcpyAsync(ref.raw, h_planes.data(), ref.bytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+      }
+    }
     for (int pass = 0; pass < 2; pass++) {
       // frame k first receives pair k-1's NEXT update, then pair k's PREV update
       int pair = pass == 0 ? k - 1 : k;
@@ -819,10 +847,36 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
       q.inverse = inverse;
       launch_update(Lh, q);
     }
+    if (last_xch) {
+      // phase 1: the planes after this shard's NEXT pass, for the right neighbour (1: one exists
+      // and will send the finished frame back in phase 3)
+      h_planes.resize(ref.bytes);
+      CU(cudaMemcpyAsync(h_planes.data(), ref.raw, ref.bytes, cudaMemcpyDeviceToHost, c->stream));
+      const int has_right = boundary(1, h_planes.data(), (long long)ref.bytes);
+      if (has_right < 0) return has_right;
+      last_from_right = has_right > 0;
+    }
     dwt_analyze(Lh, ref.p, 1, 2, Y, X, 1);
     launch_store_u8(Lh, ref.p, 0, 1, dst, 0, 0, 0, 0, Y, X);
     launch_store_u8(Lh, ref.p, 1, 1, dst, 0, comp_offset(X, Y, 1), 0, 0, Y / 2, X / 2);
     launch_store_u8(Lh, ref.p, 2, 1, dst, 0, comp_offset(X, Y, 2), 0, 0, Y / 2, X / 2);
+    if (first_xch) {
+      // phase 2: this shard's finished first frame, for the left neighbour (ignored by the first shard)
+      std::vector<uint8_t> f((size_t)fb);
+      CU(cudaMemcpyAsync(f.data(), dst, (size_t)fb, cudaMemcpyDeviceToHost, c->stream));
+      const int r = boundary(2, f.data(), fb);
+      if (r < 0) return r;
+    }
+  }
+  if (last_from_right) {
+    // phase 3: the finished shared frame from the right neighbour replaces this shard's last frame
+    std::vector<uint8_t> f((size_t)fb);
+    const int got = boundary(3, f.data(), fb);
+    if (got < 0) return got;
+    if (got > 0) {
+      CU(cudaMemcpyAsync(out + (long long)n_pairs * out_stride, f.data(), (size_t)fb, cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
   }
   CU(cudaGetLastError());
   return QSVC_OK;
@@ -963,6 +1017,12 @@ int qsvc_set_tail_exchange(qsvc_ctx *c, qsvc_tail_fn fn, void *user) {
   if (!c) return fail(QSVC_EINVAL, "null context");
   c->tail_fn = fn;
   c->tail_user = user;
+  return QSVC_OK;
+}
+int qsvc_set_boundary_exchange(qsvc_ctx *c, qsvc_boundary_fn fn, void *user) {
+  if (!c) return fail(QSVC_EINVAL, "null context");
+  c->boundary_fn = fn;
+  c->boundary_user = user;
   return QSVC_OK;
 }
 int qsvc_set_me_mode(qsvc_ctx *c, int mode) {

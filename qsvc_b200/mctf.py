@@ -140,6 +140,28 @@ class Context:
         self._tail_cb = _lib.TAIL_FN(cb)  # keep the trampoline alive
         check(self._L.qsvc_set_tail_exchange(self._h, self._tail_cb, None))
 
+    def set_boundary_exchange(self, fn=None):
+        """Installs (or clears) the GOP-shard exchange of the shared boundary frame for
+        update_factor != 0 (include/qsvc_b200.h):
+        fn(level, inverse, phase, data) with `data` a writable uint8 view (int16 planes in
+        phases 0/1, an I420 frame in phases 2/3); returns True / False as documented there."""
+        if fn is None:
+            self._boundary_cb = None
+            check(self._L.qsvc_set_boundary_exchange(self._h, _lib.BOUNDARY_FN(), None))
+            return
+
+        def cb(_user, level, inverse, phase, data, nbytes):
+            try:
+                a = np.ctypeslib.as_array(data, shape=(int(nbytes),))
+                return 1 if fn(int(level), int(inverse), int(phase), a) else 0
+            except Exception:  # noqa: BLE001 -- must not propagate through the C frame
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        self._boundary_cb = _lib.BOUNDARY_FN(cb)  # keep the trampoline alive
+        check(self._L.qsvc_set_boundary_exchange(self._h, self._boundary_cb, None))
+
     def profile_enable(self, on=True):
         check(self._L.qsvc_profile_enable(self._h, 1 if on else 0))
 

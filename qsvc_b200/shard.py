@@ -12,8 +12,12 @@ What couples neighbouring shards, and how it is handled:
     neighbour and passes its own to the right, once per temporal level (a point-to-
     point message of 3 * rows * (X << a) bytes; `TailRelay` over torch.distributed,
     `LocalTailRelay` when the shards run one after the other on one GPU);
-  * update_factor != 0: the boundary frame receives updates from both sides in a
-    fixed order (SURVEY.md 8e item 1).  Not built: refused unless allow_inexact;
+  * update_factor != 0: the boundary frame receives the left shard's NEXT update and
+    then the right shard's PREV update.  The left shard passes the
+    int16 planes of that frame to the right between the two passes and gets the finished
+    frame back, once per temporal level (`BoundaryRelay` over torch.distributed,
+    `ThreadBoundaryRelay` for shards driven by threads of one process).  The shards must
+    run concurrently;
   * X % block_size != 0 with Y % block_size != 0: the byte-plane path does not apply
     and the literal path has no exchange hook: refused.
 """
@@ -22,6 +26,14 @@ from __future__ import annotations
 import numpy as np
 
 from .mctf import gop_size, level_schedule
+
+
+def _dist_ready():
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized()
+    except ImportError:
+        return False
 
 
 def partition(GOPs: int, world: int):
@@ -43,12 +55,17 @@ def needs_tail_exchange(Y, block_size, world):
     return world > 1 and Y % block_size != 0
 
 
-def check_exact(X, Y, block_size, update_factor, world, allow_inexact=False):
+def needs_boundary_exchange(update_factor, world):
+    return world > 1 and update_factor != 0
+
+
+def check_exact(X, Y, block_size, update_factor, world, allow_inexact=False, boundary_relay=None):
     if world <= 1 or allow_inexact:
         return
-    if update_factor != 0:
+    if update_factor != 0 and boundary_relay is None:
         raise ValueError("GOP sharding with update_factor != 0 needs the boundary-frame "
-                         "exchange of SURVEY.md 8e(1); run on one GPU or pass allow_inexact")
+                         "exchange of SURVEY.md 8e(1): pass a boundary relay (shards must run "
+                         "concurrently), run on one GPU, or pass allow_inexact")
     if Y % block_size and (X % block_size or X % 8):
         raise ValueError("GOP sharding with uncovered rows AND columns has no tail exchange "
                          "(literal decorrelate path); run on one GPU or pass allow_inexact")
@@ -104,14 +121,96 @@ class TailRelay:
         return False
 
 
+class BoundaryRelay:
+    """Boundary-frame hand-over (update_factor != 0) over torch.distributed point-to-point
+    messages between neighbouring ranks that have work."""
+
+    def __init__(self, rank, ranges):
+        import torch.distributed as dist
+        active = [r for r, (a, b) in enumerate(ranges) if b > a]
+        i = active.index(rank)
+        self.left = active[i - 1] if i > 0 else None
+        self.right = active[i + 1] if i + 1 < len(active) else None
+        self.cuda = dist.get_backend() == "nccl"
+
+    def _send(self, data, dst):
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(data.copy())
+        dist.send(t.cuda() if self.cuda else t, dst=dst)
+
+    def _recv(self, data, src):
+        import torch
+        import torch.distributed as dist
+        t = torch.empty(data.shape[0], dtype=torch.uint8, device="cuda" if self.cuda else "cpu")
+        dist.recv(t, src=src)
+        data[:] = t.cpu().numpy()
+
+    def __call__(self, level, inverse, phase, data):
+        if phase == 0:
+            if self.left is None:
+                return False
+            self._recv(data, self.left)
+            return True
+        if phase == 1:
+            if self.right is None:
+                return False
+            self._send(data, self.right)
+            return True
+        if phase == 2:
+            if self.left is not None:
+                self._send(data, self.left)
+            return False
+        self._recv(data, self.right)
+        return True
+
+
+class ThreadBoundaryRelay:
+    """The same hand-over between shards driven by threads of one process (one context per
+    thread, any number of GPUs): `ThreadBoundaryRelay.make(n)` returns one relay per shard."""
+
+    def __init__(self, to_left, from_left, to_right, from_right):
+        self.to_left, self.from_left, self.to_right, self.from_right = to_left, from_left, to_right, from_right
+
+    @staticmethod
+    def make(n):
+        import queue
+        right = [queue.Queue() for _ in range(n - 1)]  # right[i]: shard i -> shard i + 1
+        left = [queue.Queue() for _ in range(n - 1)]   # left[i]:  shard i + 1 -> shard i
+        return [ThreadBoundaryRelay(left[i - 1] if i > 0 else None, right[i - 1] if i > 0 else None,
+                                    right[i] if i < n - 1 else None, left[i] if i < n - 1 else None)
+                for i in range(n)]
+
+    def __call__(self, level, inverse, phase, data):
+        if phase == 0:
+            if self.from_left is None:
+                return False
+            data[:] = self.from_left.get(timeout=600)
+            return True
+        if phase == 1:
+            if self.to_right is None:
+                return False
+            self.to_right.put(data.copy())
+            return True
+        if phase == 2:
+            if self.to_left is not None:
+                self.to_left.put(data.copy())
+            return False
+        data[:] = self.from_right.get(timeout=600)
+        return True
+
+
 def analyze_shard(ctx, low0, X, Y, GOPs, TRLs, rank, world, block_size=32, search_range=4,
                   subpixel_accuracy=0, update_factor=0.0, always_B=0, block_size_min=32,
-                  allow_inexact=False, analyze_fn=None, relay=None):
+                  allow_inexact=False, analyze_fn=None, relay=None, boundary_relay=None):
     """Runs this rank's GOP range.  `analyze_fn(frames, n_gops, first_global)` defaults
     to ctx.analyze (the CUDA path); tests may inject another callable.  `relay` is the
     tail-state hand-over (default: TailRelay when the geometry needs one)."""
-    check_exact(X, Y, block_size, update_factor, world, allow_inexact)
     ranges = partition(GOPs, world)
+    if (boundary_relay is None and needs_boundary_exchange(update_factor, world) and ctx is not None
+            and analyze_fn is None and _dist_ready()):
+        boundary_relay = BoundaryRelay(rank, ranges)
+    check_exact(X, Y, block_size, update_factor, world, allow_inexact, boundary_relay)
     g0, g1 = ranges[rank]
     if g1 == g0:
         return None
@@ -125,11 +224,15 @@ def analyze_shard(ctx, low0, X, Y, GOPs, TRLs, rank, world, block_size=32, searc
         relay = TailRelay(rank, ranges)
     if relay is not None and ctx is not None:
         ctx.set_tail_exchange(relay)
+    if boundary_relay is not None and ctx is not None:
+        ctx.set_boundary_exchange(boundary_relay)
     try:
         return analyze_fn(frames, g1 - g0, g0 == 0)
     finally:
         if relay is not None and ctx is not None:
             ctx.set_tail_exchange(None)
+        if boundary_relay is not None and ctx is not None:
+            ctx.set_boundary_exchange(None)
 
 
 def gather(parts, TRLs: int):
@@ -173,10 +276,13 @@ def shard_subbands(subbands, TRLs: int, g0: int, g1: int):
 
 def synthesize_shard(ctx, subbands, X, Y, GOPs, TRLs, rank, world, block_size=16, search_range=4,
                      subpixel_accuracy=0, update_factor=0.0, allow_inexact=False,
-                     synthesize_fn=None, relay=None):
+                     synthesize_fn=None, relay=None, boundary_relay=None):
     """Reconstructs this rank's GOP range: low_0 frames [g0*G, g1*G] inclusive."""
-    check_exact(X, Y, block_size, update_factor, world, allow_inexact)
     ranges = partition(GOPs, world)
+    if (boundary_relay is None and needs_boundary_exchange(update_factor, world) and ctx is not None
+            and synthesize_fn is None and _dist_ready()):
+        boundary_relay = BoundaryRelay(rank, ranges)
+    check_exact(X, Y, block_size, update_factor, world, allow_inexact, boundary_relay)
     g0, g1 = ranges[rank]
     if g1 == g0:
         return None
@@ -189,11 +295,15 @@ def synthesize_shard(ctx, subbands, X, Y, GOPs, TRLs, rank, world, block_size=16
         relay = TailRelay(rank, ranges)
     if relay is not None and ctx is not None:
         ctx.set_tail_exchange(relay)
+    if boundary_relay is not None and ctx is not None:
+        ctx.set_boundary_exchange(boundary_relay)
     try:
         return synthesize_fn(sub, g1 - g0)
     finally:
         if relay is not None and ctx is not None:
             ctx.set_tail_exchange(None)
+        if boundary_relay is not None and ctx is not None:
+            ctx.set_boundary_exchange(None)
 
 
 def gather_frames(parts):

@@ -290,8 +290,9 @@ def _per_level(value: str, index: int, typ=int):
 def t_synthesize(argv):
     """synthesize.py:95-153.  block_size / pixels_in_x / pixels_in_y /
     subpixel_accuracy are comma lists indexed per temporal level
-    (:127-133); this build requires them to be constant over the levels
-    (spatially scalable synthesis is SURVEY 8f)."""
+    (:127-133).  Constant lists run fused with the frames resident in HBM;
+    lists that vary per level run step by step through
+    files like the reference."""
     a = _driver_parser("synthesize", lists=True).parse(argv)
     T = a.TRLs
     bs_list = a.block_size if a.block_size is not None else "16,16,16,16"
@@ -301,8 +302,25 @@ def t_synthesize(argv):
         geo.add((_per_level(bs_list, (T - 1) - t), _per_level(a.pixels_in_x, T - t),
                  _per_level(a.pixels_in_y, T - t), _per_level(a.subpixel_accuracy, T - t)))
     if len(geo) != 1:
-        _error("synthesize: per-level geometry lists must be constant in this build\n")
-        return 255
+        # per-level geometry (spatially scalable decoding, expand.py:150-209): chain the steps with
+        # each level's own values exactly like synthesize.py:108-153 does (files in CWD)
+        pictures_all = a.GOPs * gop_size(T) + 1
+        for t in range(T - 1, 0, -1):
+            pictures, sr = pictures_all, a.search_range
+            for _ in range(1, t):
+                sr = min(sr * 2, SEARCH_RANGE_MAX)
+                pictures = (pictures + 1) // 2
+            rc = t_synthesize_step([f"--block_overlaping={a.block_overlaping}",
+                                    f"--block_size={_per_level(bs_list, (T - 1) - t)}",
+                                    f"--pictures={pictures}",
+                                    f"--pixels_in_x={_per_level(a.pixels_in_x, T - t)}",
+                                    f"--pixels_in_y={_per_level(a.pixels_in_y, T - t)}",
+                                    f"--search_range={sr}",
+                                    f"--subpixel_accuracy={_per_level(a.subpixel_accuracy, T - t)}",
+                                    f"--temporal_subband={t}", f"--update_factor={uf}"])
+            if rc:
+                return 255
+        return 0
     bs, X, Y, acc = geo.pop()
     sub = {}
     for s in level_schedule(a.GOPs, T, bs, a.search_range, bs):

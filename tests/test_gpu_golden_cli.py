@@ -118,3 +118,34 @@ def test_properties_at_1080p(ctx):
     unclamped = (h > 0) & (h < 255)
     assert unclamped.mean() > 0.9
     assert np.array_equal(rec[4][unclamped], clip[4][unclamped])
+
+
+def test_cli_synthesize_with_per_level_lists(tmp_path):
+    """synthesize.py:127-133 indexes block_size / pixels / subpixel_accuracy per temporal level
+    (spatially scalable decoding): lists that vary run level by level with
+    each level's own values, like the reference's chain of synthesize_step calls."""
+    from oracle import oracle as orc
+    g = load("quarter_pel")
+    X, Y, bs, T, GOPs, uf = g["X"], g["Y"], g["bs"], g["TRLs"], g["GOPs"], g["uf"]
+    acc = {3: 2, 2: 1, 1: 2}  # per temporal level; the list is indexed [TRLs - t]
+    d = tmp_path
+    for t in range(1, T):
+        yuv.write_frames(str(d / f"high_{t}"), g[f"high_{t}"])
+        yuv.write_motion(str(d / f"motion_{t}"), g[f"motion_filtered_{t}"])
+        (d / f"frame_types_{t}").write_bytes(bytes(g[f"frame_types_{t}"]))
+    yuv.write_frames(str(d / f"low_{T-1}"), g[f"low_{T-1}"])
+    acc_list = ["0"] * (T + 1)
+    for t, v in acc.items():
+        acc_list[T - t] = str(v)
+    _mctf(["synthesize", f"--GOPs={GOPs}", f"--TRLs={T}", f"--search_range={g['sr']}",
+           f"--block_size={','.join([str(bs)] * T)}", f"--pixels_in_x={','.join([str(X)] * (T + 1))}",
+           f"--pixels_in_y={','.join([str(Y)] * (T + 1))}", f"--subpixel_accuracy={','.join(acc_list)}",
+           f"--update_factor={uf}"], str(d))
+    low = g[f"low_{T-1}"]
+    for t, sr in reversed(schedule(g)):
+        types, mv = bytes(g[f"frame_types_{t}"]), g[f"motion_filtered_{t}"]
+        even = orc.update(low, g[f"high_{t}"], mv, types, X, Y, bs, uf, inverse=True)
+        odd, _ = orc.correlate(even, g[f"high_{t}"], mv, types, X, Y, bs, sr, acc[t])
+        low = np.empty((2 * odd.shape[0] + 1, even.shape[1]), np.uint8)
+        low[0::2], low[1::2] = even, odd
+    assert np.array_equal(yuv.read_frames(str(d / "low_0"), X, Y), low)

@@ -258,3 +258,58 @@ def test_domain_error_on_large_vectors(ctx):
     high, types, mvo, _ = ctx.decorrelate(clip[0::2], clip[1::2], mv, X, Y, bs, 64, 0, always_B=1)
     ref = orc.decorrelate(clip[0::2], clip[1::2], mv, X, Y, bs, 64, 0, always_B=1)
     assert np.array_equal(high, ref[0]) and types == ref[1] == b"B"
+
+
+@pytest.mark.parametrize("GOPs,shards", [(2, 2), (3, 3)])
+def test_gop_shards_with_boundary_exchange_match_the_whole_sequence(GOPs, shards):
+    """update_factor != 0: the frame two shards share takes the left
+    shard's NEXT update, then the right shard's PREV update.  Shards run concurrently (one
+    context per thread on this GPU) and hand the int16 planes right / the finished frame left."""
+    import threading
+    from qsvc_b200 import shard
+    from qsvc_b200.mctf import Context
+    X, Y, TRLs, bs, sr, a, uf = 128, 96, 4, 16, 4, 1, 0.25
+    clip = yuv.synthetic_clip(X, Y, GOPs * 2 ** (TRLs - 1) + 1, 37, max_shift=12)
+    ref = orc.analyze(clip, X, Y, TRLs, bs, sr, a, uf, block_size_min=bs)
+    assert any(b"B" in ref[f"frame_types_{t}"] for t in range(1, TRLs))
+    kw = dict(block_size=bs, search_range=sr, subpixel_accuracy=a, update_factor=uf)
+
+    def run_threads(fn):
+        out, err = [None] * shards, []
+
+        def work(r):
+            try:
+                with Context(0) as c:
+                    out[r] = fn(c, r)
+            except Exception as e:  # noqa: BLE001
+                err.append(e)
+
+        th = [threading.Thread(target=work, args=(r,)) for r in range(shards)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=300)
+        assert not err, err
+        return out
+
+    relays = shard.ThreadBoundaryRelay.make(shards)
+    parts = run_threads(lambda c, r: shard.analyze_shard(c, clip, X, Y, GOPs, TRLs, r, shards, block_size_min=bs,
+                                                         boundary_relay=relays[r], **kw))
+    got = shard.gather(parts, TRLs)
+    for k, v in got.items():
+        assert (np.array_equal(ref[k], v) if not isinstance(v, bytes) else ref[k] == v), k
+    naive = run_threads(lambda c, r: shard.analyze_shard(c, clip, X, Y, GOPs, TRLs, r, shards, block_size_min=bs,
+                                                         allow_inexact=True, **kw))
+    naive = shard.gather(naive, TRLs)
+    assert any(not np.array_equal(naive[f"low_{t}"], ref[f"low_{t}"]) for t in range(1, TRLs))
+
+    sub = {f"low_{TRLs-1}": ref[f"low_{TRLs-1}"]}
+    for t in range(1, TRLs):
+        sub[f"high_{t}"], sub[f"motion_{t}"] = ref[f"high_{t}"], ref[f"motion_filtered_{t}"]
+        sub[f"frame_types_{t}"] = ref[f"frame_types_{t}"]
+    with Context(0) as c:
+        whole = c.synthesize(sub, X, Y, GOPs, TRLs, bs, sr, a, uf)
+    relays = shard.ThreadBoundaryRelay.make(shards)
+    parts = run_threads(lambda c, r: shard.synthesize_shard(c, sub, X, Y, GOPs, TRLs, r, shards,
+                                                            boundary_relay=relays[r], **kw))
+    assert np.array_equal(shard.gather_frames(parts), whole)

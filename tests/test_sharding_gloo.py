@@ -134,3 +134,68 @@ def test_tail_relay_passes_state_left_to_right():
         assert got and (st == 10 * syn + t).all()
     assert res[0][1]["first"] and not res[1][1]["first"]
     assert res[0][3] == list(range(GOPs * 2 ** (TRLs - 1) + 1))  # gathered frames, no duplicates
+
+
+class _FakeUpdateCtx:
+    """Drives the boundary-frame callback the way update_level does: the shard's last frame
+    first (phase 1), then its first frame (phases 0 and 2), then the frame coming back (phase 3)."""
+
+    def __init__(self, rank):
+        self.rank, self.fn, self.log = rank, None, []
+
+    def set_tail_exchange(self, fn):
+        pass
+
+    def set_boundary_exchange(self, fn):
+        self.fn = fn
+
+    def run_levels(self):
+        for t in range(1, TRLs):
+            planes = np.full(32, 10 * self.rank + t, np.uint8)
+            has_right = self.fn(t, 0, 1, planes)
+            first = np.zeros(32, np.uint8)
+            got = self.fn(t, 0, 0, first)
+            frame = np.full(16, 100 + 10 * self.rank + t, np.uint8)
+            self.fn(t, 0, 2, frame)
+            back = np.zeros(16, np.uint8)
+            if has_right:
+                assert self.fn(t, 0, 3, back)
+            self.log.append((t, bool(has_right), bool(got), int(first[0]), int(back[0])))
+
+
+def _boundary_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = _FakeUpdateCtx(rank)
+    clip = np.zeros((GOPs * 2 ** (TRLs - 1) + 1, 8), np.uint8)
+
+    def fn(frames, n_gops, first_global):
+        ctx.run_levels()
+        return {"rank": rank}
+
+    ranges = shard.partition(GOPs, world)
+    shard.analyze_shard(ctx, clip, 64, 48, GOPs, TRLs, rank, world, block_size=16, update_factor=0.25,
+                        analyze_fn=fn, boundary_relay=shard.BoundaryRelay(rank, ranges))
+    assert ctx.fn is None
+    q.put((rank, ctx.log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_boundary_relay_passes_planes_right_and_the_frame_back():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_boundary_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for t, has_right, got, first, back in res[0]:
+        assert has_right and not got and first == 0 and back == 110 + t  # rank 1's finished frame came back
+    for t, has_right, got, first, back in res[1]:
+        assert not has_right and got and first == t and back == 0        # rank 0's planes arrived
