@@ -64,6 +64,8 @@ struct qsvc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   std::vector<cudaEvent_t> level_events;
+  std::vector<cudaEvent_t> upload_events;  // qsvc_analyze: one per GOP of the clip being uploaded
+  int upload_gops = 0, upload_gop_frames = 0;  // > 0: level 1 may start GOP by GOP behind the upload
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   long long launches = 0;
   Profiler prof;
@@ -960,6 +962,7 @@ void qsvc_destroy(qsvc_ctx *c) {
   cudaEventDestroy(c->ev2);
   cudaEventDestroy(c->ev3);
   for (auto e : c->level_events) cudaEventDestroy(e);
+  for (auto e : c->upload_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -1265,8 +1268,45 @@ int qsvc_analyze(qsvc_ctx *c, const qsvc_analyze_params *p, const uint8_t *low0,
                  const qsvc_level_out *outs) {
   ENTER(c);
   if (!p || !low0 || !outs) return fail(QSVC_EINVAL, "bad arguments");
-  TRY(qsvc_resident_load(c, low0, n_frames, p->pixels_in_x, p->pixels_in_y));
-  TRY(analyze_levels(c, p, outs));
+  const int G = p->TRLs >= 2 && p->TRLs < 31 ? 1 << (p->TRLs - 1) : 0;
+  if (G > 0 && n_frames > G + 1 && (n_frames - 1) % G == 0) {
+    // upload GOP by GOP on the copy stream; level 1's motion estimation of GOP g starts as soon
+    // as its frames (up to the boundary frame (g+1)*G) have arrived
+    TRY(check_geometry(p->pixels_in_x, p->pixels_in_y, 1, 0));
+    free_levels(c);
+    pool_free(c, c->low0);
+    c->low0 = nullptr;
+    const long long fb = frame_bytes(p->pixels_in_x, p->pixels_in_y);
+    TRY(pool_alloc(c, (size_t)fb * n_frames, (void **)&c->low0));
+    c->n_frames = n_frames;
+    c->X = p->pixels_in_x;
+    c->Y = p->pixels_in_y;
+    const int gops = (n_frames - 1) / G;
+    while ((int)c->upload_events.size() < gops) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->upload_events.push_back(e);
+    }
+    // the pool hands out memory that earlier work on the compute stream may still be using
+    CU(cudaEventRecord(c->ev3, c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev3, 0));
+    for (int g = 0; g < gops; g++) {
+      const long long f0 = g == 0 ? 0 : (long long)g * G + 1, f1 = (long long)(g + 1) * G;  // inclusive
+      CU(cudaMemcpyAsync(c->low0 + f0 * fb, low0 + f0 * fb, (size_t)((f1 - f0 + 1) * fb), cudaMemcpyHostToDevice,
+                         c->copy_stream));
+      CU(cudaEventRecord(c->upload_events[g], c->copy_stream));
+    }
+    c->upload_gops = gops;
+    c->upload_gop_frames = G;
+  } else {
+    TRY(qsvc_resident_load(c, low0, n_frames, p->pixels_in_x, p->pixels_in_y));
+  }
+  const int rc = analyze_levels(c, p, outs);
+  c->upload_gops = 0;
+  if (rc != QSVC_OK) {
+    cudaStreamSynchronize(c->copy_stream);
+    return rc;
+  }
   CU(cudaStreamSynchronize(c->copy_stream));
   for (int t = 1; t < p->TRLs; t++)
     if (outs[t].frame_types) memcpy(outs[t].frame_types, c->levels[t].types.data(), (size_t)c->levels[t].n_pairs);
@@ -1303,8 +1343,18 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
     // split (split.cpp:229-341) is index arithmetic: even k = frame 2k, odd i = frame 2i+1
     const uint8_t *even = low, *odd = low + fb;
     c->cur_level = t;
-    TRY(me_level(c, even, 2 * fb, odd, 2 * fb, n, X, Y, bs, p->border_size, sr, p->subpixel_accuracy,
-                 p->first_gop_is_global_first, lv.motion));
+    if (t == 1 && c->upload_gops > 0) {
+      const int per_gop = c->upload_gop_frames / 2;  // pairs of a GOP at level 1
+      for (int g = 0; g < c->upload_gops; g++) {
+        CU(cudaStreamWaitEvent(c->stream, c->upload_events[g], 0));
+        const long long f0 = (long long)g * per_gop;
+        TRY(me_level(c, even + f0 * 2 * fb, 2 * fb, odd + f0 * 2 * fb, 2 * fb, per_gop, X, Y, bs, p->border_size, sr,
+                     p->subpixel_accuracy, g == 0 ? p->first_gop_is_global_first : 0, lv.motion + f0 * field));
+      }
+    } else {
+      TRY(me_level(c, even, 2 * fb, odd, 2 * fb, n, X, Y, bs, p->border_size, sr, p->subpixel_accuracy,
+                   p->first_gop_is_global_first, lv.motion));
+    }
     TRY(mc_level(c, 1, even, 2 * fb, odd, 2 * fb, lv.motion, n, X, Y, bs, p->block_overlaping, sr,
                  p->subpixel_accuracy, p->always_B, nullptr, lv.high, fb, &lv.types,
                  lv.motion_filtered, nullptr));
