@@ -1055,11 +1055,24 @@ __global__ void __launch_bounds__(2 * W) k_subpel_strip(SubpelParams q, B0View v
         cw = sa ? __funnelshift_r(lo, __ldg(a4 + 1), sa) : lo;
       } else {
         int s4[4];
+        // words outside the level-l image read the reference's level-0 buffer at the same
+        // coordinates (b0_cell): the compact plane where it is materialised, zeros elsewhere,
+        // the malloc size field at x in [-4, 0) of the un-shifted rows
+        const bool outside = !row_in || x + 3 < 0 || x >= Xl;
+        const bool size_rows = y >= v.Ya - v.Ba && y < v.Ya + v.Ba;
         if (row_in && cols_in && (y < q.clean || x + 3 < q.clean)) {
           const short *src = y < q.clean
                                  ? q.strip_top + (long long)slot * q.strip_top_stride + (long long)y * Xl + x
                                  : q.strip_left + (long long)slot * q.strip_left_stride +
                                        (long long)(y - q.clean) * q.clean + x;
+#pragma unroll
+          for (int k = 0; k < 4; k++) s4[k] = src[k];
+        } else if (outside && !(size_rows && x < 0 && x + 3 >= -4) &&
+                   (y < -v.Bc || y >= v.Y + v.Bc || x + 3 < -v.Bc || x >= v.X + v.Bc)) {
+          s4[0] = s4[1] = s4[2] = s4[3] = 0;  // never-written heap
+        } else if (outside && !(size_rows && x < 0 && x + 3 >= -4) && y >= -v.Bc && y < v.Y + v.Bc &&
+                   x >= -v.Bc && x + 3 < v.X + v.Bc) {
+          const short *src = v.p.row(slot, y) + x;  // inside the compact plane
 #pragma unroll
           for (int k = 0; k < 4; k++) s4[k] = src[k];
         } else {
@@ -1170,33 +1183,38 @@ __global__ void __launch_bounds__(256) k_level1_tile(B0View v, int slot0, int Y0
 }
 
 // Level-2 strips from the level-1 image (level-1 strips where polluted, V_1 bytes elsewhere):
-// zero-high-band synthesis, columns first, then rows.  Flattened over the cells of the region
-// rows [Y0, Y1) x columns [0, W) of the level-2 image.
+// zero-high-band synthesis, columns first, then rows.  One CTA row per output row of the region
+// rows [Y0, Y1) x columns [0, W) of the level-2 image: the row's two source rows and the kind of
+// storage they live in are resolved once per CTA, a thread produces one sample.
+static constexpr int STRIP2_ROWS = 16;
 __global__ void __launch_bounds__(256) k_strip2(int Y, int X, const short *top1, long long top1_stride,
                                                 const short *left1, long long left1_stride, int clean1,
                                                 const uint8_t *v1, long long v1_slot_stride, int v1_pitch,
                                                 short *dst, long long dst_stride, int slot0, int Y0, int Y1, int W) {
-  const int slot = slot0 + blockIdx.y;
+  const int slot = slot0 + blockIdx.z;
   const int X1 = 2 * X, Y2 = 4 * Y, X2 = 4 * X;
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  if (x >= W) return;
+  // STRIP2_ROWS rows per CTA: narrow regions would otherwise be bound by the CTA launch rate
+  for (int y = Y0 + blockIdx.y * STRIP2_ROWS; y < min(Y0 + (blockIdx.y + 1) * STRIP2_ROWS, Y1); y++) {
+  const int ya = y >> 1;
+  const bool vavg = (y & 1) && y != Y2 - 1;
+  // source row yy of the level-1 image: int16 top strip, or int16 left strip + bytes
   const short *t1 = top1 + slot * top1_stride, *l1 = left1 + slot * left1_stride;
   const uint8_t *b1 = v1 + slot * v1_slot_stride;
-  auto B1 = [&](int yy, int xx) -> int {
-    if (yy < clean1) return t1[yy * X1 + xx];
-    if (xx < clean1) return l1[(yy - clean1) * clean1 + xx];
-    return b1[(long long)yy * v1_pitch + xx];
+  const bool topA = ya < clean1, topB = ya + 1 < clean1;
+  const short *sA = topA ? t1 + (long long)ya * X1 : l1 + (long long)(ya - clean1) * clean1;
+  const short *sB = topB ? t1 + (long long)(ya + 1) * X1 : l1 + (long long)(ya + 1 - clean1) * clean1;
+  const uint8_t *bA = b1 + (long long)ya * v1_pitch, *bB = bA + v1_pitch;
+  auto T2 = [&](int xp) -> int {
+    const int a0 = (topA || xp < clean1) ? (int)sA[xp] : (int)bA[xp];
+    if (!vavg) return a0;
+    const int a1 = (topB || xp < clean1) ? (int)sB[xp] : (int)bB[xp];
+    return (short)tdiv2(a0 + a1);
   };
-  const long long cells = (long long)(Y1 - Y0) * W;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < cells;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int y = Y0 + (int)(idx / W), x = (int)(idx % W);
-    const int ya = y >> 1;
-    const bool vavg = (y & 1) && y != Y2 - 1;
-    auto T2 = [&](int xp) -> int {
-      const int a0 = B1(ya, xp);
-      return vavg ? (int)(short)tdiv2(a0 + B1(ya + 1, xp)) : a0;
-    };
-    const int a0 = T2(x >> 1);
-    dst[slot * dst_stride + idx] = (!(x & 1) || x == X2 - 1) ? (short)a0 : (short)tdiv2(a0 + T2((x >> 1) + 1));
+  const int a0 = T2(x >> 1);
+  dst[slot * dst_stride + (long long)(y - Y0) * W + x] =
+      (!(x & 1) || x == X2 - 1) ? (short)a0 : (short)tdiv2(a0 + T2((x >> 1) + 1));
   }
 }
 
@@ -1235,14 +1253,11 @@ void launch_strips(const Launch &L, const SubpelParams &q, int level, int slot0,
     return;
   }
   auto run = [&](short *dst, long long dst_stride, int Y0, int Y1, int W) {
-    const long long cells = (long long)(Y1 - Y0) * W;
-    if (cells <= 0) return;
-    long long blocks = (cells + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (Y1 <= Y0 || W <= 0) return;
     ProfScope ps_(L, KC_SEARCH_EXACT);
-    k_strip2<<<dim3((unsigned)blocks, nslots), 256, 0, L.stream>>>(q.Y, q.X, top1, top1_stride, left1, left1_stride,
-                                                                  clean1, v1, v1_slot_stride, v1_pitch, dst,
-                                                                  dst_stride, slot0, Y0, Y1, W);
+    k_strip2<<<dim3((W + 255) / 256, (Y1 - Y0 + STRIP2_ROWS - 1) / STRIP2_ROWS, nslots), 256, 0, L.stream>>>(
+        q.Y, q.X, top1, top1_stride, left1, left1_stride, clean1, v1, v1_slot_stride, v1_pitch, dst, dst_stride,
+        slot0, Y0, Y1, W);
     COUNT(L);
   };
   run(top, q.strip_top_stride, 0, q.clean, Xl);
