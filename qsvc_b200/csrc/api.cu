@@ -291,7 +291,8 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     short *mv_tmp;
     int *d_slots, *d_slow;
     uint8_t *d_flags;
-    const int tiles_x = (X + 15) / 16, tiles_per_slot = tiles_x * ((Y + 15) / 16);
+    const int TSZ = 1 << SUBPEL_TILE_SHIFT;
+    const int tiles_x = (X + TSZ - 1) / TSZ, tiles_per_slot = tiles_x * ((Y + TSZ - 1) / TSZ);
     TRY(s.get((size_t)m * field * sizeof(short), (void **)&mv_tmp));
     TRY(s.get((size_t)m * 3 * sizeof(int), (void **)&d_slots));
     TRY(s.get((size_t)nslots * tiles_per_slot + 16, (void **)&d_flags));

@@ -75,13 +75,16 @@ struct SearchParams {
 };
 void launch_search(const Launch &L, const SearchParams &q, int npairs);
 // sub-pixel search levels without materialised up-sampled images (kernels_subpel.cu)
+// level-0 tiles of the "holds a non-byte sample" map are (1 << SUBPEL_TILE_SHIFT) pixels square: small
+// tiles keep isolated out-of-range pixels from sending whole neighbourhoods to the exact generator
+static constexpr int SUBPEL_TILE_SHIFT = 2;
 struct SubpelParams {
   Plane b0;            // compact level-0 buffers after the over-pixel descent
   const int *slots;    // per pair: R0 slot, R1 slot, P slot
   const uint8_t *v;    // V_l planes (u8, one per slot) of this level
   long long v_slot_stride;
   int v_pitch;
-  const uint8_t *tile_bad;  // per slot, per 16x16 level-0 tile: holds a sample outside [0,255]
+  const uint8_t *tile_bad;  // per slot, per level-0 tile: holds a sample outside [0,255]
   int tiles_x, tiles_per_slot;
   const short *mv_in;
   short *mv_out;

@@ -37,14 +37,14 @@ __global__ void __launch_bounds__(256) k_plane_to_u8(Plane src, int slot0, int Y
                                                      uint8_t *dst, long long dst_slot_stride,
                                                      int pitch, uint8_t *tile_bad, int tiles_x,
                                                      int tiles_per_slot) {
-  // tile_bad[slot][y >> 4][x >> 4] != 0: that 16x16 tile holds a sample outside [0,255]
+  // tile_bad[slot][y >> TS][x >> TS] != 0: that tile holds a sample outside [0,255]
   const int s = blockIdx.z;
   for (int y = blockIdx.y; y < Y; y += gridDim.y) {
     const short *row = src.row(slot0 + s, y);
     uint8_t *drow = dst + (long long)s * dst_slot_stride + (long long)y * pitch;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < X; x += gridDim.x * blockDim.x) {
       int v = row[x];
-      if ((unsigned)v > 255u) tile_bad[(long long)s * tiles_per_slot + (y >> 4) * tiles_x + (x >> 4)] = 1;
+      if ((unsigned)v > 255u) tile_bad[(long long)s * tiles_per_slot + (y >> SUBPEL_TILE_SHIFT) * tiles_x + (x >> SUBPEL_TILE_SHIFT)] = 1;
       drow[x] = (uint8_t)v;
     }
   }
@@ -323,7 +323,8 @@ __device__ __forceinline__ int classify_block(const SubpelParams &q, int l, int 
       const int pyl = max(y0 >> l, 0), pyh = min(((y0 + span - 1) >> l) + 1, q.Y - 1);
       const int pxl = max(x0 >> l, 0), pxh = min(((x0 + span - 1) >> l) + 1, q.X - 1);
       if (pyl > pyh || pxl > pxh) continue;
-      const int ty0 = pyl >> 4, nty = (pyh >> 4) - ty0 + 1, tx0 = pxl >> 4, ntx = (pxh >> 4) - tx0 + 1;
+      constexpr int TS = SUBPEL_TILE_SHIFT;
+      const int ty0 = pyl >> TS, nty = (pyh >> TS) - ty0 + 1, tx0 = pxl >> TS, ntx = (pxh >> TS) - tx0 + 1;
       const uint8_t *map = q.tile_bad + (long long)slot * q.tiles_per_slot;
       for (int i = threadIdx.x; i < nty * ntx; i += NT)
         bad |= map[(ty0 + i / ntx) * q.tiles_x + tx0 + i % ntx];
@@ -665,17 +666,18 @@ __global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __gr
   }
   int bad = 0;
   if (q.check_tiles) {
-    // 16x16 level-0 tiles under the three images' footprints: at most 4 x 4 each
-    if (threadIdx.x < 48) {
-      const int img = threadIdx.x >> 4, ty = (threadIdx.x >> 2) & 3, tx = threadIdx.x & 3;
-      const int slot = blk[4 + img];
-      const int y0 = img == 2 ? py0 : wy[img], x0 = img == 2 ? px0 : wx[img];
+    // level-0 tiles under the three images' footprints: at most TG x TG each (footprint <= 35 pixels)
+    constexpr int TS = SUBPEL_TILE_SHIFT, TG = (35 >> TS) + 2;
+    for (int i = threadIdx.x; i < 3 * TG * TG; i += NT) {
+      const int img = i / (TG * TG), r = i - img * (TG * TG), ty = r / TG, tx = r - ty * TG;
+      const int slot = img == 0 ? blk[4] : (img == 1 ? blk[5] : blk[6]);
+      const int y0 = img == 0 ? wy[0] : (img == 1 ? wy[1] : py0), x0 = img == 0 ? wx[0] : (img == 1 ? wx[1] : px0);
       const int span = img == 2 ? W : W + 2;
       const int pyl = max(y0 >> l, 0), pyh = min(((y0 + span - 1) >> l) + 1, q.Y - 1);
       const int pxl = max(x0 >> l, 0), pxh = min(((x0 + span - 1) >> l) + 1, q.X - 1);
-      const int tyy = (pyl >> 4) + ty, txx = (pxl >> 4) + tx;
-      if (pyl <= pyh && pxl <= pxh && tyy <= (pyh >> 4) && txx <= (pxh >> 4))
-        bad = q.tile_bad[(long long)slot * q.tiles_per_slot + tyy * q.tiles_x + txx];
+      const int tyy = (pyl >> TS) + ty, txx = (pxl >> TS) + tx;
+      if (pyl <= pyh && pxl <= pxh && tyy <= (pyh >> TS) && txx <= (pxh >> TS))
+        bad |= q.tile_bad[(long long)slot * q.tiles_per_slot + tyy * q.tiles_x + txx];
     }
     bad = __syncthreads_or(bad);
   }
