@@ -1332,7 +1332,7 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
   }
   {
     ProfScope ps_(L, KC_SEARCH_EXACT);
-    k_subpel_exact<W><<<148 * 2, 256, smem, L.stream>>>(q, v);
+    k_subpel_exact<W><<<148 * 4, 256, smem, L.stream>>>(q, v);
     COUNT(L);
   }
 }
