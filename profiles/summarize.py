@@ -119,11 +119,25 @@ json.dump({"workload": "cfg3", "source": f"gpurun_out/metrics_{tag}.csv (ncu, on
           open(os.path.join(ROOT, "profiles", f"{tag}_ncu.json"), "w"), indent=1)
 
 # ---- full captures of the top kernels
-rep = os.path.join(GO, f"top_{tag}.ncu-rep")
-if os.path.exists(rep):
+import glob
+reps = sorted(glob.glob(os.path.join(GO, f"top_{tag}*.ncu-rep")))
+cols_all, col_units, h, units = [], [], None, None
+for rep in reps:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rr = list(csv.reader(raw.splitlines()))
-    h = rr[0]
+    rr_ = list(csv.reader(raw.splitlines()))
+    if len(rr_) < 3:
+        continue
+    if h is None:
+        h, units = rr_[0], rr_[1]
+        cols_all += rr_[2:]
+        col_units += [rr_[1]] * len(rr_[2:])
+    else:  # align the columns of further reports to the first header (units differ per report)
+        pos = {n: i for i, n in enumerate(rr_[0])}
+        for r in rr_[2:]:
+            cols_all.append([r[pos[n]] if n in pos and pos[n] < len(r) else "" for n in h])
+            col_units.append([rr_[1][pos[n]] if n in pos else "" for n in h])
+if h is not None:
+    rr = [h, units] + cols_all
     want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram read"),
             ("dram__bytes_write.sum", "dram write"),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
@@ -146,12 +160,12 @@ if os.path.exists(rep):
     ki = h.index("Kernel Name")
     cols = rr[2:]
     P("## `ncu --set full --clock-control none --import-source on` of the level-1 launches of the top kernels\n")
-    P("(first temporal level of the step: 64 frame pairs)\n")
+    P("(first temporal level of the step: 64 frame pairs; `profiles/capture.sh`; k_mc_march from a second capture\n"
+      "with `-k regex:k_mc_march -c 2`)\n")
     P("| metric | " + " | ".join(f"`{kname(r[ki])}`" for r in cols) + " |")
     P("|---|" + "---:|" * len(cols))
     for i, n in idx:
-        unit = rr[1][i]
-        P(f"| {n}{' (' + unit + ')' if unit else ''} | " + " | ".join(r[i] for r in cols) + " |")
+        P(f"| {n} | " + " | ".join(f"{r[i]} {u[i]}".strip() for r, u in zip(cols, col_units)) + " |")
     P("")
 
 # ---- SASS evidence
