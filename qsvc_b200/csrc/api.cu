@@ -500,6 +500,7 @@ static int me_level(qsvc_ctx *c, const uint8_t *even, long long even_stride, con
   int S = heap_row_shorts(Xa, Ba);
   size_t slot_bytes = (size_t)((long long)Ya + 2LL * Ba + 2) * S * sizeof(short);
   int per_pair_slots = pr ? 2 : 3;
+  if (pr) slot_bytes += (size_t)Y * (((X + 7) & ~7)) * sizeof(short) * 4 / 3 + 64;  // LL snapshots of the descent
   long long max_pairs = (long long)(c->me_budget / slot_bytes - 1) / per_pair_slots;
   if (max_pairs < 1) max_pairs = 1;
 
@@ -566,10 +567,37 @@ static int me_level(qsvc_ctx *c, const uint8_t *even, long long even_stride, con
       launch_search(Lh, q, m);
       j++;
     };
-    dwt_analyze(Lh, img, 0, nslots, Y, X, L);
+    // For an invertible pyramid the descent only restores what the analysis overwrote:
+    // snapshot each LL region before it is transformed and copy it back instead of
+    // running the inverse transform (identical result, half the passes).
+    short *snap = nullptr;
+    std::vector<size_t> snap_off(L + 1, 0);
+    std::vector<int> snap_pitch(L + 1, 0);
+    size_t snap_per_slot = 0;
+    if (pr && L > 0) {
+      for (int l = 0; l < L; l++) {
+        snap_off[l] = snap_per_slot;
+        snap_pitch[l] = ((X >> l) + 7) & ~7;
+        snap_per_slot += (size_t)(Y >> l) * snap_pitch[l];
+      }
+      if (s.get(snap_per_slot * nslots * sizeof(short), (void **)&snap) != QSVC_OK) snap = nullptr;  // fall back
+    }
+    if (snap) {
+      for (int l = 0; l < L; l++) {
+        launch_region_copy(Lh, img, 0, nslots, Y >> l, X >> l, snap + snap_off[l], (long long)snap_per_slot,
+                           snap_pitch[l], true);
+        launch_dwt_level(Lh, img, 0, nslots, Y >> l, X >> l, false);
+      }
+    } else {
+      dwt_analyze(Lh, img, 0, nslots, Y, X, L);
+    }
     run_search(ME_INIT, desp(BY, L), desp(BX, L), bs, bd, 0);
     for (int l = L - 1; l >= 0; --l) {
-      dwt_synthesize(Lh, img, 0, nslots, desp(Y, l), desp(X, l), 1);
+      if (snap)
+        launch_region_copy(Lh, img, 0, nslots, Y >> l, X >> l, snap + snap_off[l], (long long)snap_per_slot,
+                           snap_pitch[l], false);
+      else
+        dwt_synthesize(Lh, img, 0, nslots, desp(Y, l), desp(X, l), 1);
       run_search(ME_DESCEND, desp(BY, l), desp(BX, l), bs, bd, sr);
     }
     for (int l = 1; l <= a; l++) {
