@@ -69,6 +69,10 @@ int qsvc_int_peak(qsvc_ctx *ctx, double *u8_sad_ops_per_s, double *i32_sad_ops_p
  * materialises the up-sampled images like the reference, 2 fused or fail.  All
  * modes produce identical motion fields. */
 int qsvc_set_me_mode(qsvc_ctx *ctx, int mode);
+/* Resident analysis with update_factor == 0: the motion estimation of level t+1 runs on a second
+ * stream beside the decorrelate of level t (every level's inputs are frames of the resident clip).
+ * 1 (default; env QSVC_OVERLAP): on, 0: one stream, strictly level by level.  Same results. */
+int qsvc_set_overlap(qsvc_ctx *ctx, int on);
 /* Same for decorrelate / correlate (env QSVC_MC_MODE): 1 literal path with materialised
  * int16 planes, 2 byte-plane fused path or fail, 0 automatic. */
 int qsvc_set_mc_mode(qsvc_ctx *ctx, int mode);

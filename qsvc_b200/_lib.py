@@ -59,6 +59,7 @@ SIGNATURES = {
     "qsvc_synchronize": (_i, [C.c_void_p]),
     "qsvc_set_tail_exchange": (_i, [C.c_void_p, TAIL_FN, C.c_void_p]),
     "qsvc_set_boundary_exchange": (_i, [C.c_void_p, BOUNDARY_FN, C.c_void_p]),
+    "qsvc_set_overlap": (_i, [C.c_void_p, _i]),
     "qsvc_set_me_mode": (_i, [C.c_void_p, _i]),
     "qsvc_set_mc_mode": (_i, [C.c_void_p, _i]),
     "qsvc_profile_enable": (_i, [C.c_void_p, _i]),

@@ -5,6 +5,8 @@
 // and the Python drivers (analyze.py:107-153, synthesize.py:95-153); all pixel
 // work runs in the kernels of kernels_*.cu on the context's CUDA stream.
 #include <math.h>
+
+#include <memory>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -49,6 +51,7 @@ struct PoolBlock {
   void *ptr;
   size_t size;
   bool used;
+  int lane;  // stream lane whose work last used the block: a free block is only handed back to that lane
 };
 
 struct LevelResult {
@@ -63,6 +66,12 @@ struct LevelResult {
 struct qsvc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
+  // second compute lane: with update_factor == 0 every level's inputs are frames of the resident clip,
+  // so the motion estimation of level t+1 runs beside the decorrelate of level t (env QSVC_OVERLAP=0: off)
+  cudaStream_t me_stream = nullptr;
+  std::vector<cudaEvent_t> me_events;
+  int lane = 0;      // lane of the pool blocks handed out right now (0: `stream`, 1: `me_stream`)
+  int overlap = 1;
   std::vector<cudaEvent_t> level_events;
   std::vector<cudaEvent_t> upload_events;  // qsvc_analyze: one per GOP of the clip being uploaded
   int upload_gops = 0, upload_gop_frames = 0;  // > 0: level 1 may start GOP by GOP behind the upload
@@ -94,7 +103,7 @@ static int pool_alloc(qsvc_ctx *c, size_t bytes, void **out) {
   if (bytes == 0) bytes = 256;
   int best = -1;
   for (size_t i = 0; i < c->pool.size(); i++)
-    if (!c->pool[i].used && c->pool[i].size >= bytes &&
+    if (!c->pool[i].used && c->pool[i].lane == c->lane && c->pool[i].size >= bytes &&
         (best < 0 || c->pool[i].size < c->pool[best].size))
       best = (int)i;
   if (best >= 0 && c->pool[best].size <= bytes * 2 + (1 << 20)) {
@@ -117,7 +126,7 @@ static int pool_alloc(qsvc_ctx *c, size_t bytes, void **out) {
     if (e != cudaSuccess)
       return fail(QSVC_ENOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
   }
-  c->pool.push_back(PoolBlock{p, bytes, true});
+  c->pool.push_back(PoolBlock{p, bytes, true, c->lane});
   *out = p;
   return QSVC_OK;
 }
@@ -948,6 +957,7 @@ qsvc_ctx *qsvc_create(int device) {
   c->device = device;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->me_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
       cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess) {
     fail(QSVC_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -965,6 +975,7 @@ qsvc_ctx *qsvc_create(int device) {
   if (const char *e = getenv("QSVC_MC_MODE")) c->mc_mode = atoi(e);
   if (const char *e = getenv("QSVC_TMA")) c->tma_mode = atoi(e);
   if (const char *e = getenv("QSVC_MC_MARCH")) c->mc_march = atoi(e);
+  if (const char *e = getenv("QSVC_OVERLAP")) c->overlap = atoi(e);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->me_budget = std::min<size_t>((size_t)64 << 30, free_b / 3);
   return c;
@@ -992,6 +1003,8 @@ void qsvc_destroy(qsvc_ctx *c) {
   cudaEventDestroy(c->ev3);
   for (auto e : c->level_events) cudaEventDestroy(e);
   for (auto e : c->upload_events) cudaEventDestroy(e);
+  for (auto e : c->me_events) cudaEventDestroy(e);
+  if (c->me_stream) cudaStreamDestroy(c->me_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -1055,6 +1068,11 @@ int qsvc_set_boundary_exchange(qsvc_ctx *c, qsvc_boundary_fn fn, void *user) {
   if (!c) return fail(QSVC_EINVAL, "null context");
   c->boundary_fn = fn;
   c->boundary_user = user;
+  return QSVC_OK;
+}
+int qsvc_set_overlap(qsvc_ctx *c, int on) {
+  if (!c) return fail(QSVC_EINVAL, "null context");
+  c->overlap = on ? 1 : 0;
   return QSVC_OK;
 }
 int qsvc_set_me_mode(qsvc_ctx *c, int mode) {
@@ -1342,6 +1360,21 @@ int qsvc_analyze(qsvc_ctx *c, const qsvc_analyze_params *p, const uint8_t *low0,
   return QSVC_OK;
 }
 
+// Runs `body` with the context switched to the motion-estimation lane (its own stream and its own
+// share of the memory pool), then switches back.
+struct MeLane {
+  qsvc_ctx *c;
+  cudaStream_t main;
+  explicit MeLane(qsvc_ctx *ctx) : c(ctx), main(ctx->stream) {
+    c->stream = c->me_stream;
+    c->lane = 1;
+  }
+  ~MeLane() {
+    c->stream = main;
+    c->lane = 0;
+  }
+};
+
 static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_level_out *outs) {
   if (!p || !c->low0) return fail(QSVC_EINVAL, "no resident sequence");
   if (p->pixels_in_x != c->X || p->pixels_in_y != c->Y) return fail(QSVC_EINVAL, "geometry mismatch");
@@ -1356,38 +1389,69 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
   const long long fb = frame_bytes(X, Y);
   int sr = p->search_range, bs = p->block_size, bs_min = p->block_size_min;
   if (bs < bs_min) bs_min = bs;  // analyze.py:118-119
+  // update_factor == 0 (analyze.py's default): update is the identity, low_t = even_t, so the inputs of
+  // every level are frames of the resident clip (even_t[k] = low_0[k << t]) and the motion estimation of
+  // level t+1 does not wait for the decorrelate of level t: two lanes, joined by one event per level.
+  const bool lanes = c->overlap != 0 && p->update_factor == 0.0f && p->TRLs > 2 && c->me_stream != nullptr;
+  {  // result buffers of every level first: nothing the pool hands out below is still in use elsewhere
+    int pics = pictures, b = bs;
+    for (int t = 1; t < p->TRLs; t++) {
+      const int n = pics / 2;
+      LevelResult &lv = c->levels[t];
+      lv.n_pairs = n;
+      lv.block_size = b;
+      const long long field = 4LL * (Y / b) * (X / b);
+      TRY(pool_alloc(c, (size_t)fb * n, (void **)&lv.high));
+      TRY(pool_alloc(c, (size_t)std::max<long long>(field, 1) * n * sizeof(short), (void **)&lv.motion));
+      TRY(pool_alloc(c, (size_t)std::max<long long>(field, 1) * n * sizeof(short), (void **)&lv.motion_filtered));
+      TRY(pool_alloc(c, (size_t)fb * (n + 1), (void **)&lv.low));
+      pics = (pics + 1) / 2;
+      b = std::max(b / 2, bs_min);
+    }
+  }
   const uint8_t *low = c->low0;
   CU(cudaEventRecord(c->ev2, c->stream));
+  if (lanes) {
+    // the ME lane starts where the main stream stands now
+    CU(cudaStreamWaitEvent(c->me_stream, c->ev2, 0));
+    while ((int)c->me_events.size() < p->TRLs) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->me_events.push_back(e);
+    }
+  }
   for (int t = 1; t < p->TRLs; t++) {
     const int n = pictures / 2;
     LevelResult &lv = c->levels[t];
-    lv.n_pairs = n;
-    lv.block_size = bs;
     lv.search_range = sr;
     const long long field = 4LL * (Y / bs) * (X / bs);
-    TRY(pool_alloc(c, (size_t)fb * n, (void **)&lv.high));
-    TRY(pool_alloc(c, (size_t)std::max<long long>(field, 1) * n * sizeof(short), (void **)&lv.motion));
-    TRY(pool_alloc(c, (size_t)std::max<long long>(field, 1) * n * sizeof(short), (void **)&lv.motion_filtered));
-    TRY(pool_alloc(c, (size_t)fb * (n + 1), (void **)&lv.low));
-    // split (split.cpp:229-341) is index arithmetic: even k = frame 2k, odd i = frame 2i+1
-    const uint8_t *even = low, *odd = low + fb;
+    // split (split.cpp:229-341) is index arithmetic: even k = frame 2k, odd i = frame 2i+1 of low_{t-1}
+    const long long in_stride = lanes ? (fb << t) : 2 * fb;
+    const uint8_t *even = lanes ? c->low0 : low, *odd = even + in_stride / 2;
     c->cur_level = t;
-    if (t == 1 && c->upload_gops > 0) {
-      const int per_gop = c->upload_gop_frames / 2;  // pairs of a GOP at level 1
-      for (int g = 0; g < c->upload_gops; g++) {
-        CU(cudaStreamWaitEvent(c->stream, c->upload_events[g], 0));
-        const long long f0 = (long long)g * per_gop;
-        TRY(me_level(c, even + f0 * 2 * fb, 2 * fb, odd + f0 * 2 * fb, 2 * fb, per_gop, X, Y, bs, p->border_size, sr,
-                     p->subpixel_accuracy, g == 0 ? p->first_gop_is_global_first : 0, lv.motion + f0 * field));
+    {
+      std::unique_ptr<MeLane> lane_guard;
+      if (lanes) lane_guard.reset(new MeLane(c));
+      if (t == 1 && c->upload_gops > 0) {
+        const int per_gop = c->upload_gop_frames / 2;  // pairs of a GOP at level 1
+        for (int g = 0; g < c->upload_gops; g++) {
+          CU(cudaStreamWaitEvent(c->stream, c->upload_events[g], 0));
+          const long long f0 = (long long)g * per_gop;
+          TRY(me_level(c, even + f0 * in_stride, in_stride, odd + f0 * in_stride, in_stride, per_gop, X, Y, bs,
+                       p->border_size, sr, p->subpixel_accuracy, g == 0 ? p->first_gop_is_global_first : 0,
+                       lv.motion + f0 * field));
+        }
+      } else {
+        TRY(me_level(c, even, in_stride, odd, in_stride, n, X, Y, bs, p->border_size, sr, p->subpixel_accuracy,
+                     p->first_gop_is_global_first, lv.motion));
       }
-    } else {
-      TRY(me_level(c, even, 2 * fb, odd, 2 * fb, n, X, Y, bs, p->border_size, sr, p->subpixel_accuracy,
-                   p->first_gop_is_global_first, lv.motion));
+      if (lanes) CU(cudaEventRecord(c->me_events[t], c->stream));
     }
-    TRY(mc_level(c, 1, even, 2 * fb, odd, 2 * fb, lv.motion, n, X, Y, bs, p->block_overlaping, sr,
+    if (lanes) CU(cudaStreamWaitEvent(c->stream, c->me_events[t], 0));
+    TRY(mc_level(c, 1, even, in_stride, odd, in_stride, lv.motion, n, X, Y, bs, p->block_overlaping, sr,
                  p->subpixel_accuracy, p->always_B, nullptr, lv.high, fb, &lv.types,
                  lv.motion_filtered, nullptr));
-    TRY(update_level(c, 0, even, 2 * fb, lv.high, fb, lv.motion_filtered, lv.types.c_str(), n, X, Y,
+    TRY(update_level(c, 0, even, in_stride, lv.high, fb, lv.motion_filtered, lv.types.c_str(), n, X, Y,
                      bs, p->update_factor, lv.low, fb));
     if (outs) {
       // stream this level's results to the host behind the next level's compute

@@ -113,6 +113,11 @@ class Context:
         """0 automatic, 1 literal (materialised) ME path, 2 fused ME path or fail."""
         check(self._L.qsvc_set_me_mode(self._h, mode))
 
+    def set_overlap(self, on: bool):
+        """Resident analysis with update_factor == 0: motion estimation of level t+1 beside the
+        decorrelate of level t on a second stream (default on).  Same results either way."""
+        check(self._L.qsvc_set_overlap(self._h, 1 if on else 0))
+
     def set_mc_mode(self, mode: int):
         """0 automatic, 1 literal decorrelate/correlate path, 2 byte-plane fused path or fail."""
         check(self._L.qsvc_set_mc_mode(self._h, mode))
