@@ -71,6 +71,7 @@ struct qsvc_ctx {
   cudaStream_t me_stream = nullptr;
   std::vector<cudaEvent_t> me_events;
   int lane = 0;      // lane of the pool blocks handed out right now (0: `stream`, 1: `me_stream`)
+  cudaEvent_t mv_ready = nullptr;  // decorrelate: wait for this event before the first use of the motion field
   int overlap = 1;
   std::vector<cudaEvent_t> level_events;
   std::vector<cudaEvent_t> upload_events;  // qsvc_analyze: one per GOP of the clip being uploaded
@@ -652,6 +653,17 @@ static void prepare_reference(qsvc_ctx *c, Plane ref, int slot_set, const uint8_
   for (int s = 1; s <= a; s++) dwt_synthesize(Lh, ref, s0, 3, Y << s, X << s, 1);
 }
 
+// The motion field of the level may still be in the making on the other lane (analyze_levels): whoever
+// reads it first waits for it here.  The byte-plane path up-samples its reference planes before.
+static int await_motion(qsvc_ctx *c) {
+  if (c->mv_ready) {
+    cudaEvent_t e = c->mv_ready;
+    c->mv_ready = nullptr;
+    CU(cudaStreamWaitEvent(c->stream, e, 0));
+  }
+  return QSVC_OK;
+}
+
 #include "mc_fused.inc"
 
 // analysis != 0: decorrelate (in = odd frames, out = high frames);
@@ -686,6 +698,7 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
   Scratch s(c);
   const bool fused = c->mc_mode != 1 && mc_fused_ok(X, Y, bs, ov, a);
   if (c->mc_mode == 2 && !fused) return fail(QSVC_EINVAL, "fused MC path requested but not applicable");
+  if (!fused) TRY(await_motion(c));
   int *d_hist = nullptr;
   const int HS = 1024;  // per pair: 256 predicted, 256 residue, 257 motion (+pad)
   const bool need_hist = analysis && !always_B;
@@ -1447,10 +1460,15 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
       }
       if (lanes) CU(cudaEventRecord(c->me_events[t], c->stream));
     }
-    if (lanes) CU(cudaStreamWaitEvent(c->stream, c->me_events[t], 0));
-    TRY(mc_level(c, 1, even, in_stride, odd, in_stride, lv.motion, n, X, Y, bs, p->block_overlaping, sr,
-                 p->subpixel_accuracy, p->always_B, nullptr, lv.high, fb, &lv.types,
-                 lv.motion_filtered, nullptr));
+    if (lanes) c->mv_ready = c->me_events[t];  // awaited inside, after the reference planes are up-sampled
+    {
+      const int rc = mc_level(c, 1, even, in_stride, odd, in_stride, lv.motion, n, X, Y, bs, p->block_overlaping, sr,
+                              p->subpixel_accuracy, p->always_B, nullptr, lv.high, fb, &lv.types,
+                              lv.motion_filtered, nullptr);
+      const int rw = await_motion(c);  // nothing read it (no pairs): the lanes still have to meet
+      if (rc != QSVC_OK) return rc;
+      if (rw != QSVC_OK) return rw;
+    }
     TRY(update_level(c, 0, even, in_stride, lv.high, fb, lv.motion_filtered, lv.types.c_str(), n, X, Y,
                      bs, p->update_factor, lv.low, fb));
     if (outs) {
