@@ -190,6 +190,36 @@ def _pictures_per_level(w):
     return out
 
 
+def bind_to_gpu_numa(index):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off (and thereby, by first touch,
+    its pinned host buffers to that node's memory): with several ranks per box the host<->device copies
+    of the end-to-end path otherwise cross the socket interconnect.  Best effort; returns a note."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(index)
+        bdf = None
+        if hasattr(props, "pci_bus_id") and hasattr(props, "pci_device_id"):
+            bdf = f"{getattr(props, 'pci_domain_id', 0):04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        if bdf is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True).stdout.strip()
+            bdf = out[-12:].lower() if out else None
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return "numa: unknown node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa: node {node} has no allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"numa: node {node}, {len(cpus)} CPUs"
+    except Exception as e:  # noqa: BLE001
+        return f"numa: not bound ({type(e).__name__})"
+
+
 # ----------------------------------------------------------------------- main
 
 def main():
@@ -243,6 +273,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (qsvc_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_note = bind_to_gpu_numa(local_rank) if world > 1 else "numa: single rank, not bound"
     if world > 1:
         # NCCL's own log lines (version banner, NCCL_DEBUG=INFO) must not share stdout with the JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -406,7 +437,7 @@ def main():
         "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": cfg, "clocks": clocks,
+        "config": dict(cfg, host=numa_note), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
