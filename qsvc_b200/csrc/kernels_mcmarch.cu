@@ -22,6 +22,8 @@
 //   * the LL rows that fall into the warp's row segment are turned into residue / reconstruction
 //     bytes (and histograms) on the spot.
 // No shared memory (except the optional histograms), no block barriers, no intermediate planes.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 #define COUNT(L) (++*(L).counter)
@@ -556,9 +558,11 @@ void launch_mc_march(const Launch &L, MarchParams q, int npairs) {
   q.bs_shift = 0;
   while ((1 << q.bs_shift) < q.bsa) q.bs_shift++;
   q.nstrips = (q.Xa + 8 * MARCH_UL - 1) / (8 * MARCH_UL);
-  // enough warps to fill the machine several times over, segments as tall as that allows
+  // enough warps to fill the machine several times over (measured: 12 rounds of 20 warps per SM beat 8;
+  // beyond 24 the warm-up rows of the extra segments cost more), segments as tall as that allows
   const long long cols = (long long)npairs * 3 * q.nstrips;
-  long long want = (148LL * 20 * 8 + cols - 1) / cols;
+  static const int seg_waves = getenv("QSVC_MARCH_WAVES") ? atoi(getenv("QSVC_MARCH_WAVES")) : 12;
+  long long want = (148LL * 20 * seg_waves + cols - 1) / cols;
   int seg_p = (int)((q.Ya + want - 1) / want);
   seg_p = (seg_p + 7) & ~7;
   if (seg_p < 64) seg_p = 64;
