@@ -361,7 +361,6 @@ __global__ void __launch_bounds__((W / 4) * (W / 8)) k_subpel_fast(SubpelParams 
 
   const int bx = blockIdx.x, by = blockIdx.y, pair = blockIdx.z;
   const int l = q.l;
-  const int Yl = q.Y << l, Xl = q.X << l;
   short c[4];
   subpel_centre(q, pair, by, bx, c);
   const int r0s = q.slots[3 * pair], r1s = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
@@ -970,43 +969,6 @@ __device__ __forceinline__ int level_cell(const SubpelParams &q, const B0View &v
     return q.v[(long long)slot * q.v_slot_stride + (long long)y * q.v_pitch + x];
   }
   return b0_cell(v, slot, y, x);
-}
-
-// H x WW window of the level-l image of `slot` at (y0, x0) into dst (row stride WW): one warp
-// per row, the row-invariant part of level_cell hoisted.
-// STRIPS = false: the image has no polluted strips (predicted frames: never border-filled) and the
-// window lies inside the picture.
-template <int H, int WW, bool STRIPS>
-__device__ __forceinline__ void load_window(const SubpelParams &q, const B0View &v, int slot, int y0, int x0,
-                                            short *dst) {
-  const int Yl = q.Y << q.l, Xl = q.X << q.l;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int yy = warp; yy < H; yy += 8) {
-    const int y = y0 + yy;
-    short *d = dst + yy * WW;
-    if (!STRIPS) {
-      const uint8_t *vb = q.v + (long long)slot * q.v_slot_stride + (long long)y * q.v_pitch + x0;
-      for (int xx = lane; xx < WW; xx += 32) d[xx] = vb[xx];
-      continue;
-    }
-    if (y < 0 || y >= Yl) {
-      for (int xx = lane; xx < WW; xx += 32) d[xx] = (short)b0_cell(v, slot, y, x0 + xx);
-      continue;
-    }
-    const short *top = q.strip_top + (long long)slot * q.strip_top_stride + (long long)y * Xl;
-    const short *left = q.strip_left + (long long)slot * q.strip_left_stride + (long long)(y - q.clean) * q.clean;
-    const uint8_t *vb = q.v + (long long)slot * q.v_slot_stride + (long long)y * q.v_pitch;
-    const bool in_top = y < q.clean;
-    for (int xx = lane; xx < WW; xx += 32) {
-      const int x = x0 + xx;
-      int val;
-      if (x < 0 || x >= Xl) val = b0_cell(v, slot, y, x);
-      else if (in_top) val = top[x];
-      else if (x < q.clean) val = left[x];
-      else val = vb[x];
-      d[xx] = (short)val;
-    }
-  }
 }
 
 // Blocks whose windows touch the polluted strips or leave the picture.  The predicted block is
