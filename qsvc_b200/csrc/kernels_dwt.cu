@@ -123,12 +123,22 @@ __global__ void __launch_bounds__(1024) k_dwt_cols(Plane p, int slot0, int ny, i
   const short *s = sm + c;
   // one row pointer walk per output stream
   if (!SYNTH) {
-    for (int i = i0; i < i1; i++) {
-      int l, h;
-      ana_pair(s, CW, i, ny, l, h);
-      p.row(slot, i)[x0 + c] = (short)l;
-      p.row(slot, nlow + i)[x0 + c] = (short)h;
-      if ((ny & 1) && i == half - 1) p.row(slot, half)[x0 + c] = (short)(s[(ny - 1) * CW] + tdiv2(h));
+    // sliding form: h[i-1] and the sample s[2i] carry over from the previous output pair
+    if (i0 < i1) {
+      int s0 = s[(2 * i0) * CW];
+      int hp = i0 > 0 ? (short)(s[(2 * i0 - 1) * CW] - tdiv2(s[(2 * i0 - 2) * CW] + s0)) : 0;
+      for (int i = i0; i < i1; i++) {
+        const int s1 = s[(2 * i + 1) * CW];
+        const bool last_even = !(ny & 1) && i == half - 1;
+        const int s2 = last_even ? 0 : s[(2 * i + 2) * CW];
+        const int h = (short)(last_even ? s1 - s0 : s1 - tdiv2(s0 + s2));
+        const int l = (short)(i == 0 ? s0 + tdiv2(h) : s0 + tdiv4(h + hp));
+        p.row(slot, i)[x0 + c] = (short)l;
+        p.row(slot, nlow + i)[x0 + c] = (short)h;
+        if ((ny & 1) && i == half - 1) p.row(slot, half)[x0 + c] = (short)(s[(ny - 1) * CW] + tdiv2(h));
+        hp = h;
+        s0 = s2;
+      }
     }
   } else {
     const short *lo = s, *hi = s + (long long)nlow * CW;
