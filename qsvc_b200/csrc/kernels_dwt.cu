@@ -185,6 +185,8 @@ static void launch_rows(const Launch &L, Plane p, int slot0, int nslots, int ny,
 static void launch_cols(const Launch &L, Plane p, int slot0, int nslots, int ny, int nx, bool synth) {
   int cw_log2 = 5;
   while (cw_log2 > 0 && ((size_t)ny << cw_log2) * sizeof(short) > (size_t)kMaxDynSmem) cw_log2--;
+  // at least two CTAs per SM: a strip is loaded, transformed and stored in phases that only overlap across CTAs
+  while (cw_log2 > 4 && ((size_t)ny << cw_log2) * sizeof(short) > (size_t)100 * 1024) cw_log2--;
   // keep at least ~2 CTAs per SM worth of strips when the image is narrow
   while (cw_log2 > 3 && ((nx + (1 << cw_log2) - 1) >> cw_log2) * nslots < 296) cw_log2--;
   dim3 grid((nx + (1 << cw_log2) - 1) >> cw_log2, 1, nslots);
