@@ -35,3 +35,28 @@ def test_oracle_matches_live_reference(X, Y, GOPs, TRLs, bs, sr, a, uf, flat):
             assert np.array_equal(yuv.read_frames(os.path.join(d, f"high_{t}"), X, Y), res[f"high_{t}"])
             assert np.array_equal(yuv.read_frames(os.path.join(d, f"low_{t}"), X, Y), res[f"low_{t}"])
             assert open(os.path.join(d, f"frame_types_{t}"), "rb").read() == res[f"frame_types_{t}"]
+
+
+OBMC_CASES = [
+    # X, Y, TRLs, bs, sr, a, uf, block_overlaping
+    (96, 64, 3, 16, 4, 0, 0.25, 2),
+    (64, 48, 3, 16, 4, 1, 0.0, 2),
+    (64, 64, 3, 16, 4, 2, 0.25, 4),
+    (64, 48, 2, 16, 4, 1, 0.0, 3),
+]
+
+
+@pytest.mark.parametrize("X,Y,TRLs,bs,sr,a,uf,ov", OBMC_CASES)
+def test_oracle_overlapped_prediction_matches_live_reference(X, Y, TRLs, bs, sr, a, uf, ov):
+    """--block_overlaping > 0 (decorrelate.cpp:84-88, 99-172) through the whole analysis chain."""
+    frames = 2 ** (TRLs - 1) + 1
+    clip = yuv.synthetic_clip(X, Y, frames, 33, max_shift=12)
+    with tempfile.TemporaryDirectory() as d:
+        yuv.write_frames(os.path.join(d, "low_0"), clip)
+        sched = run_ref.analyze(d, X, Y, 1, TRLs, bs, sr, a, uf, 0, block_overlaping=ov, block_size_min=bs)
+        res = orc.analyze(clip, X, Y, TRLs, bs, sr, a, uf, block_overlaping=ov, block_size_min=bs)
+        for s in sched:
+            t = s["t"]
+            assert np.array_equal(yuv.read_frames(os.path.join(d, f"high_{t}"), X, Y), res[f"high_{t}"])
+            assert np.array_equal(yuv.read_frames(os.path.join(d, f"low_{t}"), X, Y), res[f"low_{t}"])
+            assert open(os.path.join(d, f"frame_types_{t}"), "rb").read() == res[f"frame_types_{t}"]
