@@ -227,17 +227,34 @@ __global__ void __launch_bounds__(256) k_upsample_chain(const uint8_t *__restric
       cur = nxt;
       cp = np;
     } else {
-      // 256 threads = 16 rows x 16 column groups of 16 bytes; each thread walks down four rows
-      const int q = threadIdx.x & 15;
+      // 256 threads = 16 rows x 16 column groups of 16 bytes; each thread walks down four rows of
+      // the same parity: source and destination pointers advance by constants
+      const int q = threadIdx.x & 15, ty = threadIdx.x >> 4;
       if (gx0 + 16 * q < gm) {
-        for (int y = threadIdx.x >> 4; y < rows && gy0 + y < gn; y += 16) {
-          const uint4 v = up_row16(cur, cp, y, q);
-          uint8_t *d = g + (long long)y * o.pitch[k] + 16 * q;
+        const uint8_t *sp = cur + (ty >> 1) * cp + 8 * q;
+        uint8_t *d = g + (long long)ty * o.pitch[k] + 16 * q;
+        const long long dstep = 16LL * o.pitch[k];
+        const bool odd = ty & 1, tail8 = gx0 + 16 * q + 8 < gm;
+#pragma unroll
+        for (int y = ty; y < rows; y += 16, sp += 8 * cp, d += dstep) {
+          if (gy0 + y >= gn) break;
+          uint2 a = *reinterpret_cast<const uint2 *>(sp);
+          unsigned an = sp[8];
+          if (odd) {
+            const uint2 b = *reinterpret_cast<const uint2 *>(sp + cp);
+            a.x = __vhaddu4(a.x, b.x);
+            a.y = __vhaddu4(a.y, b.y);
+            an = (an + sp[cp + 8]) >> 1;
+          }
+          const unsigned h0 = __vhaddu4(a.x, __funnelshift_r(a.x, a.y, 8));
+          const unsigned h1 = __vhaddu4(a.y, __funnelshift_r(a.y, an, 8));
+          const uint4 v = make_uint4(__byte_perm(a.x, h0, 0x5140), __byte_perm(a.x, h0, 0x7362),
+                                     __byte_perm(a.y, h1, 0x5140), __byte_perm(a.y, h1, 0x7362));
           if (al16) {
             *reinterpret_cast<uint4 *>(d) = v;
           } else {
             *reinterpret_cast<uint2 *>(d) = make_uint2(v.x, v.y);
-            if (gx0 + 16 * q + 8 < gm) *reinterpret_cast<uint2 *>(d + 8) = make_uint2(v.z, v.w);
+            if (tail8) *reinterpret_cast<uint2 *>(d + 8) = make_uint2(v.z, v.w);
           }
         }
       }
