@@ -1026,7 +1026,7 @@ __global__ void __launch_bounds__(2 * W) k_subpel_strip(SubpelParams q, B0View v
       const int d = i / (RW * TP), r = i - d * (RW * TP), yy = r / TP, w = r - yy * TP;
       const int slot = rs[d], y = wy[d] + yy, x = wx[d] + 4 * w;
       unsigned cw = 0, ew = 0;
-      const bool row_in = y >= 0 && y < Yl, cols_in = x >= 0 && x + 3 < Xl;
+      const bool row_in = y >= 0 && y < Yl;
       if (row_in && y >= q.clean && x >= q.clean && x + 3 < Xl) {
         // byte plane: unaligned word = two aligned words + funnel shift
         const uint8_t *vb = q.v + (long long)slot * q.v_slot_stride + (long long)y * q.v_pitch + x;
@@ -1035,30 +1035,36 @@ __global__ void __launch_bounds__(2 * W) k_subpel_strip(SubpelParams q, B0View v
         const unsigned lo = __ldg(a4);
         cw = sa ? __funnelshift_r(lo, __ldg(a4 + 1), sa) : lo;
       } else {
+        // One per-sample rule for every other word (strip words, words outside the level-l image,
+        // words that straddle two regions), with the row-dependent parts resolved once: inside the
+        // image the int16 strips or the byte plane; outside it the reference's level-0 buffer at
+        // the same coordinates (b0_cell): the compact plane where it is materialised, the malloc
+        // size field at x in [-4, 0) of the un-shifted rows, zeros (never-written heap) elsewhere.
         int s4[4];
-        // words outside the level-l image read the reference's level-0 buffer at the same
-        // coordinates (b0_cell): the compact plane where it is materialised, zeros elsewhere,
-        // the malloc size field at x in [-4, 0) of the un-shifted rows
-        const bool outside = !row_in || x + 3 < 0 || x >= Xl;
-        const bool size_rows = y >= v.Ya - v.Ba && y < v.Ya + v.Ba;
-        if (row_in && cols_in && (y < q.clean || x + 3 < q.clean)) {
-          const short *src = y < q.clean
-                                 ? q.strip_top + (long long)slot * q.strip_top_stride + (long long)y * Xl + x
-                                 : q.strip_left + (long long)slot * q.strip_left_stride +
-                                       (long long)(y - q.clean) * q.clean + x;
+        const short *srow = nullptr;  // int16 strip row: top strip (all x) or left strip (x < clean)
+        const uint8_t *vrow = nullptr;
+        if (row_in) {
+          if (y < q.clean) {
+            srow = q.strip_top + (long long)slot * q.strip_top_stride + (long long)y * Xl;
+          } else {
+            srow = q.strip_left + (long long)slot * q.strip_left_stride + (long long)(y - q.clean) * q.clean;
+            vrow = q.v + (long long)slot * q.v_slot_stride + (long long)y * q.v_pitch;
+          }
+        }
+        const short *prow = (y >= -v.Bc && y < v.Y + v.Bc) ? v.p.row(slot, y) : nullptr;
+        const bool size_row = y >= v.Ya - v.Ba && y < v.Ya + v.Ba;
 #pragma unroll
-          for (int k = 0; k < 4; k++) s4[k] = src[k];
-        } else if (outside && !(size_rows && x < 0 && x + 3 >= -4) &&
-                   (y < -v.Bc || y >= v.Y + v.Bc || x + 3 < -v.Bc || x >= v.X + v.Bc)) {
-          s4[0] = s4[1] = s4[2] = s4[3] = 0;  // never-written heap
-        } else if (outside && !(size_rows && x < 0 && x + 3 >= -4) && y >= -v.Bc && y < v.Y + v.Bc &&
-                   x >= -v.Bc && x + 3 < v.X + v.Bc) {
-          const short *src = v.p.row(slot, y) + x;  // inside the compact plane
-#pragma unroll
-          for (int k = 0; k < 4; k++) s4[k] = src[k];
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; k++) s4[k] = level_cell(q, v, slot, y, x + k);
+        for (int k = 0; k < 4; k++) {
+          const int xk = x + k;
+          int sv = 0;
+          if (row_in && (unsigned)xk < (unsigned)Xl) {
+            sv = (vrow == nullptr || xk < q.clean) ? (int)srow[xk] : (int)vrow[xk];
+          } else if (prow != nullptr && xk >= -v.Bc && xk < v.X + v.Bc) {
+            sv = prow[xk];
+          } else if (size_row && xk < 0 && xk >= -4) {
+            sv = (short)((v.size_field >> (16 * (xk + 4))) & 0xffff);
+          }
+          s4[k] = sv;
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -1299,7 +1305,7 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
   const int RW = W + 2, TW = W / 2 + 4;
   {
     ProfScope ps_(L, KC_SEARCH_EXACT);
-    k_subpel_strip<W><<<148 * 8, 2 * W, 0, L.stream>>>(q, v);
+    k_subpel_strip<W><<<148 * 10, 2 * W, 0, L.stream>>>(q, v);
     COUNT(L);
   }
   size_t smem = ((size_t)W * W + 2 * (size_t)RW * RW + (size_t)TW * TW + 2 * (size_t)RW * TW + 4 * (size_t)TW * TW) *
