@@ -1119,8 +1119,11 @@ __global__ void __launch_bounds__(256) k_level1_tile(B0View v, int slot0, int Y0
     return xp < X ? (int)v.p.row(slot, i)[xp] : b0_high(v, slot, i, xp);
   };
   // phase A: even rows of the column pass
-  for (int t = threadIdx.x; t < 2 * ni * (nj + 1); t += 256) {
-    const int set = t / (ni * (nj + 1)), r = t % (ni * (nj + 1)), ii = r / (nj + 1), jj = r % (nj + 1);
+  // (the loops run over the padded index space so that every index is decoded with constant divisors)
+  constexpr int NI = TR / 2 + 2, NJ = NC + 1;
+  for (int t = threadIdx.x; t < 2 * NI * NJ; t += 256) {
+    const int set = t / (NI * NJ), r = t - set * (NI * NJ), ii = r / NJ, jj = r - ii * NJ;
+    if (ii >= ni || jj > nj) continue;
     const int i = i0 + ii;
     const int xp = set ? X + j0 - 1 + jj : j0 + jj;
     int val = 0;
@@ -1133,8 +1136,9 @@ __global__ void __launch_bounds__(256) k_level1_tile(B0View v, int slot0, int Y0
   }
   __syncthreads();
   // phase B: all rows of the column pass
-  for (int t = threadIdx.x; t < 2 * (yb - ya) * (nj + 1); t += 256) {
-    const int set = t / ((yb - ya) * (nj + 1)), r = t % ((yb - ya) * (nj + 1)), yy = r / (nj + 1), jj = r % (nj + 1);
+  for (int t = threadIdx.x; t < 2 * TR * NJ; t += 256) {
+    const int set = t / (TR * NJ), r = t - set * (TR * NJ), yy = r / NJ, jj = r - yy * NJ;
+    if (yy >= yb - ya || jj > nj) continue;
     const int y = ya + yy, i = y >> 1, ii = i - i0;
     const int xp = set ? X + j0 - 1 + jj : j0 + jj;
     int val = TE[set][ii][jj];
@@ -1146,8 +1150,9 @@ __global__ void __launch_bounds__(256) k_level1_tile(B0View v, int slot0, int Y0
   }
   __syncthreads();
   // phase C: even columns of the row pass, j = j0 + jj
-  for (int t = threadIdx.x; t < (yb - ya) * nj; t += 256) {
-    const int yy = t / nj, jj = t % nj, j = j0 + jj;
+  for (int t = threadIdx.x; t < TR * NJ; t += 256) {
+    const int yy = t / NJ, jj = t - yy * NJ, j = j0 + jj;
+    if (yy >= yb - ya || jj >= nj) continue;
     int val = 0;
     if (j < X) {
       // high-set index of column X + j is jj + 1, of X + j - 1 is jj
@@ -1158,8 +1163,9 @@ __global__ void __launch_bounds__(256) k_level1_tile(B0View v, int slot0, int Y0
   }
   __syncthreads();
   short *d = dst + (long long)slot * dst_slot_stride;
-  for (int t = threadIdx.x; t < (yb - ya) * (xb - xa); t += 256) {
-    const int yy = t / (xb - xa), xx = t % (xb - xa), x = xa + xx, j = x >> 1, jj = j - j0;
+  for (int t = threadIdx.x; t < TR * TC; t += 256) {
+    const int yy = t / TC, xx = t - yy * TC, x = xa + xx, j = x >> 1, jj = j - j0;
+    if (yy >= yb - ya || xx >= xb - xa) continue;
     int val = EE[yy][jj];
     if (x & 1) {
       const int h = TT[1][yy][jj + 1];
