@@ -1,7 +1,7 @@
 """Multi-GPU check (not collected by pytest): one sequence whose height is not a multiple
 of the block size, GOP-sharded over the ranks of a torchrun job (one GPU per rank, NCCL
-point-to-point for the prediction tail state), analysis and synthesis, compared byte for
-byte on rank 0 with the CPU oracle.
+point-to-point for the prediction tail state and, with update_factor != 0, for the boundary
+frame), analysis and synthesis, compared byte for byte on rank 0 with the CPU oracle.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
       --master-port 29511 tests/run_sharded_parity.py
@@ -28,26 +28,30 @@ def main():
     X, Y, TRLs, bs, sr, a = 128, 72, 4, 16, 4, 2
     GOPs = max(2, world)
     clip = yuv.synthetic_clip(X, Y, GOPs * 2 ** (TRLs - 1) + 1, 31, max_shift=12)
-    kw = dict(block_size=bs, search_range=sr, subpixel_accuracy=a, update_factor=0.0)
+    ok = True
     with Context(local) as ctx:
-        got = shard.analyze_distributed(ctx, clip, X, Y, GOPs, TRLs, block_size_min=bs, **kw)
-        ref = orc.analyze(clip, X, Y, TRLs, bs, sr, a, 0.0, block_size_min=bs)
-        sub = {f"low_{TRLs-1}": ref[f"low_{TRLs-1}"]}
-        for t in range(1, TRLs):
-            sub[f"high_{t}"], sub[f"motion_{t}"] = ref[f"high_{t}"], ref[f"motion_filtered_{t}"]
-            sub[f"frame_types_{t}"] = ref[f"frame_types_{t}"]
-        rec = shard.synthesize_distributed(ctx, sub, X, Y, GOPs, TRLs, **kw)
-        ok = True
-        if rank == 0:
-            for k, v in got.items():
-                same = np.array_equal(ref[k], v) if not isinstance(v, bytes) else ref[k] == v
-                ok &= bool(same)
-                if not same:
-                    print("MISMATCH", k)
-            whole = ctx.synthesize(sub, X, Y, GOPs, TRLs, bs, sr, a, 0.0)
-            same = np.array_equal(rec, whole)
-            ok &= bool(same)
-            print(f"sharded parity over {world} GPUs: analysis+synthesis {'OK' if ok else 'FAILED'}")
+        # update_factor 0: tail hand-over only; 0.25: also the boundary-frame hand-over
+        for uf in (0.0, 0.25):
+            kw = dict(block_size=bs, search_range=sr, subpixel_accuracy=a, update_factor=uf)
+            got = shard.analyze_distributed(ctx, clip, X, Y, GOPs, TRLs, block_size_min=bs, **kw)
+            ref = orc.analyze(clip, X, Y, TRLs, bs, sr, a, uf, block_size_min=bs)
+            sub = {f"low_{TRLs-1}": ref[f"low_{TRLs-1}"]}
+            for t in range(1, TRLs):
+                sub[f"high_{t}"], sub[f"motion_{t}"] = ref[f"high_{t}"], ref[f"motion_filtered_{t}"]
+                sub[f"frame_types_{t}"] = ref[f"frame_types_{t}"]
+            rec = shard.synthesize_distributed(ctx, sub, X, Y, GOPs, TRLs, **kw)
+            if rank == 0:
+                good = True
+                for k, v in got.items():
+                    same = np.array_equal(ref[k], v) if not isinstance(v, bytes) else ref[k] == v
+                    good &= bool(same)
+                    if not same:
+                        print("MISMATCH", k)
+                whole = ctx.synthesize(sub, X, Y, GOPs, TRLs, bs, sr, a, uf)
+                good &= bool(np.array_equal(rec, whole))
+                ok &= good
+                print(f"sharded parity over {world} GPUs, update_factor {uf}: analysis+synthesis "
+                      f"{'OK' if good else 'FAILED'}")
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
