@@ -203,23 +203,6 @@ struct PredU8Params {
 };
 void launch_predict_u8(const Launch &L, const PredU8Params &q, int npairs);
 
-struct LLParams {
-  const uint8_t *p;          // P_a planes, [pair][component]
-  long long p_plane_stride;
-  int p_pitch;
-  const uint8_t *in;         // analysis: odd frames; synthesis: high frames (I420, per pair)
-  long long in_stride;
-  uint8_t *out;              // analysis: high frames ('B' variant); synthesis: odd frames
-  long long out_stride;
-  uint8_t *prediction;       // nullable: prediction_<even> side output, frame stride pred_stride
-  long long pred_stride;
-  int *hist;                 // nullable: per pair [0,256) predicted luma, [256,512) residue + 128
-  int hist_stride;
-  const char *types;         // synthesis: frame types (device)
-  int X, Y, a, synth;
-  int smem_a, smem_b;        // filled by the launcher
-};
-void launch_ll_residue(const Launch &L, LLParams q, int npairs);
 // ---- line-based decorrelate / correlate (kernels_mcmarch.cu) ----
 struct MarchParams {
   const uint8_t *v;          // V_a planes, [even frame][component], (Ya + 2) x v_pitch each

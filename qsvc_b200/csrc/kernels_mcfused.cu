@@ -11,9 +11,10 @@
 //   P_a  = (V_a0[+mv0] + V_a1[+mv1]) >> 1   k_predict_u8: __vhaddu4 on 32-bit words; blocks
 //          whose displaced footprint leaves the picture use the closed-form border
 //          rule of the reference's texture::alloc/fill_border (bordered_ref)
-//   LL   = LL-only multi-level integer 5/3 analysis of P_a, tile by tile in shared
-//          memory, fused with the residue / reconstruction and the I/B histograms
-//          (k_ll_residue).
+//   LL   = LL-only multi-level integer 5/3 analysis of P_a fused with the residue /
+//          reconstruction and the I/B histograms: k_mc_march (kernels_mcmarch.cu), which also
+//          folds the prediction in, so that P_a is only materialised for the last block row
+//          that feeds the tail chain below.
 // Rows of P_a below the last whole block (Y % block_size != 0) are never written by
 // predict(); the reference keeps there what the previous pair's in-place analysis
 // left.  k_tail_state reproduces that chain: it is the only
@@ -117,263 +118,6 @@ template <typename F>
 __device__ __forceinline__ int hh53(F S, int i, int n) {
   return (i == (n >> 1) - 1) ? (short)(S(n - 1) - S(n - 2))
                              : (short)(S(2 * i + 1) - tdiv2(S(2 * i) + S(2 * i + 2)));
-}
-
-// Flattened 2-D loop over h x w elements by 256 threads without a division per element.
-#define LL_NT 512
-#define FOR_2D(r, c, h, w)                                                                      \
-  for (int i_ = threadIdx.x, r = i_ / (w), c = i_ - r * (w), dc_ = LL_NT % (w), dr_ = LL_NT / (w); \
-       i_ < (h) * (w); i_ += LL_NT, c += dc_, r += dr_, r += (c >= (w)), c -= (c >= (w)) ? (w) : 0)
-
-// l[m] from a line reached through s[g * st] (g = global index minus `base`), line
-// length n.  Branch-free: out-of-line taps of the first / last sample are re-pointed at
-// valid cells and masked by selects.
-template <typename T>
-__device__ __forceinline__ int ll53_line(const T *s, int st, int base, int m, int n) {
-  const T *p = s + (2 * m - base) * st;
-  const bool last = (m == (n >> 1) - 1), first = (m == 0);
-  const int s0 = p[0], s1 = p[st];
-  const int s2 = p[last ? st : 2 * st];
-  const int sm1 = p[first ? 0 : -st], sm2 = p[first ? 0 : -2 * st];
-  const int hm = (short)(s1 - (last ? s0 : tdiv2(s0 + s2)));
-  const int hm1 = (short)(sm1 - tdiv2(sm2 + s0));
-  const int hs = first ? 2 * hm : hm + hm1;  // l[0] = s[0] + h[0]/2 == s[0] + (2 h[0])/4
-  return (short)(s0 + tdiv4(hs));
-}
-
-// Sliding LL pass along one line: outputs l[m0 .. m0+cnt) of a line of n samples read
-// through src[(g - base) * sst] (g = global sample index) into dst[k * dst_st].  Each step
-// loads two new samples and reuses s[2m] and h[m-1] from the previous step.
-__device__ __forceinline__ void ll53_slide(const short *src, int sst, int base, int n, int m0, int cnt,
-                                           short *dst, int dst_st) {
-  if (cnt <= 0) return;
-  const int half = n >> 1;
-  const short *p = src + (2 * m0 - base) * sst;
-  int s0 = p[0];
-  int hprev = 0;
-  if (m0 > 0) hprev = (short)(p[-sst] - tdiv2(p[-2 * sst] + s0));
-  for (int k = 0; k < cnt; k++) {
-    const int m = m0 + k;
-    const int s1 = p[sst];
-    int hm, s2 = 0;
-    if (m == half - 1) {
-      hm = (short)(s1 - s0);
-    } else {
-      s2 = p[2 * sst];
-      hm = (short)(s1 - tdiv2(s0 + s2));
-    }
-    const int hs = (m == 0) ? 2 * hm : hm + hprev;
-    dst[k * dst_st] = (short)(s0 + tdiv4(hs));
-    hprev = hm;
-    s0 = s2;
-    p += 2 * sst;
-  }
-}
-
-// Level 0 -> 1 row pass on bytes: one thread produces the four outputs m = 4g+1 .. 4g+4
-// of one tile row from the 11 bytes [8g, 8g+11) held in three aligned words.
-__device__ __forceinline__ void ll53_row_u8x4(const unsigned *row_words, int xs, int nwords, int g,
-                                              int n, int mx0, int mx1, short *dst /* row, index m - mx0 */) {
-  const int half = n >> 1;
-  // word index of byte 8g inside the staged row (xs is a multiple of 8)
-  const int wi = (8 * g - xs) >> 2;
-  unsigned w[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    int idx = wi + k;
-    idx = idx < 0 ? 0 : (idx >= nwords ? nwords - 1 : idx);
-    w[k] = row_words[idx];
-  }
-  int s[11];
-#pragma unroll
-  for (int k = 0; k < 11; k++) s[k] = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
-  // h_rel[j] = h[4g + j], j = 0..4 (bytes are non-negative: /2 is a shift)
-  int h[5];
-#pragma unroll
-  for (int j = 0; j < 5; j++) {
-    const int gi = 4 * g + j;
-    h[j] = (gi == half - 1) ? s[2 * j + 1] - s[2 * j] : s[2 * j + 1] - ((s[2 * j] + s[2 * j + 2]) >> 1);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int m = 4 * g + 1 + i;
-    if (m >= mx0 && m < mx1 && m > 0) {
-      const int hs = h[i + 1] + h[i];  // m >= 1 here: l[m] = s[2m] + (h[m] + h[m-1]) / 4
-      dst[m - mx0] = (short)(s[2 * i + 2] + tdiv4(hs));
-    }
-  }
-}
-
-// Output tile [oy0,oy0+T) x [ox0,ox0+T) of the level-nlev LL band of one P_a plane,
-// then residue (analysis) or reconstruction (synthesis) of that tile.
-// grid (ceil(X/32), ceil(Y/32), pairs * 3)
-__global__ void __launch_bounds__(LL_NT) k_ll_residue(LLParams q) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  __shared__ int h_pred[256], h_res[256];
-  const int pair = blockIdx.z / 3, c = blockIdx.z % 3;
-  const int nlev = q.a + (c ? 1 : 0);
-  const int T = nlev >= 3 ? 16 : 32;
-  const int OW = c ? q.X / 2 : q.X, OH = c ? q.Y / 2 : q.Y;  // component size = LL size
-  const int ox0 = blockIdx.x * T, oy0 = blockIdx.y * T;
-  if (ox0 >= OW || oy0 >= OH) return;
-  const int ox1 = min(ox0 + T, OW), oy1 = min(oy0 + T, OH);
-  const uint8_t *P = q.p + ((long long)pair * 3 + c) * q.p_plane_stride;
-  const long long coff = c == 0 ? 0 : (long long)q.X * q.Y + (long long)(c - 1) * (q.X / 2) * (q.Y / 2);
-  const bool do_hist = q.hist && c == 0 && !q.synth;
-  if (do_hist) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) h_pred[i] = h_res[i] = 0;
-  }
-  // required index ranges per level, top-down: l[m] needs s[2m-2 .. 2m+2]
-  int ry0[4], ry1[4], rx0[4], rx1[4];
-  ry0[nlev] = oy0; ry1[nlev] = oy1; rx0[nlev] = ox0; rx1[nlev] = ox1;
-  for (int k = nlev; k > 0; k--) {
-    const int ny = (q.Y << q.a) >> (k - 1), nx = (q.X << q.a) >> (k - 1);
-    ry0[k - 1] = max(0, 2 * ry0[k] - 2); ry1[k - 1] = min(ny, 2 * ry1[k] + 1);
-    rx0[k - 1] = max(0, 2 * rx0[k] - 2); rx1[k - 1] = min(nx, 2 * rx1[k] + 1);
-  }
-  short *A = reinterpret_cast<short *>(smraw);  // row-pass output
-  short *B = A + q.smem_a;                      // column-pass output (level image)
-  const short *LL = nullptr;
-  int ll_w = 0;
-  if (nlev > 0) {
-    // level-0 bytes are read straight from the plane (aligned 32-bit loads through L1)
-    const int xs = rx0[0] & ~7;
-    const int uw = (rx1[0] - xs + 3) >> 2;  // words per tile row
-    // level 0 -> 1
-    {
-      const int h0 = ry1[0] - ry0[0], w1 = rx1[1] - rx0[1], h1 = ry1[1] - ry0[1];
-      const int nx = q.X << q.a, ny = q.Y << q.a;
-      const int mx0 = rx0[1], my0 = ry0[1];
-      {
-        // row pass: groups of four outputs m = 4g+1 .. 4g+4; m = 0 (first column of the
-        // picture) is outside every group and handled by the generic tap code
-        const int mx1 = rx1[1];
-        const int g_lo = (max(mx0, 1) - 1) >> 2, g_hi = (mx1 - 2) >> 2;
-        const int ng = g_hi - g_lo + 1;
-        FOR_2D(r, gg, h0, ng)
-          ll53_row_u8x4(reinterpret_cast<const unsigned *>(P + (long long)(ry0[0] + r) * q.p_pitch + xs), xs, uw,
-                        g_lo + gg, nx, mx0, mx1, A + r * w1);
-        if (mx0 == 0)
-          for (int r = threadIdx.x; r < h0; r += LL_NT)
-            A[r * w1] = (short)ll53_line(P + (long long)(ry0[0] + r) * q.p_pitch, 1, 0, 0, nx);
-      }
-      __syncthreads();
-      {
-        // column pass: thread = (column, row segment), sliding down the column
-        const int nseg = max(1, LL_NT / w1), per = (h1 + nseg - 1) / nseg;
-        const int col = threadIdx.x % w1, seg = threadIdx.x / w1;
-        if (seg < nseg) {
-          const int k0 = seg * per, cnt = min(per, h1 - k0);
-          ll53_slide(A + col, w1, ry0[0], ny, my0 + k0, cnt, B + k0 * w1 + col, w1);
-        }
-      }
-      __syncthreads();
-    }
-    for (int k = 1; k < nlev; k++) {
-      const int hk = ry1[k] - ry0[k], wk = rx1[k] - rx0[k];
-      const int w1 = rx1[k + 1] - rx0[k + 1], h1 = ry1[k + 1] - ry0[k + 1];
-      const int nx = (q.X << q.a) >> k, ny = (q.Y << q.a) >> k;
-      const int mx0 = rx0[k + 1], my0 = ry0[k + 1], bx0 = rx0[k], by0 = ry0[k];
-      {
-        // row pass: thread = (row, column segment), sliding along the row
-        const int nseg = max(1, LL_NT / hk), per = (w1 + nseg - 1) / nseg;
-        const int row = threadIdx.x % hk, seg = threadIdx.x / hk;
-        if (seg < nseg) {
-          const int k0 = seg * per, cnt = min(per, w1 - k0);
-          ll53_slide(B + row * wk, 1, bx0, nx, mx0 + k0, cnt, A + row * w1 + k0, 1);
-        }
-      }
-      __syncthreads();
-      {
-        const int nseg = max(1, LL_NT / w1), per = (h1 + nseg - 1) / nseg;
-        const int col = threadIdx.x % w1, seg = threadIdx.x / w1;
-        if (seg < nseg) {
-          const int k0 = seg * per, cnt = min(per, h1 - k0);
-          ll53_slide(A + col, w1, by0, ny, my0 + k0, cnt, B + k0 * w1 + col, w1);
-        }
-      }
-      __syncthreads();
-    }
-    LL = B;
-    ll_w = ox1 - ox0;
-  } else if (do_hist) {
-    __syncthreads();
-  }
-  const uint8_t *in = q.in + (long long)pair * q.in_stride + coff;
-  uint8_t *out = q.out + (long long)pair * q.out_stride + coff;
-  uint8_t *pout = q.prediction ? q.prediction + (long long)pair * q.pred_stride + coff : nullptr;
-  const int is_I = q.synth && q.types[pair] == 'I';
-  const int tw = ox1 - ox0, th = oy1 - oy0;
-  FOR_2D(r, cc, th, tw) {
-    const int y = oy0 + r, x = ox0 + cc;
-    const int p = LL ? (int)LL[r * ll_w + cc] : (int)P[(long long)y * q.p_pitch + x];
-    const int s = in[(long long)y * OW + x];
-    int o;
-    if (!q.synth) {
-      int rr = s - p;
-      rr = rr < -128 ? -128 : (rr > 127 ? 127 : rr);
-      o = rr + 128;
-      if (do_hist) {
-        atomicAdd(&h_pred[s], 1);
-        atomicAdd(&h_res[o], 1);
-      }
-    } else if (is_I) {
-      o = s;
-    } else {
-      o = s - 128 + p;
-      o = o < 0 ? 0 : (o > 255 ? 255 : o);
-    }
-    out[(long long)y * OW + x] = (uint8_t)o;
-    if (pout) pout[(long long)y * OW + x] = (uint8_t)p;
-  }
-  if (do_hist) {
-    __syncthreads();
-    int *hist = q.hist + (long long)pair * q.hist_stride;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-      if (h_pred[i]) atomicAdd(&hist[i], h_pred[i]);
-      if (h_res[i]) atomicAdd(&hist[256 + i], h_res[i]);
-    }
-  }
-}
-
-// shared-memory footprint (shorts) of the row-pass (A) and level (B) buffers
-static void ll_smem(int a, int *sa, int *sb, int *su) {
-  int A = 0, B = 0, U = 0;
-  for (int c = 0; c < 2; c++) {
-    int nlev = a + c;
-    if (nlev == 0) continue;
-    int T = nlev >= 3 ? 16 : 32;
-    int ext[4];
-    ext[nlev] = T;
-    for (int k = nlev; k > 0; k--) ext[k - 1] = 2 * ext[k] + 3;
-    U = U > ext[0] * (ext[0] + 12) ? U : ext[0] * (ext[0] + 12);
-    for (int k = 0; k < nlev; k++) {
-      A = A > ext[k] * ext[k + 1] ? A : ext[k] * ext[k + 1];
-      B = B > ext[k + 1] * ext[k + 1] ? B : ext[k + 1] * ext[k + 1];
-    }
-  }
-  *sa = (A + 7) & ~7;
-  *sb = (B + 7) & ~7;
-  *su = (U + 15) & ~15;
-}
-
-void launch_ll_residue(const Launch &L, LLParams q, int npairs) {
-  if (npairs <= 0) return;
-  int sa, sb, su;
-  ll_smem(q.a, &sa, &sb, &su);
-  q.smem_a = sa;
-  q.smem_b = sb;
-  size_t smem = (size_t)(sa + sb) * sizeof(short);
-  (void)su;
-  static size_t s_attr = 0;
-  if (smem > 48 * 1024 && smem > s_attr) {
-    cudaFuncSetAttribute(k_ll_residue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    s_attr = smem;
-  }
-  dim3 grid((q.X + 31) / 32, (q.Y + 31) / 32, npairs * 3);
-  ProfScope ps_(L, KC_RESIDUE);
-  k_ll_residue<<<grid, LL_NT, smem, L.stream>>>(q);
-  COUNT(L);
 }
 
 // ---- chained tail rows (Y % block_size != 0) ----

@@ -123,7 +123,7 @@ def test_me_literal_and_fused_paths_agree_with_oracle(ctx, mode, X, Y, GOPs, TRL
 @pytest.mark.parametrize("X,Y,GOPs,TRLs,bs,sr,a,uf,flat", CASES)
 def test_mc_literal_and_fused_paths_agree_with_oracle(ctx, mode, X, Y, GOPs, TRLs, bs, sr, a, uf, flat):
     """decorrelate / correlate: mode 1 materialises int16 planes like the reference,
-    mode 2 runs on byte planes (k_predict_u8 + k_ll_residue + chained tail rows)."""
+    mode 2 runs on byte planes (k_mc_march + chained tail rows)."""
     from qsvc_b200._lib import QsvcError
     low = clip_for(X, Y, GOPs, TRLs, sr, flat, seed=17)
     ctx.set_mc_mode(mode)
