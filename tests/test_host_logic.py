@@ -77,3 +77,34 @@ def test_cli_split_merge_and_exit_codes(tmp_path):
     # unreadable input: abort
     r = _run(["split", "--low_fn=missing"] + geo, d)
     assert r.returncode == 134 and b"aborting" in r.stderr
+
+
+def test_thread_boundary_relay_routes_between_neighbours():
+    """shard.ThreadBoundaryRelay: planes travel right (phase 1 -> phase 0), the finished frame travels
+    back left (phase 2 -> phase 3); the first shard has no left neighbour, the last no right one."""
+    import threading
+
+    from qsvc_b200 import shard
+    n = 3
+    relays = shard.ThreadBoundaryRelay.make(n)
+    log = [None] * n
+
+    def work(r):
+        planes = np.full(8, 10 + r, np.uint8)
+        has_right = relays[r](1, 0, 1, planes)          # last frame after the NEXT pass
+        first = np.zeros(8, np.uint8)
+        got = relays[r](1, 0, 0, first)                 # first frame: the left neighbour's planes
+        relays[r](1, 0, 2, np.full(4, 100 + r, np.uint8))
+        back = np.zeros(4, np.uint8)
+        if has_right:
+            assert relays[r](1, 0, 3, back)
+        log[r] = (bool(has_right), bool(got), int(first[0]), int(back[0]))
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=30)
+    assert log[0] == (True, False, 0, 101)
+    assert log[1] == (True, True, 10, 102)
+    assert log[2] == (False, True, 11, 0)
