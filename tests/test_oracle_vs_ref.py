@@ -18,6 +18,9 @@ CASES = [
     (96, 72, 1, 4, 16, 4, 1, 0.0, 0),
     (64, 60, 1, 3, 8, 64, 0, 0.0, 0),
     (80, 48, 1, 3, 16, 16, 2, 0.25, 0),
+    (176, 144, 2, 3, 32, 4, 1, 0.5, 3),     # 32 x 32 blocks, X % bs != 0, two GOPs, I frames
+    (128, 72, 2, 4, 16, 4, 2, 0.25, 0),     # Y % bs != 0 at quarter-pel: tail chain across GOPs
+    (96, 64, 1, 3, 16, 6, 1, 0.25, 0),      # search range that is not a power of two
 ]
 
 
