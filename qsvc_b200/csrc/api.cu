@@ -153,6 +153,8 @@ struct Scratch {
     if (rc == QSVC_OK) ptrs.push_back(*out);
     return rc;
   }
+  // hands the block over to the caller (it outlives the scope)
+  void detach(void *p) { ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), p), ptrs.end()); }
 };
 
 // ---------------------------------------------------------------- geometry
@@ -1459,6 +1461,10 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
       if (lanes) CU(cudaEventRecord(c->me_events[t], c->stream));
     }
     if (lanes) c->mv_ready = c->me_events[t];  // awaited inside, after the reference planes are up-sampled
+    if (t == 1 && c->upload_gops > 0)
+      // the decorrelate of level 1 reads the clip on this stream before it meets the ME lane
+      // (which is the one that waited GOP by GOP): the whole upload has to have landed
+      CU(cudaStreamWaitEvent(c->stream, c->upload_events[c->upload_gops - 1], 0));
     {
       const int rc = mc_level(c, 1, even, in_stride, odd, in_stride, lv.motion, n, X, Y, bs, p->block_overlaping, sr,
                               p->subpixel_accuracy, p->always_B, nullptr, lv.high, fb, &lv.types,
@@ -1603,17 +1609,19 @@ int qsvc_resident_synthesize(qsvc_ctx *c, const qsvc_analyze_params *p) {
     for (int j = 1; j < t; j++) sr = std::min(sr * 2, 128);
     uint8_t *dst;  // low_{t-1}: 2n+1 frames, even_t at even positions, odd_t at odd positions
     c->cur_level = t;
-    TRY(pool_alloc(c, (size_t)fb * (2 * n + 1), (void **)&dst));
+    Scratch guard(c);  // an error below gives the block back to the pool
+    TRY(guard.get((size_t)fb * (2 * n + 1), (void **)&dst));
+    if (t - 1 >= 1 && c->levels[t - 1].n_pairs != 2 * n)
+      return fail(QSVC_EINVAL, "level %d has %d pairs, expected %d", t - 1, c->levels[t - 1].n_pairs, 2 * n);
     TRY(update_level(c, 1, lv.low, fb, lv.high, fb, lv.motion, lv.types.c_str(), n, X, Y,
                      lv.block_size, p->update_factor, dst, 2 * fb));
     TRY(mc_level(c, 0, dst, 2 * fb, lv.high, fb, lv.motion, n, X, Y, lv.block_size,
                  p->block_overlaping, sr, p->subpixel_accuracy, 1, lv.types.c_str(), dst + fb, 2 * fb,
                  nullptr, nullptr, nullptr));
+    guard.detach(dst);
     if (t - 1 >= 1) {
       pool_free(c, c->levels[t - 1].low);
       c->levels[t - 1].low = dst;
-      if (c->levels[t - 1].n_pairs != 2 * n)
-        return fail(QSVC_EINVAL, "level %d has %d pairs, expected %d", t - 1, c->levels[t - 1].n_pairs, 2 * n);
     } else {
       pool_free(c, c->low0);
       c->low0 = dst;
