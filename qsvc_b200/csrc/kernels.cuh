@@ -226,6 +226,9 @@ struct MarchParams {
   int bs_shift, nstrips, nsegs, seg_p;  // filled by the launcher
 };
 void launch_mc_march(const Launch &L, MarchParams q, int npairs);
+// same contract, banded shared-memory pipeline (kernels_mctile.cu); a in {1, 2}, (bs << a) % 16 == 0
+bool mc_tile_supported(int a, int bsa, int X);
+void launch_mc_tile(const Launch &L, MarchParams q, int npairs);
 
 void launch_tail_state(const Launch &L, const uint8_t *P, long long plane_stride, int pitch,
                        uint8_t *Pnext, int Ya, int Xa, int cy, int first_comp, int ncomp);
