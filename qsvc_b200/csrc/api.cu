@@ -87,7 +87,7 @@ struct qsvc_ctx {
   int cur_level = 0;  // temporal level of the running resident analysis / synthesis
   int tma_mode = 1;  // 0: plain loads in the sub-pixel fast path (env QSVC_TMA=0)
   int mc_mode = 0;  // same three values for the decorrelate / correlate path
-  int mc_kernel = 1;  // byte-plane path: 1 banded shared-memory pipeline (k_mc_tile), 0 register march (k_mc_march); env QSVC_MC_KERNEL
+  int mc_kernel = 0;  // byte-plane path: 0 register march (k_mc_march, default: faster), 1 banded shared-memory pipeline (k_mc_tile); env QSVC_MC_KERNEL
   int me_mode = 0;  // 0: automatic, 1: literal (materialised) path only, 2: fused path required
   size_t me_budget = (size_t)40 << 30;  // bytes of HBM for the ME image planes of one chunk
   // resident sequence

@@ -360,6 +360,10 @@ class Context:
             self._out_cache[key] = bufs
         outs = (LevelOut * TRLs)()
         types = {}
+        # update_factor == 0 (analyze.py's default): update is the identity, low_t == even_t, i.e.
+        # frames of the clip the caller already holds.  Only low_{TRLs-1} is downloaded (for symmetry
+        # with the files texture_compress.py:183-215 consumes); the lower levels are views of low0.
+        host_low = float(update_factor) == 0.0
         for s in sched:
             t = s["t"]
             types[t] = C.create_string_buffer(max(s["pairs"], 1))
@@ -367,18 +371,25 @@ class Context:
             outs[t].motion = _i16(bufs[f"motion_{t}"])
             outs[t].motion_filtered = _i16(bufs[f"motion_filtered_{t}"])
             outs[t].frame_types = C.cast(types[t], C.c_void_p)
-            outs[t].low = _u8(bufs[f"low_{t}"])
+            if not (host_low and t < TRLs - 1):
+                outs[t].low = _u8(bufs[f"low_{t}"])
         p = self._params(X, Y, TRLs, block_size, search_range, subpixel_accuracy, update_factor,
                          always_B, block_overlaping, border_size, block_size_min, first_global)
         check(self._L.qsvc_analyze(self._h, C.byref(p), _u8(low0), low0.shape[0], outs))
         self._geom = (X, Y, low0.shape[0])
         out = {}
+        self.last_d2h_bytes = 0
         for s in sched:
             t = s["t"]
             for name in ("high", "motion", "motion_filtered", "low"):
+                if name == "low" and host_low and t < TRLs - 1:
+                    out[f"low_{t}"] = low0[:: 2 ** t]  # even_t: every 2^t-th frame of the input clip
+                    continue
                 a = bufs[f"{name}_{t}"]
+                self.last_d2h_bytes += a.nbytes
                 out[f"{name}_{t}"] = a if reuse_buffers else a.copy()
             out[f"frame_types_{t}"] = types[t].raw[: s["pairs"]]
+            self.last_d2h_bytes += s["pairs"]
         return out
 
     def synthesize(self, subbands, X, Y, GOPs, TRLs, block_size=16, search_range=4,
