@@ -8,9 +8,11 @@ motion_estimate -> decorrelate -> update) of one synthetic clip per GPU.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
                   [--workload cfg3|cfg2|cfg1|cfg4]
 
-N > 1: launched under torchrun, one rank per GPU; whole GOPs are sharded (each
-rank analyses its own clip of the named shape: weak scaling, no data-path
-collective); NCCL is used only for the barrier and the max-over-ranks time.
+N > 1: launched under torchrun, one rank per GPU.  The job is ONE clip of N times the workload's
+GOPs, GOP-sharded (qsvc_b200/shard.py): every rank analyses its GOP range, the prediction tail of
+pictures whose height is not a multiple of the block size is handed from shard to shard, and the
+end-to-end leg gathers every rank's results into one set of sub-band files in the reference's layout
+(weak scaling; NCCL carries the barrier, the max-over-ranks time and the point-to-point tail state).
 """
 from __future__ import annotations
 
@@ -250,6 +252,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -291,9 +294,11 @@ def main():
         print(json.dumps(line))
         return 0
 
+    import zlib
+
     import torch
     import torch.distributed as dist
-    from qsvc_b200 import yuv
+    from qsvc_b200 import shard, yuv
     from qsvc_b200.mctf import Context, level_schedule
 
     if not torch.cuda.is_available():
@@ -310,40 +315,60 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # one clip per rank (different seed per rank: independent GOP shards)
-    clip = yuv.synthetic_clip(w["X"], w["Y"], frames, SEEDS[wname] + 1000 * rank,
-                              max_shift=min(48, 3 * w["sr"]))
+    X, Y, GOPs, T, bs = w["X"], w["Y"], w["GOPs"], w["TRLs"], w["bs"]
+    # ONE long clip of world * GOPs GOPs, GOP-sharded: rank r takes GOPs [r*GOPs, (r+1)*GOPs), i.e. frames
+    # [r*(frames-1), (r+1)*(frames-1)] inclusive.  The long clip is the seeded base clip played
+    # forwards and backwards in turn, so that neighbouring shards agree on the frame they share and every
+    # rank can build its shard without the others'.  Weak scaling: the per-GPU work is fixed.
+    base = yuv.synthetic_clip(X, Y, frames, SEEDS[wname], max_shift=min(48, 3 * w["sr"]))
+    clip = base if rank % 2 == 0 else base[::-1]
     pinned = torch.empty(clip.shape, dtype=torch.uint8).pin_memory()
     pinned.numpy()[...] = clip
     clip_pinned = pinned.numpy()
+    if world > 1:
+        cfg["sharding"] = (f"one clip of {world * GOPs} GOPs ({world * (frames - 1) + 1} frames), whole GOPs per GPU "
+                           f"({GOPs} each), no data-path collective; the prediction tail of the {Y}-line picture "
+                           "is handed from shard to shard GPU to GPU (NCCL point-to-point, once per level)"
+                           if Y % bs else
+                           f"one clip of {world * GOPs} GOPs, whole GOPs per GPU ({GOPs} each), no collective")
 
     ctx = Context(local_rank)
-    kw = dict(TRLs=w["TRLs"], block_size=w["bs"], search_range=w["sr"], subpixel_accuracy=w["a"],
-              update_factor=0.0, always_B=w["always_B"], block_size_min=w["bs"])
-    sched = level_schedule(w["GOPs"], w["TRLs"], w["bs"], w["sr"], w["bs"])
+    kw = dict(TRLs=T, block_size=bs, search_range=w["sr"], subpixel_accuracy=w["a"],
+              update_factor=0.0, always_B=w["always_B"], block_size_min=bs)
+    sched = level_schedule(GOPs, T, bs, w["sr"], bs)
+    ranges = shard.partition(world * GOPs, world)
+    relay = shard.TailRelay(rank, ranges) if shard.needs_tail_exchange(Y, bs, world) else None
+    if relay is not None:
+        ctx.set_tail_exchange(relay, device=relay.device)
+    first_global = rank == 0
 
     # ---- device-resident throughput: inputs already in HBM when the timed region starts
-    ctx.resident_load(clip_pinned, w["X"], w["Y"])
+    ctx.resident_load(clip_pinned, X, Y)
     sampler = ClockSampler(local_rank)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
-        ctx.resident_analyze(**kw)
+        ctx.resident_analyze(first_global=first_global, **kw)
     barrier()
     l0 = ctx.launches
     t_a = time.time()
     ctx.timer_start()
     for _ in range(args.steps):
-        ctx.resident_analyze(**kw)
+        ctx.resident_analyze(first_global=first_global, **kw)
     ms = ctx.timer_stop()
     barrier()
     clocks = sampler.stop(t_a, time.time())
     launches = ctx.launches - l0
+    # checksums of the resident results: the end-to-end leg below must reproduce them
+    crc_res = {}
+    for s_ in sched:
+        got = ctx.resident_fetch(s_["t"], s_["pairs"], s_["block_size"], want=("high", "motion"))
+        crc_res[s_["t"]] = (zlib.crc32(got["high"]), zlib.crc32(got["motion"]))
     # per-class device times: separate, untimed steps (two events per launch perturb the step), with the
     # two compute lanes serialised so that every kernel is timed alone
     ctx.set_overlap(False)
     ctx.profile_enable(True)
     for _ in range(args.steps):
-        ctx.resident_analyze(**kw)
+        ctx.resident_analyze(first_global=first_global, **kw)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
     ctx.set_overlap(True)
@@ -354,19 +379,61 @@ def main():
     ms_per_step = ms_max / args.steps
     value = world * frames / (ms_per_step * 1e-3)
 
-    # ---- end to end through the public API with host buffers (H2D + analysis + D2H)
+    # ---- end to end through the public API with host buffers (H2D + analysis + D2H + gather)
     fb = clip.shape[1]
-    outs = {}
     h2d = clip.nbytes
-    d2h = 0
-    for s in sched:
-        n, b = s["pairs"], s["block_size"]
-        d2h += n * fb + 2 * n * 8 * (w["Y"] // b) * (w["X"] // b) + n
-        d2h += (n + 1) * fb
+    # host-side gather (north_star): every rank's results land in ONE set of sub-band files laid out like
+    # the reference's (high_t, motion_t, motion_filtered_t of all GOPs in order; low_{T-1}).  The files are
+    # a shared mapping that every rank page-locks, and qsvc_analyze's device-to-host copies write the rank's
+    # slices in place: the gather costs no extra pass over the data.
+    gather_note, out_bufs, maps = "single GPU: results in pinned buffers of the context", None, {}
+    if world > 1:
+        shm_dir = f"/dev/shm/qsvc_bench_{os.environ.get('MASTER_PORT', '0')}"
+        need = 0
+        shapes = {}
+        for s_ in sched:
+            t_, n, b = s_["t"], s_["pairs"], s_["block_size"]
+            shapes[f"high_{t_}"] = ((world * n, fb), np.uint8)
+            shapes[f"motion_{t_}"] = ((world * n, 4, Y // b, X // b), np.int16)
+            shapes[f"motion_filtered_{t_}"] = ((world * n, 4, Y // b, X // b), np.int16)
+        shapes[f"low_{T-1}"] = ((world * GOPs + 1, fb), np.uint8)
+        need = sum(int(np.prod(sh)) * np.dtype(dt).itemsize for sh, dt in shapes.values())
+        ok = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            try:
+                os.makedirs(shm_dir, exist_ok=True)
+                st = os.statvfs(shm_dir)
+                if st.f_bavail * st.f_frsize > need + (64 << 20):
+                    for k, (sh, dt) in shapes.items():
+                        np.memmap(os.path.join(shm_dir, k), dtype=dt, mode="w+", shape=sh).flush()
+                    ok[0] = 1
+            except OSError:
+                pass
+        dist.broadcast(ok, 0)
+        if int(ok.item()):
+            registered = True
+            for k, (sh, dt) in shapes.items():
+                maps[k] = np.memmap(os.path.join(shm_dir, k), dtype=dt, mode="r+", shape=sh)
+                registered = ctx.host_register(maps[k]) and registered
+            out_bufs = {}
+            for s_ in sched:
+                t_, n = s_["t"], s_["pairs"]
+                for name in ("high", "motion", "motion_filtered"):
+                    out_bufs[f"{name}_{t_}"] = maps[f"{name}_{t_}"][rank * n:(rank + 1) * n]
+            out_bufs[f"low_{T-1}"] = maps[f"low_{T-1}"][rank * GOPs:rank * GOPs + GOPs + 1]
+            gather_note = (f"rank slices written in place into shared sub-band files in {shm_dir} "
+                           f"({need / 1e6:.0f} MB, reference file layout), "
+                           + ("page-locked by every rank: the device-to-host copies are the gather"
+                              if registered else "NOT page-locked (cudaHostRegister refused): pageable copies"))
+        else:
+            gather_note = f"no shared memory for the gathered files ({need / 1e6:.0f} MB needed): results stay per rank"
+
+    outs = {}
 
     def e2e_step():
         # the public API call: host clip in, host sub-bands out (pinned buffers reused)
-        outs.update(ctx.analyze(clip_pinned, w["X"], w["Y"], w["GOPs"], reuse_buffers=True, **kw))
+        outs.update(ctx.analyze(clip_pinned, X, Y, GOPs, reuse_buffers=True, first_global=first_global,
+                                out=out_bufs, **kw))
 
     e2e_step()
     barrier()
@@ -375,12 +442,34 @@ def main():
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    d2h = int(ctx.last_d2h_bytes)
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * frames * args.steps / float(t.item())
+    e2e_ok = all((zlib.crc32(outs[f"high_{t_}"]), zlib.crc32(outs[f"motion_{t_}"])) == crc_res[t_] for t_ in crc_res)
+    tt = torch.tensor([1 if e2e_ok else 0], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+    e2e_ok = bool(int(tt.item()))
+
+    # sharded == whole (N = 2: the 2-shard clip once more on rank 0 alone, untimed, against the gathered files)
+    sharded_equals_whole = None
+    if world == 2 and maps:
+        barrier()
+        if rank == 0:
+            ctx.set_tail_exchange(None)
+            long_clip = np.concatenate([base, base[::-1][1:]], axis=0)
+            whole = ctx.analyze(long_clip, X, Y, 2 * GOPs, first_global=True, **kw)
+            sharded_equals_whole = all(np.array_equal(whole[k], maps[k]) for k in maps)
+            del whole, long_clip
+        barrier()
+    if relay is not None:
+        ctx.set_tail_exchange(None)
 
     if rank != 0:
+        for m_ in maps.values():
+            ctx.host_unregister(m_)
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -399,14 +488,21 @@ def main():
     cls_n = {k: v[1] // steps for k, v in prof.items()}
     sad = sad_ops_total(w)
     search_ms = cls_ms["search"] + cls_ms.get("search_exact", 0.0)
-    me_ms = cls_ms["search"] + cls_ms["dwt_rows"] + cls_ms["dwt_cols"]  # upper bound: includes MC's DWT
-    mc_ms = cls_ms["predict"] + cls_ms["residue"] + cls_ms["update"]
+    # everything motion estimation launches: pyramid DWT, byte planes and their interpolations, searches
+    # (the image class also holds decorrelate's reference up-sampling: an upper bound for ME)
+    me_all_ms = search_ms + cls_ms["dwt_rows"] + cls_ms["dwt_cols"] + cls_ms["image"]
     dominant = max(cls_ms, key=cls_ms.get)
     rooflines = {
         "me_search": {"bound": "int-sad", "achieved": sad / (search_ms * 1e-3) / 1e9 if search_ms else None,
                       "peak": u8_peak / 1e9, "peak_i32": i32_peak / 1e9, "unit": "G SAD-op/s",
                       "frac": (sad / (search_ms * 1e-3)) / u8_peak if search_ms else None,
-                      "note": "peak = measured __vsadu4 issue rate x4 (qsvc_int_peak); algorithmic SAD-ops of SURVEY 8(d)"},
+                      "frac_all_me_kernels": (sad / (me_all_ms * 1e-3)) / u8_peak if me_all_ms else None,
+                      "frac_whole_step": (sad / (ms_per_step * 1e-3)) / u8_peak,
+                      "note": "peak = measured VABSDIFF4.U8.ACC issue rate x4 (qsvc_int_peak: >95% of the loop's "
+                              "instructions are SADs, profiles/r2_int_peak_sass.txt; 64 thread-instr/clk/SM, "
+                              "profiles/r2_pipe_probe.txt); algorithmic SAD-ops of SURVEY 8(d); frac = against the "
+                              "time in the search kernels, frac_all_me_kernels = against search + pyramid DWT + "
+                              "plane preparation, frac_whole_step = against the whole analysis step"},
         "mc_path": {"bound": "hbm", "achieved": mc_bytes_total(w) / (ms_per_step * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s",
                     "frac": mc_bytes_total(w) / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
@@ -415,20 +511,22 @@ def main():
     # the dominant kernel class of the step, against the bound that applies to it
     share = cls_ms[dominant] / max(1e-9, sum(cls_ms.values()))
     pairs_total = sum(p // 2 for p in _pictures_per_level(w))
-    fbytes = w["X"] * w["Y"] * 3 // 2
-    field_bytes = 8 * (w["Y"] // w["bs"]) * (w["X"] // w["bs"])
+    fbytes = X * Y * 3 // 2
+    field_bytes = 8 * (Y // bs) * (X // bs)
     # algorithmic bytes of decorrelate per pair = two reference frames and the odd
     # frame read, the high frame written, one motion field read and written (12.4 MB at 1080p)
     mc_pair_bytes = 4 * fbytes + 2 * field_bytes
     kernel_of = {"residue": "k_mc_march", "image": "k_upsample_chain/k_upsample2x (+ plane loads, border fills)",
                  "predict": "k_predict_u8/k_tail_state", "dwt_rows": "k_dwt_rows", "dwt_cols": "k_dwt_cols"}
     # dram__bytes_read+write per step of the class's kernels, from the committed ncu capture
-    # (profiles/r1_ncu.json, written by profiles/summarize.py; cfg3 only)
+    # (profiles/r*_ncu.json, written by profiles/summarize.py; cfg3 only)
     traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu.json"))).get("dram_bytes_per_step", {})
-    except (OSError, ValueError):
-        pass
+    for tag in ("r2", "r1"):
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_ncu.json"))).get("dram_bytes_per_step", {})
+            break
+        except (OSError, ValueError):
+            pass
     if dominant in ("search", "search_exact"):
         roof = {"bound": "int-sad", "kernel": "k_subpel_tma/k_subpel_strip/k_subpel_exact/k_search16",
                 "achieved": rooflines["me_search"]["achieved"], "peak": u8_peak / 1e9, "unit": "G SAD-op/s",
@@ -445,7 +543,7 @@ def main():
                         "summed device time (CUDA events on the library's stream); traffic = ncu dram bytes "
                         "of the same launches.  k_mc_march reads the up-sampled reference planes "
                         "(16x the frame bytes) and is bound by instruction issue, not by HBM: see "
-                        "profiles/r1_summary.md"}
+                        "profiles/r2_summary.md"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -460,6 +558,13 @@ def main():
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
                    "sample": f"failed: {e}"}
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        try:
+            extras = measure_extras(ctx, w, wname, clip_pinned, outs, kw)
+        except Exception as e:  # noqa: BLE001
+            extras = {"failed": f"{type(e).__name__}: {e}"}
+
     line = {
         "metric": "1080p MCTF analysis frames/s" if wname == "cfg3" else f"{wname} MCTF analysis frames/s",
         "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -467,7 +572,11 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": dict(cfg, host=numa_note), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h)},
+                "d2h_bytes_per_step": int(d2h), "matches_resident_run": e2e_ok, "gather": gather_note,
+                "sharded_equals_whole": sharded_equals_whole,
+                "note": "update_factor 0: low_t of the lower levels are frames of the input clip and are not "
+                        "copied back (views of the caller's array); high_t, both motion fields, frame types "
+                        "and low_{T-1} are"},
         "gpu_launches": int(launches),
         "roofline": roof, "rooflines": rooflines,
         "me_sad_gops": sad / (ms_per_step * 1e-3) / 1e9,
@@ -476,11 +585,98 @@ def main():
                           "(every kernel alone); the timed steps overlap motion estimation of level t+1 with the "
                           "decorrelate of level t, so the classes sum to more than ms_per_step",
         "cpu_baseline": cpu,
+        "extras": extras,
     }
     print(json.dumps(line))
+    for m_ in maps.values():
+        ctx.host_unregister(m_)
     if world > 1:
+        try:
+            import shutil
+            shutil.rmtree(f"/dev/shm/qsvc_bench_{os.environ.get('MASTER_PORT', '0')}", ignore_errors=True)
+        except OSError:
+            pass
         dist.destroy_process_group()
     return 0
+
+
+def measure_extras(ctx, w, wname, clip_pinned, outs, kw):
+    """What production runs besides the headline (not part of `value`): the workload with the codec's
+    default --update_factor=0.25 (compress.py:101), its synthesis (north_star config 5: the decode path),
+    and the cfg2 analyze + synthesize round trip (config 2).  A few steps each."""
+    import zlib
+    from qsvc_b200 import yuv
+    X, Y, GOPs, T, bs = w["X"], w["Y"], w["GOPs"], w["TRLs"], w["bs"]
+    frames = n_frames(w)
+    ex = {}
+    # (a) update_factor 0.25, device-resident
+    kw25 = dict(kw, update_factor=0.25)
+    ctx.resident_load(clip_pinned, X, Y)
+    ctx.resident_analyze(**kw25)
+    ctx.timer_start()
+    for _ in range(2):
+        ctx.resident_analyze(**kw25)
+    ms = ctx.timer_stop() / 2
+    ctx.profile_enable(True)
+    ctx.resident_analyze(**kw25)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    ex["update_factor_0.25"] = {"ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3),
+                                "kernel_ms": {k: v[0] for k, v in prof.items()},
+                                "dominant": max(prof, key=lambda k: prof[k][0]),
+                                "note": "device-resident analysis, one lane (level t+1 needs low_t)"}
+    # (b) synthesis of the headline analysis (update_factor 0), host sub-bands in, host frames out
+    sub = {f"low_{T-1}": outs[f"low_{T-1}"]}
+    for t in range(1, T):
+        sub[f"high_{t}"], sub[f"motion_{t}"] = outs[f"high_{t}"], outs[f"motion_filtered_{t}"]
+        sub[f"frame_types_{t}"] = outs[f"frame_types_{t}"]
+    rec = ctx.host_alloc(clip_pinned.shape)
+    skw = dict(block_size=bs, search_range=w["sr"], subpixel_accuracy=w["a"], update_factor=0.0)
+    ctx.synthesize(sub, X, Y, GOPs, T, out=rec, **skw)
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(2):
+        ctx.synthesize(sub, X, Y, GOPs, T, out=rec, **skw)
+        dev_ms += ctx.resident_stats()["total_ms"]
+    e2e_s = (time.perf_counter() - t0) / 2
+    G = 2 ** (T - 1)
+    ex["synthesis"] = {"e2e_frames_per_s": frames / e2e_s, "device_ms_per_step": dev_ms / 2,
+                       "device_frames_per_s": frames / (dev_ms / 2 * 1e-3),
+                       "even_frames_of_top_level_restored": bool(np.array_equal(rec[0::G], clip_pinned[0::G])),
+                       "crc32_low_0": zlib.crc32(rec),
+                       "note": "inverse MCTF (un_update, correlate, merge per level) of the sub-bands the e2e leg "
+                               "produced; e2e = pushes + synthesis + download of low_0"}
+    # (c) cfg2 round trip
+    if wname != "cfg2":
+        w2 = WORKLOADS["cfg2"]
+        c2 = yuv.synthetic_clip(w2["X"], w2["Y"], n_frames(w2), SEEDS["cfg2"], max_shift=min(48, 3 * w2["sr"]))
+        k2 = dict(TRLs=w2["TRLs"], block_size=w2["bs"], search_range=w2["sr"], subpixel_accuracy=w2["a"],
+                  update_factor=0.0, always_B=w2["always_B"], block_size_min=w2["bs"])
+        p2 = ctx.host_alloc(c2.shape)
+        p2[...] = c2
+        r2 = ctx.host_alloc(c2.shape)
+
+        def trip():
+            o = ctx.analyze(p2, w2["X"], w2["Y"], w2["GOPs"], reuse_buffers=True, **k2)
+            sb = {f"low_{w2['TRLs']-1}": o[f"low_{w2['TRLs']-1}"]}
+            for t in range(1, w2["TRLs"]):
+                sb[f"high_{t}"], sb[f"motion_{t}"] = o[f"high_{t}"], o[f"motion_filtered_{t}"]
+                sb[f"frame_types_{t}"] = o[f"frame_types_{t}"]
+            ta = time.perf_counter()
+            ctx.synthesize(sb, w2["X"], w2["Y"], w2["GOPs"], w2["TRLs"], block_size=w2["bs"],
+                           search_range=w2["sr"], subpixel_accuracy=w2["a"], update_factor=0.0, out=r2)
+            return time.perf_counter() - ta
+
+        trip()
+        t0 = time.perf_counter()
+        syn = sum(trip() for _ in range(3))
+        tot = time.perf_counter() - t0
+        f2 = n_frames(w2)
+        ex["cfg2_round_trip"] = {"analyze_frames_per_s": 3 * f2 / (tot - syn), "synthesize_frames_per_s": 3 * f2 / syn,
+                                 "round_trip_frames_per_s": 3 * f2 / tot,
+                                 "psnr_db": float(10 * np.log10(255.0 ** 2 / max(1e-9, ((r2.astype(np.float64) - c2) ** 2).mean()))),
+                                 "note": "704x576, 65 frames, GOP 16, half-pel: analyze + synthesize through host buffers"}
+    return ex
 
 
 if __name__ == "__main__":

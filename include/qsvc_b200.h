@@ -91,6 +91,12 @@ int qsvc_set_mc_mode(qsvc_ctx *ctx, int mode);
 typedef int (*qsvc_tail_fn)(void *user, int level, int synthesis, int phase, uint8_t *state,
                             long long bytes);
 int qsvc_set_tail_exchange(qsvc_ctx *ctx, qsvc_tail_fn fn, void *user);
+/* Same exchange with `state` a DEVICE pointer (memory of the context's GPU, valid for the duration
+ * of the call): the shards hand the state over GPU to GPU (NCCL point-to-point, peer copies)
+ * without the host hop.  The context's stream is idle when the callback runs; the callback's own
+ * transfers must have completed (phase 0) / may still read the buffer only until it returns
+ * (phase 1). */
+int qsvc_set_tail_exchange_device(qsvc_ctx *ctx, qsvc_tail_fn fn, void *user);
 
 /* GOP shards with update_factor != 0: the frame two neighbouring shards
  * share receives the left shard's NEXT update first and the right shard's PREV update second
@@ -214,6 +220,10 @@ int qsvc_analyze(qsvc_ctx *ctx, const qsvc_analyze_params *params, const uint8_t
                  int n_frames, const qsvc_level_out *outs);
 void *qsvc_host_alloc(size_t bytes);
 void qsvc_host_free(void *ptr);
+/* Page-locks caller-owned host memory (e.g. a shared mapping several GOP shards write their
+ * slices of the gathered sub-band files into) so that qsvc_analyze's copies land there directly. */
+int qsvc_host_register(void *ptr, size_t bytes);
+int qsvc_host_unregister(void *ptr);
 
 /* Inverse: un_update -> correlate -> merge per level from TRLs-1 down to 1
  * (synthesize.py:95-153, synthesize_step.py:84-143), frames resident in HBM.

@@ -58,6 +58,7 @@ SIGNATURES = {
     "qsvc_timer_stop": (_i, [C.c_void_p, C.POINTER(C.c_float)]),
     "qsvc_synchronize": (_i, [C.c_void_p]),
     "qsvc_set_tail_exchange": (_i, [C.c_void_p, TAIL_FN, C.c_void_p]),
+    "qsvc_set_tail_exchange_device": (_i, [C.c_void_p, TAIL_FN, C.c_void_p]),
     "qsvc_set_boundary_exchange": (_i, [C.c_void_p, BOUNDARY_FN, C.c_void_p]),
     "qsvc_set_overlap": (_i, [C.c_void_p, _i]),
     "qsvc_set_me_mode": (_i, [C.c_void_p, _i]),
@@ -80,6 +81,8 @@ SIGNATURES = {
     "qsvc_analyze": (_i, [C.c_void_p, C.POINTER(AnalyzeParams), u8p, _i, C.POINTER(LevelOut)]),
     "qsvc_host_alloc": (C.c_void_p, [C.c_size_t]),
     "qsvc_host_free": (None, [C.c_void_p]),
+    "qsvc_host_register": (_i, [C.c_void_p, C.c_size_t]),
+    "qsvc_host_unregister": (_i, [C.c_void_p]),
     "qsvc_resident_fetch": (_i, [C.c_void_p, _i, u8p, i16p, i16p, C.c_void_p, u8p]),
     "qsvc_resident_stats": (_i, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float)]),

@@ -82,6 +82,7 @@ struct qsvc_ctx {
   std::vector<PoolBlock> pool;
   qsvc_tail_fn tail_fn = nullptr;  // GOP-shard exchange of the prediction tail state (A.2.6)
   void *tail_user = nullptr;
+  int tail_on_device = 0;  // the callback's `state` is a device pointer (qsvc_set_tail_exchange_device)
   qsvc_boundary_fn boundary_fn = nullptr;  // GOP-shard exchange of the boundary frame (update_factor != 0)
   void *boundary_user = nullptr;
   int cur_level = 0;  // temporal level of the running resident analysis / synthesis
@@ -1077,6 +1078,32 @@ int qsvc_set_tail_exchange(qsvc_ctx *c, qsvc_tail_fn fn, void *user) {
   if (!c) return fail(QSVC_EINVAL, "null context");
   c->tail_fn = fn;
   c->tail_user = user;
+  c->tail_on_device = 0;
+  return QSVC_OK;
+}
+int qsvc_set_tail_exchange_device(qsvc_ctx *c, qsvc_tail_fn fn, void *user) {
+  if (!c) return fail(QSVC_EINVAL, "null context");
+  c->tail_fn = fn;
+  c->tail_user = user;
+  c->tail_on_device = fn ? 1 : 0;
+  return QSVC_OK;
+}
+int qsvc_host_register(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(QSVC_EINVAL, "bad arguments");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(QSVC_ECUDA, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  }
+  return QSVC_OK;
+}
+int qsvc_host_unregister(void *ptr) {
+  if (!ptr) return QSVC_OK;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(QSVC_ECUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+  }
   return QSVC_OK;
 }
 int qsvc_set_boundary_exchange(qsvc_ctx *c, qsvc_boundary_fn fn, void *user) {

@@ -122,11 +122,14 @@ class Context:
         """0 automatic, 1 literal decorrelate/correlate path, 2 byte-plane fused path or fail."""
         check(self._L.qsvc_set_mc_mode(self._h, mode))
 
-    def set_tail_exchange(self, fn=None):
+    def set_tail_exchange(self, fn=None, device=False):
         """Installs (or clears) the GOP-shard exchange of the prediction tail state
         (include/qsvc_b200.h): fn(level, synthesis, phase, state) with
         `state` a writable uint8 array; phase 0 returns True after filling in the left
-        neighbour's state, phase 1 receives the state to pass to the right."""
+        neighbour's state, phase 1 receives the state to pass to the right.
+        device=True: `state` is instead a (device pointer, bytes) tuple of the context's GPU
+        (qsvc_set_tail_exchange_device): the state travels GPU to GPU without a host hop."""
+        setter = self._L.qsvc_set_tail_exchange_device if device else self._L.qsvc_set_tail_exchange
         if fn is None:
             self._tail_cb = None
             check(self._L.qsvc_set_tail_exchange(self._h, _lib.TAIL_FN(), None))
@@ -134,7 +137,10 @@ class Context:
 
         def cb(_user, level, synthesis, phase, state, nbytes):
             try:
-                a = np.ctypeslib.as_array(state, shape=(int(nbytes),))
+                if device:
+                    a = (C.cast(state, C.c_void_p).value, int(nbytes))
+                else:
+                    a = np.ctypeslib.as_array(state, shape=(int(nbytes),))
                 r = fn(int(level), int(synthesis), int(phase), a)
                 return 1 if r else 0
             except Exception:  # noqa: BLE001 -- must not propagate through the C frame
@@ -143,7 +149,7 @@ class Context:
                 return -1
 
         self._tail_cb = _lib.TAIL_FN(cb)  # keep the trampoline alive
-        check(self._L.qsvc_set_tail_exchange(self._h, self._tail_cb, None))
+        check(setter(self._h, self._tail_cb, None))
 
     def set_boundary_exchange(self, fn=None):
         """Installs (or clears) the GOP-shard exchange of the shared boundary frame for
@@ -334,20 +340,44 @@ class Context:
         buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
+    def host_register(self, array):
+        """Page-locks caller-owned host memory (qsvc_host_register), e.g. a shared mapping that
+        several GOP shards write their slices of the gathered files into; False if the driver
+        refuses (the copies then go through staging, slower but correct)."""
+        rc = self._L.qsvc_host_register(C.c_void_p(array.ctypes.data), array.nbytes)
+        return rc == _lib.QSVC_OK
+
+    def host_unregister(self, array):
+        self._L.qsvc_host_unregister(C.c_void_p(array.ctypes.data))
+
     def analyze(self, low0, X, Y, GOPs, TRLs, block_size=32, search_range=4, subpixel_accuracy=0,
                 update_factor=0.0, always_B=0, block_overlaping=0, border_size=0,
-                block_size_min=32, first_global=True, reuse_buffers=False):
+                block_size_min=32, first_global=True, reuse_buffers=False, out=None):
         """analyze.py equivalent on arrays: returns {file name: payload}.
 
         One C-ABI call (qsvc_analyze): upload, every temporal level, and the download of
         each level's results overlapped with the next level's compute.  With
         reuse_buffers=True the returned arrays are views of pinned buffers owned by the
-        context and are overwritten by the next call with the same geometry."""
+        context and are overwritten by the next call with the same geometry.  `out`: caller-
+        provided contiguous arrays per file name (high_t, motion_t, motion_filtered_t, low_t) that
+        receive the results directly, e.g. slices of a page-locked gathered file (host_register)."""
         low0 = np.ascontiguousarray(low0, np.uint8)
         assert low0.shape == (GOPs * gop_size(TRLs) + 1, frame_bytes(X, Y))
         sched = level_schedule(GOPs, TRLs, block_size, search_range, block_size_min)
         key = (X, Y, GOPs, TRLs, block_size, block_size_min)
-        bufs = self._out_cache.get(key)
+        bufs = self._out_cache.get(key) if out is None else out
+        if out is not None:
+            reuse_buffers = True
+            for s in sched:
+                t, n, b = s["t"], s["pairs"], s["block_size"]
+                want = {f"high_{t}": ((n, fb := frame_bytes(X, Y)), np.uint8),
+                        f"motion_{t}": ((n, 4, Y // b, X // b), np.int16),
+                        f"motion_filtered_{t}": ((n, 4, Y // b, X // b), np.int16)}
+                if not (float(update_factor) == 0.0 and t < TRLs - 1):
+                    want[f"low_{t}"] = ((n + 1, fb), np.uint8)
+                for k, (shape, dt) in want.items():
+                    a = out[k]
+                    assert a.shape == shape and a.dtype == dt and a.flags["C_CONTIGUOUS"], k
         if bufs is None:
             bufs = {}
             fb = frame_bytes(X, Y)
@@ -393,9 +423,10 @@ class Context:
         return out
 
     def synthesize(self, subbands, X, Y, GOPs, TRLs, block_size=16, search_range=4,
-                   subpixel_accuracy=0, update_factor=0.25, block_overlaping=0):
+                   subpixel_accuracy=0, update_factor=0.25, block_overlaping=0, out=None):
         """synthesize.py equivalent on arrays.  `subbands` maps high_t, motion_t,
-        frame_types_t (t = 1..TRLs-1) and low_{TRLs-1} to their payloads.  Returns low_0."""
+        frame_types_t (t = 1..TRLs-1) and low_{TRLs-1} to their payloads.  Returns low_0
+        (written into `out`, e.g. a host_alloc'd array, when given)."""
         fb = frame_bytes(X, Y)
         for t in range(TRLs - 1, 0, -1):
             high = np.ascontiguousarray(subbands[f"high_{t}"], np.uint8)
@@ -414,7 +445,9 @@ class Context:
                          block_overlaping, 0, block_size)
         check(self._L.qsvc_resident_synthesize(self._h, C.byref(p)))
         frames = GOPs * gop_size(TRLs) + 1
-        out = np.zeros((frames, fb), np.uint8)
+        if out is None:
+            out = np.zeros((frames, fb), np.uint8)
+        assert out.shape == (frames, fb) and out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"]
         check(self._L.qsvc_resident_fetch_low0(self._h, _u8(out), frames))
         self._geom = (X, Y, frames)
         return out

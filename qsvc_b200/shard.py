@@ -93,9 +93,18 @@ class LocalTailRelay:
         return False
 
 
+class _DeviceBytes:
+    """A device buffer of the context seen through __cuda_array_interface__ (torch.as_tensor)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
 class TailRelay:
     """Tail-state hand-over over torch.distributed point-to-point messages: receive from
-    the nearest rank on the left that has work, send to the nearest on the right."""
+    the nearest rank on the left that has work, send to the nearest on the right.  With the
+    NCCL backend the state stays on the devices (`device` = True: the library hands out a
+    device buffer, qsvc_set_tail_exchange_device); with gloo it travels through host arrays."""
 
     def __init__(self, rank, ranges):
         import torch.distributed as dist
@@ -103,21 +112,34 @@ class TailRelay:
         i = active.index(rank)
         self.left = active[i - 1] if i > 0 else None
         self.right = active[i + 1] if i + 1 < len(active) else None
-        self.cuda = dist.get_backend() == "nccl"
+        self.device = dist.get_backend() == "nccl"
 
     def __call__(self, level, synthesis, phase, state):
         import torch
         import torch.distributed as dist
+        if self.device:
+            ptr, nbytes = state
+            if phase == 0:
+                if self.left is None:
+                    return False
+                t = torch.as_tensor(_DeviceBytes(ptr, nbytes), device="cuda")
+                dist.recv(t, src=self.left)
+                torch.cuda.current_stream().synchronize()
+                return True
+            if self.right is not None:
+                t = torch.as_tensor(_DeviceBytes(ptr, nbytes), device="cuda")
+                dist.send(t, dst=self.right)
+                torch.cuda.current_stream().synchronize()
+            return False
         if phase == 0:
             if self.left is None:
                 return False
-            t = torch.empty(state.shape[0], dtype=torch.uint8, device="cuda" if self.cuda else "cpu")
+            t = torch.empty(state.shape[0], dtype=torch.uint8)
             dist.recv(t, src=self.left)
-            state[:] = t.cpu().numpy()
+            state[:] = t.numpy()
             return True
         if self.right is not None:
-            t = torch.from_numpy(state.copy())
-            dist.send(t.cuda() if self.cuda else t, dst=self.right)
+            dist.send(torch.from_numpy(state.copy()), dst=self.right)
         return False
 
 
@@ -202,7 +224,7 @@ class ThreadBoundaryRelay:
 
 def analyze_shard(ctx, low0, X, Y, GOPs, TRLs, rank, world, block_size=32, search_range=4,
                   subpixel_accuracy=0, update_factor=0.0, always_B=0, block_size_min=32,
-                  allow_inexact=False, analyze_fn=None, relay=None, boundary_relay=None):
+                  allow_inexact=False, analyze_fn=None, relay=None, boundary_relay=None, **analyze_kw):
     """Runs this rank's GOP range.  `analyze_fn(frames, n_gops, first_global)` defaults
     to ctx.analyze (the CUDA path); tests may inject another callable.  `relay` is the
     tail-state hand-over (default: TailRelay when the geometry needs one)."""
@@ -219,11 +241,14 @@ def analyze_shard(ctx, low0, X, Y, GOPs, TRLs, rank, world, block_size=32, searc
         def analyze_fn(fr, n_gops, first_global):
             return ctx.analyze(fr, X, Y, n_gops, TRLs, block_size, search_range,
                                subpixel_accuracy, update_factor, always_B,
-                               block_size_min=block_size_min, first_global=first_global)
+                               block_size_min=block_size_min, first_global=first_global, **analyze_kw)
     if relay is None and needs_tail_exchange(Y, block_size, world) and ctx is not None:
         relay = TailRelay(rank, ranges)
     if relay is not None and ctx is not None:
-        ctx.set_tail_exchange(relay)
+        if getattr(relay, "device", False):
+            ctx.set_tail_exchange(relay, device=True)
+        else:
+            ctx.set_tail_exchange(relay)
     if boundary_relay is not None and ctx is not None:
         ctx.set_boundary_exchange(boundary_relay)
     try:
@@ -294,7 +319,10 @@ def synthesize_shard(ctx, subbands, X, Y, GOPs, TRLs, rank, world, block_size=16
     if relay is None and needs_tail_exchange(Y, block_size, world) and ctx is not None:
         relay = TailRelay(rank, ranges)
     if relay is not None and ctx is not None:
-        ctx.set_tail_exchange(relay)
+        if getattr(relay, "device", False):
+            ctx.set_tail_exchange(relay, device=True)
+        else:
+            ctx.set_tail_exchange(relay)
     if boundary_relay is not None and ctx is not None:
         ctx.set_boundary_exchange(boundary_relay)
     try:
