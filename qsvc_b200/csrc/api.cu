@@ -836,6 +836,66 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
     CU(cudaGetLastError());
     return QSVC_OK;
   }
+  if (c->boundary_fn == nullptr || n_pairs == 0) {
+    // Frames are independent of each other (frame k takes pair k-1's NEXT update, then pair k's PREV
+    // update): every frame of the level goes through the same handful of launches, chunked by HBM.
+    const int tiles_x = (X + 15) / 16, tiles_y = (Y + 15) / 16, ntiles = tiles_x * tiles_y, CAP = 32;
+    char *d_types;
+    int *d_cnt, *d_list, *d_reach;
+    TRY(s.get((size_t)n_pairs + 16, (void **)&d_types));
+    TRY(s.get((size_t)2 * n_pairs * ntiles * sizeof(int), (void **)&d_cnt));
+    TRY(s.get((size_t)2 * n_pairs * ntiles * CAP * sizeof(int), (void **)&d_list));
+    TRY(s.get((size_t)2 * n_pairs * sizeof(int) + 16, (void **)&d_reach));
+    CU(cudaMemcpyAsync(d_types, types, (size_t)n_pairs, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(d_cnt, 0, (size_t)2 * n_pairs * ntiles * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(d_reach, 0, (size_t)2 * n_pairs * sizeof(int), c->stream));
+    UpdateBatchParams q;
+    q.high = high;
+    q.high_stride = high_stride;
+    q.mv = mv;
+    q.types = d_types;
+    q.cnt = d_cnt;
+    q.list = d_list;
+    q.reach = d_reach;
+    q.cap = CAP;
+    q.n_pairs = n_pairs;
+    q.BY = BY;
+    q.BX = BX;
+    q.bs = bs;
+    q.Y = Y;
+    q.X = X;
+    q.tiles_x = tiles_x;
+    q.tiles_y = tiles_y;
+    q.uf = uf;
+    q.inverse = inverse;
+    q.slots_per_comp = 0;
+    q.frame0 = 0;
+    q.ref = ref.p;
+    launch_update_bin(Lh, q);
+    const size_t per_frame = (size_t)3 * Y * ((X + 7) & ~7) * sizeof(short);
+    int max_frames = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pairs + 1, (c->me_budget / 4) / per_frame));
+    for (int k0 = 0; k0 <= n_pairs; k0 += max_frames) {
+      const int m = std::min(max_frames, n_pairs + 1 - k0);
+      Scratch sc(c);
+      PlaneAlloc planes;
+      TRY(alloc_dense_planes(sc, 3 * m, Y, X, &planes));
+      CU(cudaMemsetAsync(planes.raw, 0, planes.bytes, c->stream));
+      launch_load_u8(Lh, planes.p, 0, m, in, in_stride, 0, k0, 1, Y, X);
+      launch_load_u8(Lh, planes.p, m, m, in, in_stride, comp_offset(X, Y, 1), k0, 1, Y / 2, X / 2);
+      launch_load_u8(Lh, planes.p, 2 * m, m, in, in_stride, comp_offset(X, Y, 2), k0, 1, Y / 2, X / 2);
+      dwt_synthesize(Lh, planes.p, m, 2 * m, Y, X, 1);
+      q.ref = planes.p;
+      q.slots_per_comp = m;
+      q.frame0 = k0;
+      launch_update_batch(Lh, q, m);
+      dwt_analyze(Lh, planes.p, m, 2 * m, Y, X, 1);
+      launch_store_u8(Lh, planes.p, 0, m, out, out_stride, 0, k0, 1, Y, X);
+      launch_store_u8(Lh, planes.p, m, m, out, out_stride, comp_offset(X, Y, 1), k0, 1, Y / 2, X / 2);
+      launch_store_u8(Lh, planes.p, 2 * m, m, out, out_stride, comp_offset(X, Y, 2), k0, 1, Y / 2, X / 2);
+    }
+    CU(cudaGetLastError());
+    return QSVC_OK;
+  }
   // GOP shards: the frame shared with a neighbour receives the left
   // shard's NEXT update first and the right shard's PREV update second, and every contribution
   // is clamped and truncated, so the int16 planes travel from left to right between the two

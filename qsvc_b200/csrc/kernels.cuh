@@ -108,6 +108,7 @@ struct SubpelParams {
   int debug;             // env QSVC_SUBPEL_DEBUG: 1 = fast blocks go to the strip kernel, 2 = strip blocks go to the exact generator
   int npairs, pair_group;  // TMA kernel: block order (launch_subpel fills these)
   int check_tiles;       // 0: every tile of every slot is known to hold bytes (tile_bad not consulted)
+  unsigned kmul[3];      // 2^24, 2^16, 2^8: funnel shifts as multiplies on the FMA pipe (filled by launch_subpel)
   alignas(64) unsigned char tm_p[128];
   alignas(64) unsigned char tm_r[128];
 };
@@ -184,6 +185,22 @@ struct UpdateParams {
   const int *reach;     // device: max |vector component| of this direction (launch_mv_reach)
 };
 void launch_update(const Launch &L, const UpdateParams &q);
+// all frames [frame0, frame0 + nframes) of a level in one launch (frames are independent of each other)
+struct UpdateBatchParams {
+  Plane ref;                 // dense luma-sized planes: slot = c * slots_per_comp + (frame - frame0)
+  int slots_per_comp, frame0;
+  const uint8_t *high;       // high frames of the level's pairs (I420); residue = high - 128
+  long long high_stride;
+  const short *mv;           // the level's fields
+  const char *types;         // device: frame types of the pairs
+  int *cnt, *list, *reach;   // per (pair, direction): per tile block count and ids; largest |vector component|
+  int cap;                   // list capacity per tile
+  int n_pairs, BY, BX, bs, Y, X, tiles_x, tiles_y;
+  float uf;
+  int inverse;
+};
+void launch_update_bin(const Launch &L, const UpdateBatchParams &q);  // cnt and reach zeroed by the caller
+void launch_update_batch(const Launch &L, const UpdateBatchParams &q, int nframes);
 void launch_mv_reach(const Launch &L, const short *mv, int n, int *out);
 // residue plane: top-left h x w = high - 128 (rest untouched)
 void launch_load_residue(const Launch &L, Plane dst, int slot, const uint8_t *src, int h, int w);

@@ -432,6 +432,162 @@ __global__ void __launch_bounds__(256) k_update(UpdateParams q) {
   if (active) *target = cur;
 }
 
+// ---- update / un_update for all frames of a level at once ----
+// Frames are independent of each other: frame k first takes the NEXT contributions of pair k-1,
+// then the PREV contributions of pair k (update.cpp:506-656).  Instead of scanning every block
+// that could reach a tile, the blocks are binned first: k_update_bin appends each block of each
+// (pair, direction) to the 16x16 target tiles its displaced, edge-clipped footprint touches
+// (bounded lists; a tile whose list overflows -- blocks folded onto a picture edge -- falls back
+// to the scan), and k_update_batch sorts a tile's short list back into raster order (the order
+// is part of the result) and replays the contributions per target pixel.
+__global__ void __launch_bounds__(256) k_update_bin(UpdateBatchParams q) {
+  const int pd = blockIdx.y, pair = pd >> 1, dir = pd & 1;  // dir 0: PREV, 1: NEXT
+  if (q.types[pair] != 'B') return;
+  const long long plane = (long long)q.BY * q.BX;
+  const short *mvx = q.mv + (long long)pair * 4 * plane + (long long)(dir ? MV_NEXT_X : MV_PREV_X) * plane;
+  const short *mvy = mvx + plane;
+  const int ntiles = q.tiles_x * q.tiles_y;
+  int *cnt = q.cnt + (long long)pd * ntiles;
+  int *list = q.list + (long long)pd * ntiles * q.cap;
+  int reach = 0;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < (int)plane; b += gridDim.x * blockDim.x) {
+    const int by = b / q.BX, bx = b - by * q.BX;
+    const int vy = mvy[b], vx = mvx[b];
+    reach = max(reach, max(abs(vy), abs(vx)));
+    const int oy = by * q.bs + vy, ox = bx * q.bs + vx;
+    const int fy0 = iclamp(oy, 0, q.Y - 1) >> 4, fy1 = iclamp(oy + q.bs - 1, 0, q.Y - 1) >> 4;
+    const int fx0 = iclamp(ox, 0, q.X - 1) >> 4, fx1 = iclamp(ox + q.bs - 1, 0, q.X - 1) >> 4;
+    for (int ty = fy0; ty <= fy1; ty++)
+      for (int tx = fx0; tx <= fx1; tx++) {
+        const int t = ty * q.tiles_x + tx;
+        const int pos = atomicAdd(&cnt[t], 1);
+        if (pos < q.cap) list[(long long)t * q.cap + pos] = b;
+      }
+  }
+  reach = __reduce_max_sync(0xffffffffu, reach);
+  if ((threadIdx.x & 31) == 0 && reach > 0) atomicMax(&q.reach[pd], reach);
+}
+
+__global__ void __launch_bounds__(256) k_update_batch(UpdateBatchParams q) {
+  __shared__ int s_list[256];
+  __shared__ int s_sorted[256];
+  __shared__ int s_count;
+  __shared__ int s_warp[8];
+  const int frame = q.frame0 + blockIdx.z / 3, c = blockIdx.z % 3;
+  const int tx = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int ty = blockIdx.y * 16 + (threadIdx.x >> 4);
+  const int tile_x0 = blockIdx.x * 16, tile_y0 = blockIdx.y * 16;
+  const int tile_x1 = min(tile_x0 + 15, q.X - 1), tile_y1 = min(tile_y0 + 15, q.Y - 1);
+  const bool active = tx < q.X && ty < q.Y;
+  const long long plane = (long long)q.BY * q.BX;
+  const int ntiles = q.tiles_x * q.tiles_y, tile = blockIdx.y * q.tiles_x + blockIdx.x;
+  short *target = active ? q.ref.row(c * q.slots_per_comp + (frame - q.frame0), ty) + tx : nullptr;
+  short cur = active ? *target : (short)0;
+  const int cw = c ? q.X >> 1 : q.X, ch = c ? q.Y >> 1 : q.Y;  // residue[1|2] only exists in its top-left quarter
+  const long long coff = c == 0 ? 0 : (long long)q.X * q.Y + (long long)(c - 1) * (q.X / 2) * (q.Y / 2);
+
+  for (int pass = 0; pass < 2; pass++) {
+    // frame k first receives pair k-1's NEXT update, then pair k's PREV update
+    const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
+    if (pair < 0 || pair >= q.n_pairs || q.types[pair] != 'B') continue;  // uniform per CTA
+    const int pd = pair * 2 + dir;
+    const short *mvx = q.mv + (long long)pair * 4 * plane + (long long)(dir ? MV_NEXT_X : MV_PREV_X) * plane;
+    const short *mvy = mvx + plane;
+    const uint8_t *res = q.high + (long long)pair * q.high_stride + coff;
+    const int total = q.cnt[(long long)pd * ntiles + tile];
+    auto replay = [&](int cnt, const int *ids) {
+      if (!active) return;
+      for (int k = 0; k < cnt; k++) {
+        const int bb = ids[k];
+        const int byy = bb / q.BX, bxx = bb - byy * q.BX;
+        const int oy = byy * q.bs + mvy[bb], ox = bxx * q.bs + mvx[bb];
+        // source rows y in [0,bs) with clip(oy + y) == ty, in increasing order
+        // (edge targets collect every source that clip() folds onto them)
+        int ylo = (ty == 0) ? 0 : ty - oy, yhi = (ty == q.Y - 1) ? q.bs - 1 : ty - oy;
+        int xlo = (tx == 0) ? 0 : tx - ox, xhi = (tx == q.X - 1) ? q.bs - 1 : tx - ox;
+        ylo = max(ylo, 0), yhi = min(yhi, q.bs - 1);
+        xlo = max(xlo, 0), xhi = min(xhi, q.bs - 1);
+        for (int y = ylo; y <= yhi; y++) {
+          const int ry = byy * q.bs + y;
+          for (int x = xlo; x <= xhi; x++) {
+            const int rx = bxx * q.bs + x;
+            const int r = (ry < ch && rx < cw) ? (int)res[(long long)ry * cw + rx] - 128 : 0;
+            const float prod = __fmul_rn((float)r, q.uf);
+            float aux = (float)cur;
+            aux = q.inverse ? __fsub_rn(aux, prod) : __fadd_rn(aux, prod);
+            if (aux > 255.f) aux = 255.f;
+            else if (aux < 0.f) aux = 0.f;
+            cur = (short)aux;  // float -> short truncation toward zero
+          }
+        }
+      }
+    };
+    if (total <= q.cap) {
+      // short list: rank sort back into raster order (ids are distinct)
+      __syncthreads();
+      if ((int)threadIdx.x < total) s_list[threadIdx.x] = q.list[((long long)pd * ntiles + tile) * q.cap + threadIdx.x];
+      __syncthreads();
+      if ((int)threadIdx.x < total) {
+        const int me = s_list[threadIdx.x];
+        int rank = 0;
+        for (int k = 0; k < total; k++) rank += s_list[k] < me;
+        s_sorted[rank] = me;
+      }
+      __syncthreads();
+      replay(total, s_sorted);
+    } else {
+      // overflow: ordered scan of every block within reach of the tile (blocks folded onto an edge)
+      const int reach = q.reach[pd];
+      const int by_lo = max(0, (tile_y0 - reach - q.bs + 1 + (q.bs - 1) * (tile_y0 - reach - q.bs + 1 > 0)) / q.bs);
+      const int by_hi = min(q.BY - 1, (tile_y1 + reach) / q.bs);
+      const int bx_lo = max(0, (tile_x0 - reach - q.bs + 1 + (q.bs - 1) * (tile_x0 - reach - q.bs + 1 > 0)) / q.bs);
+      const int bx_hi = min(q.BX - 1, (tile_x1 + reach) / q.bs);
+      const int nbw = max(bx_hi - bx_lo + 1, 0), nbh = max(by_hi - by_lo + 1, 0);
+      const int nblocks = nbw * nbh;
+      for (int base = 0; base < nblocks; base += 256) {
+        __syncthreads();
+        int b = -1;
+        bool hit = false;
+        if (base + (int)threadIdx.x < nblocks) {
+          const int k = base + threadIdx.x;
+          const int cby = by_lo + k / nbw, cbx = bx_lo + k % nbw;
+          b = cby * q.BX + cbx;
+          const int oy = cby * q.bs + mvy[b], ox = cbx * q.bs + mvx[b];
+          const int fy0 = iclamp(oy, 0, q.Y - 1), fy1 = iclamp(oy + q.bs - 1, 0, q.Y - 1);
+          const int fx0 = iclamp(ox, 0, q.X - 1), fx1 = iclamp(ox + q.bs - 1, 0, q.X - 1);
+          hit = fy0 <= tile_y1 && fy1 >= tile_y0 && fx0 <= tile_x1 && fx1 >= tile_x0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int prefix = 0;
+        for (int w = 0; w < warp; w++) prefix += s_warp[w];
+        if (hit) s_list[prefix + __popc(m & ((1u << lane) - 1))] = b;
+        if (threadIdx.x == 255) s_count = prefix + __popc(m);
+        __syncthreads();
+        replay(s_count, s_list);
+      }
+    }
+  }
+  if (active) *target = cur;
+}
+
+void launch_update_bin(const Launch &L, const UpdateBatchParams &q) {
+  if (q.n_pairs <= 0) return;
+  ProfScope ps_(L, KC_UPDATE);
+  const int plane = q.BY * q.BX;
+  k_update_bin<<<dim3((plane + 255) / 256, 2 * q.n_pairs), 256, 0, L.stream>>>(q);
+  COUNT(L);
+}
+
+void launch_update_batch(const Launch &L, const UpdateBatchParams &q, int nframes) {
+  if (nframes <= 0) return;
+  ProfScope ps_(L, KC_UPDATE);
+  k_update_batch<<<dim3(q.tiles_x, q.tiles_y, nframes * 3), 256, 0, L.stream>>>(q);
+  COUNT(L);
+}
+
 // largest |component| of the two planes (x, y) of one direction of a field
 __global__ void k_mv_reach(const short *__restrict__ mv, int n, int *out) {
   __shared__ int s_max;

@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -495,32 +496,44 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, in
 // offset of window column 0 inside word 0 of the row pointer (0 when the window was staged
 // aligned); EX adds the sums of a second byte window (the "excess" of int16 samples outside
 // [0,255], see k_subpel_strip) under the same shifts.
-template <int S>
-__device__ __forceinline__ void shifted3(const unsigned *rw, unsigned sh[3]) {
+// Funnel shift right by 8 * k bits.  FM: as two integer multiplies by a power of two the compiler
+// cannot see (IMAD.HI + IMAD on the FMA pipe) instead of one SHF on the ALU pipe, which the SAD
+// instructions saturate (profiles/r2_pipe_probe.txt: VABSDIFF4 and SHF share a pipe, IMAD does not).
+template <bool FM>
+__device__ __forceinline__ unsigned fshr(unsigned lo, unsigned hi, int k, const unsigned *km) {
+  if (!FM) return __funnelshift_r(lo, hi, 8 * k);
+  unsigned t, r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(lo), "r"(km[k - 1]));
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "r"(km[k - 1]), "r"(t));
+  return r;
+}
+
+template <int S, bool FM>
+__device__ __forceinline__ void shifted3(const unsigned *rw, unsigned sh[3], const unsigned *km) {
   const unsigned w0 = rw[0], w1 = rw[1];
   if (S == 0) {
     sh[0] = w0;
-    sh[1] = __funnelshift_r(w0, w1, 8);
-    sh[2] = __funnelshift_r(w0, w1, 16);
+    sh[1] = fshr<FM>(w0, w1, 1, km);
+    sh[2] = fshr<FM>(w0, w1, 2, km);
   } else if (S == 1) {
-    sh[0] = __funnelshift_r(w0, w1, 8);
-    sh[1] = __funnelshift_r(w0, w1, 16);
-    sh[2] = __funnelshift_r(w0, w1, 24);
+    sh[0] = fshr<FM>(w0, w1, 1, km);
+    sh[1] = fshr<FM>(w0, w1, 2, km);
+    sh[2] = fshr<FM>(w0, w1, 3, km);
   } else if (S == 2) {
-    sh[0] = __funnelshift_r(w0, w1, 16);
-    sh[1] = __funnelshift_r(w0, w1, 24);
+    sh[0] = fshr<FM>(w0, w1, 2, km);
+    sh[1] = fshr<FM>(w0, w1, 3, km);
     sh[2] = w1;
   } else {
     const unsigned w2 = rw[2];
-    sh[0] = __funnelshift_r(w0, w1, 24);
+    sh[0] = fshr<FM>(w0, w1, 3, km);
     sh[1] = w1;
-    sh[2] = __funnelshift_r(w1, w2, 8);
+    sh[2] = fshr<FM>(w1, w2, 1, km);
   }
 }
 
-template <int W, int S, bool EX>
+template <int W, int S, bool EX, bool FM = false>
 __device__ __forceinline__ void sad_rows(const unsigned *P4, const unsigned *R4, const unsigned *E4, int rp,
-                                         unsigned acc[9]) {
+                                         unsigned acc[9], const unsigned *km = nullptr) {
   constexpr int WPR = W / 4, RPT = W / 4;
   unsigned p[RPT];
 #pragma unroll
@@ -528,8 +541,8 @@ __device__ __forceinline__ void sad_rows(const unsigned *P4, const unsigned *R4,
 #pragma unroll
   for (int rr = 0; rr < RPT + 2; rr++) {
     unsigned sh[3], se[3];
-    shifted3<S>(R4 + rr * rp, sh);
-    if (EX) shifted3<S>(E4 + rr * rp, se);
+    shifted3<S, FM>(R4 + rr * rp, sh, km);
+    if (EX) shifted3<S, FM>(E4 + rr * rp, se, km);
 #pragma unroll
     for (int wdy = -1; wdy <= 1; wdy++) {
       const int r = rr - 1 - wdy;  // block row paired with window row rr under vertical shift wdy
@@ -606,7 +619,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar) {
   }
 }
 
-template <int W, int ALIGNED>
+template <int W, int ALIGNED, bool FM>
 __global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __grid_constant__ CUtensorMap tmP,
                                                       const __grid_constant__ CUtensorMap tmR) {
   constexpr int WPR = W / 4, RPT = W / 4, NT = 2 * W;
@@ -714,13 +727,13 @@ __global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __gr
   if (ALIGNED) {
     R4 += (wx[d] & 15) >> 2;
     switch (wx[d] & 3) {
-      case 0: sad_rows<W, 0, false>(P4, R4, nullptr, TP, acc); break;
-      case 1: sad_rows<W, 1, false>(P4, R4, nullptr, TP, acc); break;
-      case 2: sad_rows<W, 2, false>(P4, R4, nullptr, TP, acc); break;
-      default: sad_rows<W, 3, false>(P4, R4, nullptr, TP, acc); break;
+      case 0: sad_rows<W, 0, false, FM>(P4, R4, nullptr, TP, acc, q.kmul); break;
+      case 1: sad_rows<W, 1, false, FM>(P4, R4, nullptr, TP, acc, q.kmul); break;
+      case 2: sad_rows<W, 2, false, FM>(P4, R4, nullptr, TP, acc, q.kmul); break;
+      default: sad_rows<W, 3, false, FM>(P4, R4, nullptr, TP, acc, q.kmul); break;
     }
   } else {
-    sad_rows<W, 0, false>(P4, R4, nullptr, TP, acc);
+    sad_rows<W, 0, false, FM>(P4, R4, nullptr, TP, acc, q.kmul);
   }
   short c[4] = {(short)blk[0], (short)blk[1], (short)blk[2], (short)blk[3]};
   sad_finish<W>(q, acc, s_err, pair, by, bx, c);
@@ -1301,8 +1314,14 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
     const dim3 ggrid(q.BX, q.BY * qg.pair_group, (npairs + qg.pair_group - 1) / qg.pair_group);
     const CUtensorMap &tp = *reinterpret_cast<const CUtensorMap *>(q.tm_p);
     const CUtensorMap &tr = *reinterpret_cast<const CUtensorMap *>(q.tm_r);
-    if (q.use_tma)
-      k_subpel_tma<W, 1><<<ggrid, 2 * W, 0, L.stream>>>(qg, tp, tr);
+    static const int fm = getenv("QSVC_SUBPEL_FM") ? atoi(getenv("QSVC_SUBPEL_FM")) : 1;
+    qg.kmul[0] = 1u << 24;  // >> 8
+    qg.kmul[1] = 1u << 16;  // >> 16
+    qg.kmul[2] = 1u << 8;   // >> 24
+    if (q.use_tma && fm)
+      k_subpel_tma<W, 1, true><<<ggrid, 2 * W, 0, L.stream>>>(qg, tp, tr);
+    else if (q.use_tma)
+      k_subpel_tma<W, 1, false><<<ggrid, 2 * W, 0, L.stream>>>(qg, tp, tr);
     else
       k_subpel_fast<W><<<grid, (W / 4) * (W / 8), 0, L.stream>>>(q);
     COUNT(L);
