@@ -1314,7 +1314,7 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
     const dim3 ggrid(q.BX, q.BY * qg.pair_group, (npairs + qg.pair_group - 1) / qg.pair_group);
     const CUtensorMap &tp = *reinterpret_cast<const CUtensorMap *>(q.tm_p);
     const CUtensorMap &tr = *reinterpret_cast<const CUtensorMap *>(q.tm_r);
-    static const int fm = getenv("QSVC_SUBPEL_FM") ? atoi(getenv("QSVC_SUBPEL_FM")) : 1;
+    static const int fm = getenv("QSVC_SUBPEL_FM") ? atoi(getenv("QSVC_SUBPEL_FM")) : 0;  // measured: no gain (the kernel is not ALU-bound)
     qg.kmul[0] = 1u << 24;  // >> 8
     qg.kmul[1] = 1u << 16;  // >> 16
     qg.kmul[2] = 1u << 8;   // >> 24
