@@ -67,9 +67,55 @@ def make(name, X, Y, GOPs, TRLs, bs, sr, a, uf, always_B, flat, seed, ov=0):
         shutil.rmtree(d)
 
 
+def make_level_lists():
+    """synthesize.py:127-133 with geometry lists that vary per temporal level (SURVEY.md 8f
+    rank 4, expand.py:150-209): the reference runs one synthesize_step per level with that
+    level's own --pixels_in_x / --pixels_in_y / --block_size / --subpixel_accuracy, and the
+    files handed from level to level are simply re-read with the next level's geometry.  The
+    fixture keeps the frame bytes and the block count equal across levels (64x48 <-> 48x64,
+    block 16 -> 12 blocks either way) so that every file has a consistent length; inputs are
+    the analysis outputs of the 'quarter_pel' geometry plus level-specific vectors."""
+    rng = np.random.default_rng(77)
+    GOPs, TRLs, bs, sr, uf = 1, 4, 16, 4, 0.25
+    geo = {3: (64, 48, 1), 2: (48, 64, 0), 1: (64, 48, 2)}  # per temporal level: X, Y, subpixel_accuracy
+    fb = 64 * 48 * 3 // 2
+    d = tempfile.mkdtemp(prefix="golden_")
+    try:
+        out = {"params": np.array([GOPs, TRLs, bs, sr], np.int64), "update_factor": np.array([uf], np.float64),
+               "geometry": np.array([[t, *geo[t]] for t in (3, 2, 1)], np.int64)}
+        pictures = {1: 9, 2: 5, 3: 3}
+        clip = yuv.synthetic_clip(64, 48, 9, 31, max_shift=8)
+        out["low_3"] = clip[:2]
+        yuv.write_frames(os.path.join(d, "low_3"), out["low_3"])
+        for t in (1, 2, 3):
+            n = pictures[t] // 2
+            X, Y, a = geo[t]
+            high = (128 + rng.integers(-20, 21, size=(n, fb))).astype(np.uint8)
+            mv = rng.integers(-(sr << a), (sr << a) + 1, size=(n, 4, Y // bs, X // bs)).astype(np.int16)
+            types = np.frombuffer(b"B" * n, np.uint8).copy()
+            if t == 1:
+                types[1] = ord("I")
+            out[f"high_{t}"], out[f"motion_{t}"], out[f"frame_types_{t}"] = high, mv, types
+            yuv.write_frames(os.path.join(d, f"high_{t}"), high)
+            yuv.write_motion(os.path.join(d, f"motion_{t}"), mv)
+            open(os.path.join(d, f"frame_types_{t}"), "wb").write(types.tobytes())
+        search = {1: sr, 2: 2 * sr, 3: 4 * sr}
+        for t in (3, 2, 1):
+            X, Y, a = geo[t]
+            run_ref.synthesize_step(d, t, pictures[t], X, Y, bs, search[t], a, uf)
+        out["syn_low_0"] = yuv.read_frames(os.path.join(d, "low_0"), 64, 48)
+        path = os.path.join(ROOT, "tests", "golden", "level_lists.npz")
+        np.savez_compressed(path, **out)
+        print("level_lists", os.path.getsize(path), "bytes")
+    finally:
+        shutil.rmtree(d)
+
+
 if __name__ == "__main__":
     assert run_ref.build(), "oracle/_ref is missing and /root/reference is not available"
     only = sys.argv[1:]
     for k, v in CASES.items():
         if not only or k in only:
             make(k, *v)
+    if not only or "level_lists" in only:
+        make_level_lists()

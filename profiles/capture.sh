@@ -21,4 +21,7 @@ ncu --metrics $M --clock-control none -s $N -c $N --csv --log-file $OUT/metrics_
 ncu --set full --clock-control none --import-source on \
     -k regex:"k_mc_march|k_subpel_tma|k_subpel_strip|k_upsample_chain" -c 8 -o $OUT/top_$TAG -f \
     python profiles/run_step.py cfg3 1 > $OUT/ncu_top_$TAG.log 2>&1
+# the dominant kernel (its launches come after the eight above)
+ncu --set full --clock-control none --import-source on -k regex:k_mc_march -c 2 -o $OUT/march_$TAG -f \
+    python profiles/run_step.py cfg3 1 > $OUT/ncu_march_$TAG.log 2>&1
 ls -la $OUT/*_$TAG.*

@@ -88,6 +88,7 @@ struct qsvc_ctx {
   int cur_level = 0;  // temporal level of the running resident analysis / synthesis
   int tma_mode = 1;  // 0: plain loads in the sub-pixel fast path (env QSVC_TMA=0)
   int mc_mode = 0;  // same three values for the decorrelate / correlate path
+  int mc_ring = 1;  // byte-plane path: materialised border ring around the reference planes (env QSVC_MC_RING=0: off)
   int mc_kernel = 0;  // byte-plane path: 0 register march (k_mc_march, default: faster), 1 banded shared-memory pipeline (k_mc_tile); env QSVC_MC_KERNEL
   int me_mode = 0;  // 0: automatic, 1: literal (materialised) path only, 2: fused path required
   size_t me_budget = (size_t)40 << 30;  // bytes of HBM for the ME image planes of one chunk
@@ -1051,6 +1052,7 @@ qsvc_ctx *qsvc_create(int device) {
   if (const char *e = getenv("QSVC_MC_MODE")) c->mc_mode = atoi(e);
   if (const char *e = getenv("QSVC_TMA")) c->tma_mode = atoi(e);
   if (const char *e = getenv("QSVC_MC_KERNEL")) c->mc_kernel = atoi(e);
+  if (const char *e = getenv("QSVC_MC_RING")) c->mc_ring = atoi(e);
   if (const char *e = getenv("QSVC_OVERLAP")) c->overlap = atoi(e);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->me_budget = std::min<size_t>((size_t)64 << 30, free_b / 3);

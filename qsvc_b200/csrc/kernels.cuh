@@ -240,6 +240,7 @@ struct MarchParams {
   const char *types;         // synthesis: frame types (device)
   int X, Y, a, synth;
   int BY, BX, bsa, Ya, Xa, ba, padh, cy;
+  int ring;                  // samples of materialised border around every V plane (launch_fill_ring), 0: none
   int bs_shift, nstrips, nsegs, seg_p;  // filled by the launcher
 };
 void launch_mc_march(const Launch &L, MarchParams q, int npairs);
@@ -247,6 +248,9 @@ void launch_mc_march(const Launch &L, MarchParams q, int npairs);
 bool mc_tile_supported(int a, int bsa, int X);
 void launch_mc_tile(const Launch &L, MarchParams q, int npairs);
 
+// border ring of the reference's border rule around the interior of nplanes byte planes (U = interior origin)
+void launch_fill_ring(const Launch &L, uint8_t *U, long long plane_stride, int pitch, int nplanes, int Yd, int Xd,
+                      int ring, int b, int padh);
 void launch_tail_state(const Launch &L, const uint8_t *P, long long plane_stride, int pitch,
                        uint8_t *Pnext, int Ya, int Xa, int cy, int first_comp, int ncomp);
 void launch_copy_rows(const Launch &L, const uint8_t *src, uint8_t *dst, long long plane_stride,

@@ -38,6 +38,42 @@ __device__ __forceinline__ int bordered_ref_u8(const uint8_t *U, int pitch, int 
   return U[(long long)iclamp(y, 0, Yd - 1) * pitch + iclamp(x, 0, Xd - 1)];
 }
 
+// Materialises the reference's border rule (texture::alloc + fill_border, bordered_ref_u8) as a
+// ring of `ring` samples around the interior of every plane, so that displaced windows which
+// leave the picture by less than that are plain loads.  U = interior origin of plane 0.
+// One thread per ring cell: the top and bottom bands (full width), then the left and right bands.
+__global__ void __launch_bounds__(256) k_fill_ring(uint8_t *U, long long plane_stride, int pitch, int Yd, int Xd,
+                                                   int ring, int b, int padh) {
+  uint8_t *P = U + (long long)blockIdx.z * plane_stride;
+  const int W = Xd + 2 * ring;
+  const long long nA = 2LL * ring * W, nB = 2LL * ring * Yd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nA + nB; i += (long long)gridDim.x * blockDim.x) {
+    int y, x;
+    if (i < nA) {
+      const int r = (int)(i / W);
+      x = (int)(i - (long long)r * W) - ring;
+      y = r < ring ? r - ring : Yd + (r - ring);
+    } else {
+      const long long j = i - nA;
+      y = (int)(j / (2 * ring));
+      const int k = (int)(j - (long long)y * (2 * ring));
+      x = k < ring ? k - ring : Xd + (k - ring);
+    }
+    P[(long long)y * pitch + x] = (uint8_t)bordered_ref_u8(P, pitch, Yd, Xd, b, padh, y, x);
+  }
+}
+
+void launch_fill_ring(const Launch &L, uint8_t *U, long long plane_stride, int pitch, int nplanes, int Yd, int Xd,
+                      int ring, int b, int padh) {
+  if (nplanes <= 0 || ring <= 0) return;
+  const long long cells = 2LL * ring * (Xd + 2 * ring) + 2LL * ring * Yd;
+  int blocks = (int)((cells + 1023) / 1024);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope ps_(L, KC_IMG);
+  k_fill_ring<<<dim3(blocks, 1, nplanes), 256, 0, L.stream>>>(U, plane_stride, pitch, Yd, Xd, ring, b, padh);
+  COUNT(L);
+}
+
 __device__ __forceinline__ unsigned load_u32_unaligned(const uint8_t *p) {
   const uintptr_t a = (uintptr_t)p;
   const unsigned *w = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);

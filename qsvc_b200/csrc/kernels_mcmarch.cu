@@ -175,10 +175,13 @@ struct Marcher {
     }
     col0 = xs + mx0;
     col1 = xs + mx1;
-    xin0 = col0 >= 0 && col0 + 8 <= q.Xa;
-    xin1 = col1 >= 0 && col1 + 8 <= q.Xa;
+    // the planes carry a materialised border ring of q.ring samples (the reference's border rule,
+    // k_fill_ring): windows that stay inside it are plain loads
+    xin0 = col0 >= -q.ring && col0 + 8 <= q.Xa + q.ring;
+    xin1 = col1 >= -q.ring && col1 + 8 <= q.Xa + q.ring;
     const int y0 = by << q.bs_shift, y1 = min(y0 + q.bsa, q.cy) - 1;
-    const bool noclamp = y0 + my0 >= 0 && y1 + my0 < q.Ya && y0 + my1 >= 0 && y1 + my1 < q.Ya;
+    const bool noclamp = y0 + my0 >= -q.ring && y1 + my0 < q.Ya + q.ring && y0 + my1 >= -q.ring &&
+                         y1 + my1 < q.Ya + q.ring;
     fastrow = __all_sync(FULL, xin0 && xin1 && noclamp);
     const int o0 = my0 * q.v_pitch + col0, o1 = my1 * q.v_pitch + col1;  // pitch % 4 == 0
     sa = 8 * (o0 & 3);
@@ -190,9 +193,11 @@ struct Marcher {
   // One row, any case.  Columns inside the picture: V(y, x) = U[clamp(y)][x] (the border quirks
   // of texture::fill_border need x < 0 or x >= Xd); otherwise the closed-form border rule.
   __device__ __forceinline__ void fetch_row_general(int r, unsigned *a, unsigned *b) {
+    // columns inside the ring: rows beyond it repeat its outermost row (the border rule is constant
+    // along y there); otherwise the closed-form rule per sample
     if (xin0) {
-      const unsigned off = (unsigned)(min(max(r + my0, 0), q.Ya - 1) * q.v_pitch + col0);
-      const unsigned *a4 = reinterpret_cast<const unsigned *>(V0() + (off & ~3u));
+      const int off = min(max(r + my0, -q.ring), q.Ya + q.ring - 1) * q.v_pitch + col0;
+      const unsigned *a4 = reinterpret_cast<const unsigned *>(V0() + (off & ~3));
       a[0] = __ldg(a4);
       a[1] = __ldg(a4 + 1);
       a[2] = __ldg(a4 + 2);
@@ -203,8 +208,8 @@ struct Marcher {
       a[2] = 0;
     }
     if (xin1) {
-      const unsigned off = (unsigned)(min(max(r + my1, 0), q.Ya - 1) * q.v_pitch + col1);
-      const unsigned *b4 = reinterpret_cast<const unsigned *>(V1() + (off & ~3u));
+      const int off = min(max(r + my1, -q.ring), q.Ya + q.ring - 1) * q.v_pitch + col1;
+      const unsigned *b4 = reinterpret_cast<const unsigned *>(V1() + (off & ~3));
       b[0] = __ldg(b4);
       b[1] = __ldg(b4 + 1);
       b[2] = __ldg(b4 + 2);

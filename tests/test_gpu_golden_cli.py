@@ -149,3 +149,28 @@ def test_cli_synthesize_with_per_level_lists(tmp_path):
         low = np.empty((2 * odd.shape[0] + 1, even.shape[1]), np.uint8)
         low[0::2], low[1::2] = even, odd
     assert np.array_equal(yuv.read_frames(str(d / "low_0"), X, Y), low)
+
+
+def test_cli_synthesize_with_per_level_picture_sizes_matches_reference(tmp_path):
+    """Lists that vary in pixels_in_x / pixels_in_y AND subpixel_accuracy per temporal level
+    (synthesize.py:127-133 indexes block_size [(TRLs-1)-t], the others
+    [TRLs-t]) against the low_0 the unmodified reference tools produced for the same files
+    (tests/golden/level_lists.npz)."""
+    from golden_util import load_level_lists
+    g = load_level_lists()
+    T, d = g["TRLs"], tmp_path
+    for t in range(1, T):
+        yuv.write_frames(str(d / f"high_{t}"), g[f"high_{t}"])
+        yuv.write_motion(str(d / f"motion_{t}"), g[f"motion_{t}"])
+        (d / f"frame_types_{t}").write_bytes(bytes(g[f"frame_types_{t}"]))
+    yuv.write_frames(str(d / f"low_{T-1}"), g[f"low_{T-1}"])
+    xs, ys, acc = ["0"] * (T + 1), ["0"] * (T + 1), ["0"] * (T + 1)
+    for t, (X, Y, a) in g["geo"].items():
+        xs[T - t], ys[T - t], acc[T - t] = str(X), str(Y), str(a)
+    xs[0], ys[0] = xs[1], ys[1]
+    _mctf(["synthesize", f"--GOPs={g['GOPs']}", f"--TRLs={T}", f"--search_range={g['sr']}",
+           f"--block_size={','.join([str(g['bs'])] * T)}", f"--pixels_in_x={','.join(xs)}",
+           f"--pixels_in_y={','.join(ys)}", f"--subpixel_accuracy={','.join(acc)}",
+           f"--update_factor={g['uf']}"], str(d))
+    X1, Y1, _ = g["geo"][1]
+    assert np.array_equal(yuv.read_frames(str(d / "low_0"), X1, Y1), g["syn_low_0"])

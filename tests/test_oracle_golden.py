@@ -63,3 +63,22 @@ def test_dwt53_round_trip_and_layout():
     img = np.full((8, 8), 37, np.int16)
     a = orc.dwt53(img, 2)
     assert (a[:2, :2] == 37).all() and (a[4:, :] == 0).all() and (a[:, 4:] == 0).all()
+
+
+def test_oracle_synthesis_with_per_level_geometry_matches_reference():
+    """synthesize.py:127-133 with lists that vary per level: each level's
+    un_update / correlate run with that level's own picture size and sub-pixel accuracy, the
+    merged frames are re-read with the next level's geometry (fixture made by the unmodified
+    reference tools, oracle/make_golden.py make_level_lists)."""
+    from golden_util import load_level_lists
+    g = load_level_lists()
+    low, sr = g["low_3"], {1: g["sr"], 2: 2 * g["sr"], 3: 4 * g["sr"]}
+    for t in (3, 2, 1):
+        X, Y, a = g["geo"][t]
+        types = bytes(g[f"frame_types_{t}"])
+        low = low.reshape(-1, X * Y * 3 // 2)
+        even = orc.update(low, g[f"high_{t}"], g[f"motion_{t}"], types, X, Y, g["bs"], g["uf"], inverse=True)
+        odd, _ = orc.correlate(even, g[f"high_{t}"], g[f"motion_{t}"], types, X, Y, g["bs"], sr[t], a)
+        low = np.empty((2 * odd.shape[0] + 1, even.shape[1]), np.uint8)
+        low[0::2], low[1::2] = even, odd
+    assert np.array_equal(low, g["syn_low_0"])
