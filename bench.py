@@ -253,6 +253,9 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every GPU takes the workload's GOPs of an N times longer clip (default); "
+                         "strong = the workload's own GOPs are divided among the GPUs (north_star config 4)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -315,32 +318,48 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    X, Y, GOPs, T, bs = w["X"], w["Y"], w["GOPs"], w["TRLs"], w["bs"]
-    # ONE long clip of world * GOPs GOPs, GOP-sharded: rank r takes GOPs [r*GOPs, (r+1)*GOPs), i.e. frames
-    # [r*(frames-1), (r+1)*(frames-1)] inclusive.  The long clip is the seeded base clip played
-    # forwards and backwards in turn, so that neighbouring shards agree on the frame they share and every
-    # rank can build its shard without the others'.  Weak scaling: the per-GPU work is fixed.
+    X, Y, T, bs = w["X"], w["Y"], w["TRLs"], w["bs"]
+    G = 2 ** (T - 1)
+    strong = args.scaling == "strong" and world > 1
+    # ONE clip, GOP-sharded: rank r takes GOPs [g0, g1), i.e. frames [g0*G, g1*G] inclusive.
+    # weak (default): the job is world times the workload's GOPs, every rank takes the workload's count.  The
+    #   long clip is the seeded base clip played forwards and backwards in turn, so that neighbouring shards
+    #   agree on the frame they share and every rank can build its shard without the others'.
+    # strong: the workload's own GOPs are divided among the ranks (cfg4: 8 GOPs over 2 / 4 / 8 GPUs).
     base = yuv.synthetic_clip(X, Y, frames, SEEDS[wname], max_shift=min(48, 3 * w["sr"]))
-    clip = base if rank % 2 == 0 else base[::-1]
+    if strong:
+        if w["GOPs"] < world:
+            raise SystemExit(f"bench.py: --scaling strong needs at least one GOP per GPU ({w['GOPs']} GOPs, {world} GPUs)")
+        job_gops = w["GOPs"]
+        ranges = shard.partition(job_gops, world)
+        g0, g1 = ranges[rank]
+        clip = base[g0 * G:g1 * G + 1]
+    else:
+        job_gops = world * w["GOPs"]
+        ranges = shard.partition(job_gops, world)
+        g0, g1 = ranges[rank]
+        clip = base if rank % 2 == 0 else base[::-1]
+    GOPs = g1 - g0                      # this rank's GOPs
+    my_frames = GOPs * G + 1
+    job_frames = n_frames(w) if strong else world * frames  # units the whole job processes
     pinned = torch.empty(clip.shape, dtype=torch.uint8).pin_memory()
     pinned.numpy()[...] = clip
     clip_pinned = pinned.numpy()
+    cfg["frames_per_gpu"] = my_frames
     if world > 1:
-        cfg["sharding"] = (f"one clip of {world * GOPs} GOPs ({world * (frames - 1) + 1} frames), whole GOPs per GPU "
-                           f"({GOPs} each), no data-path collective; the prediction tail of the {Y}-line picture "
-                           "is handed from shard to shard GPU to GPU (NCCL point-to-point, once per level)"
-                           if Y % bs else
-                           f"one clip of {world * GOPs} GOPs, whole GOPs per GPU ({GOPs} each), no collective")
+        cfg["sharding"] = (f"one clip of {job_gops} GOPs ({job_gops * G + 1} frames), whole GOPs per GPU "
+                           f"({'/'.join(str(b - a) for a, b in ranges)}), no data-path collective"
+                           + (f"; the prediction tail of the {Y}-line picture is handed from shard to shard GPU to GPU "
+                              "(NCCL point-to-point, once per level)" if Y % bs else ""))
 
     ctx = Context(local_rank)
     kw = dict(TRLs=T, block_size=bs, search_range=w["sr"], subpixel_accuracy=w["a"],
               update_factor=0.0, always_B=w["always_B"], block_size_min=bs)
     sched = level_schedule(GOPs, T, bs, w["sr"], bs)
-    ranges = shard.partition(world * GOPs, world)
     relay = shard.TailRelay(rank, ranges) if shard.needs_tail_exchange(Y, bs, world) else None
     if relay is not None:
         ctx.set_tail_exchange(relay, device=relay.device)
-    first_global = rank == 0
+    first_global = g0 == 0
 
     # ---- device-resident throughput: inputs already in HBM when the timed region starts
     ctx.resident_load(clip_pinned, X, Y)
@@ -377,7 +396,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     ms_per_step = ms_max / args.steps
-    value = world * frames / (ms_per_step * 1e-3)
+    value = job_frames / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with host buffers (H2D + analysis + D2H + gather)
     fb = clip.shape[1]
@@ -392,11 +411,12 @@ def main():
         need = 0
         shapes = {}
         for s_ in sched:
-            t_, n, b = s_["t"], s_["pairs"], s_["block_size"]
-            shapes[f"high_{t_}"] = ((world * n, fb), np.uint8)
-            shapes[f"motion_{t_}"] = ((world * n, 4, Y // b, X // b), np.int16)
-            shapes[f"motion_filtered_{t_}"] = ((world * n, 4, Y // b, X // b), np.int16)
-        shapes[f"low_{T-1}"] = ((world * GOPs + 1, fb), np.uint8)
+            t_, b = s_["t"], s_["block_size"]
+            n = job_gops * (G >> t_)  # pairs of the whole job at this level
+            shapes[f"high_{t_}"] = ((n, fb), np.uint8)
+            shapes[f"motion_{t_}"] = ((n, 4, Y // b, X // b), np.int16)
+            shapes[f"motion_filtered_{t_}"] = ((n, 4, Y // b, X // b), np.int16)
+        shapes[f"low_{T-1}"] = ((job_gops + 1, fb), np.uint8)
         need = sum(int(np.prod(sh)) * np.dtype(dt).itemsize for sh, dt in shapes.values())
         ok = torch.zeros(1, dtype=torch.int32, device="cuda")
         if rank == 0:
@@ -417,10 +437,10 @@ def main():
                 registered = ctx.host_register(maps[k]) and registered
             out_bufs = {}
             for s_ in sched:
-                t_, n = s_["t"], s_["pairs"]
+                t_, ppg = s_["t"], G >> s_["t"]  # pairs per GOP at this level
                 for name in ("high", "motion", "motion_filtered"):
-                    out_bufs[f"{name}_{t_}"] = maps[f"{name}_{t_}"][rank * n:(rank + 1) * n]
-            out_bufs[f"low_{T-1}"] = maps[f"low_{T-1}"][rank * GOPs:rank * GOPs + GOPs + 1]
+                    out_bufs[f"{name}_{t_}"] = maps[f"{name}_{t_}"][g0 * ppg:g1 * ppg]
+            out_bufs[f"low_{T-1}"] = maps[f"low_{T-1}"][g0:g1 + 1]
             gather_note = (f"rank slices written in place into shared sub-band files in {shm_dir} "
                            f"({need / 1e6:.0f} MB, reference file layout), "
                            + ("page-locked by every rank: the device-to-host copies are the gather"
@@ -446,7 +466,7 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * frames * args.steps / float(t.item())
+    e2e_value = job_frames * args.steps / float(t.item())
     e2e_ok = all((zlib.crc32(outs[f"high_{t_}"]), zlib.crc32(outs[f"motion_{t_}"])) == crc_res[t_] for t_ in crc_res)
     tt = torch.tensor([1 if e2e_ok else 0], dtype=torch.int32, device="cuda")
     if world > 1:
@@ -459,8 +479,8 @@ def main():
         barrier()
         if rank == 0:
             ctx.set_tail_exchange(None)
-            long_clip = np.concatenate([base, base[::-1][1:]], axis=0)
-            whole = ctx.analyze(long_clip, X, Y, 2 * GOPs, first_global=True, **kw)
+            long_clip = base if strong else np.concatenate([base, base[::-1][1:]], axis=0)
+            whole = ctx.analyze(long_clip, X, Y, job_gops, first_global=True, **kw)
             sharded_equals_whole = all(np.array_equal(whole[k], maps[k]) for k in maps)
             del whole, long_clip
         barrier()
@@ -486,7 +506,9 @@ def main():
     steps = args.steps
     cls_ms = {k: v[0] / steps for k, v in prof.items()}
     cls_n = {k: v[1] // steps for k, v in prof.items()}
-    sad = sad_ops_total(w)
+    share_of_workload = GOPs / w["GOPs"]  # strong scaling: rank 0 holds a part of the workload's GOPs
+    sad = sad_ops_total(w) * share_of_workload
+    mc_total = mc_bytes_total(w) * share_of_workload
     search_ms = cls_ms["search"] + cls_ms.get("search_exact", 0.0)
     # everything motion estimation launches: pyramid DWT, byte planes and their interpolations, searches
     # (the image class also holds decorrelate's reference up-sampling: an upper bound for ME)
@@ -503,14 +525,14 @@ def main():
                               "profiles/r2_pipe_probe.txt); algorithmic SAD-ops of SURVEY 8(d); frac = against the "
                               "time in the search kernels, frac_all_me_kernels = against search + pyramid DWT + "
                               "plane preparation, frac_whole_step = against the whole analysis step"},
-        "mc_path": {"bound": "hbm", "achieved": mc_bytes_total(w) / (ms_per_step * 1e-3) / 1e9,
+        "mc_path": {"bound": "hbm", "achieved": mc_total / (ms_per_step * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s",
-                    "frac": mc_bytes_total(w) / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                    "frac": mc_total / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                     "note": "algorithmic frame+motion bytes of all levels / whole step time"},
     }
     # the dominant kernel class of the step, against the bound that applies to it
     share = cls_ms[dominant] / max(1e-9, sum(cls_ms.values()))
-    pairs_total = sum(p // 2 for p in _pictures_per_level(w))
+    pairs_total = sum(s_["pairs"] for s_ in sched)
     fbytes = X * Y * 3 // 2
     field_bytes = 8 * (Y // bs) * (X // bs)
     # algorithmic bytes of decorrelate per pair = two reference frames and the odd
@@ -532,7 +554,7 @@ def main():
                 "achieved": rooflines["me_search"]["achieved"], "peak": u8_peak / 1e9, "unit": "G SAD-op/s",
                 "frac": rooflines["me_search"]["frac"], "traffic": None, "share_of_step": share}
     else:
-        a_bytes = mc_pair_bytes * pairs_total if dominant in ("residue", "predict") else mc_bytes_total(w)
+        a_bytes = mc_pair_bytes * pairs_total if dominant in ("residue", "predict") else mc_total
         ach = a_bytes / (cls_ms[dominant] * 1e-3) / 1e9
         tr = traffic.get(dominant) if wname == "cfg3" else None
         roof = {"bound": "hbm", "kernel": kernel_of.get(dominant, dominant), "achieved": ach, "peak": hbm_peak,
@@ -569,7 +591,7 @@ def main():
         "metric": "1080p MCTF analysis frames/s" if wname == "cfg3" else f"{wname} MCTF analysis frames/s",
         "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": dict(cfg, host=numa_note), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "matches_resident_run": e2e_ok, "gather": gather_note,

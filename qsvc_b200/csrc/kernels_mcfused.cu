@@ -19,6 +19,8 @@
 // predict(); the reference keeps there what the previous pair's in-place analysis
 // left.  k_tail_state reproduces that chain: it is the only
 // sequential step and touches 2*(Ya - cy) rows per pair.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 #define COUNT(L) (++*(L).counter)
@@ -41,37 +43,52 @@ __device__ __forceinline__ int bordered_ref_u8(const uint8_t *U, int pitch, int 
 // Materialises the reference's border rule (texture::alloc + fill_border, bordered_ref_u8) as a
 // ring of `ring` samples around the interior of every plane, so that displaced windows which
 // leave the picture by less than that are plain loads.  U = interior origin of plane 0.
-// One thread per ring cell: the top and bottom bands (full width), then the left and right bands.
-__global__ void __launch_bounds__(256) k_fill_ring(uint8_t *U, long long plane_stride, int pitch, int Yd, int Xd,
-                                                   int ring, int b, int padh) {
+// Above and below the picture the columns inside it repeat the first / last row (none of the
+// rule's quirks applies there): 8-byte copies.  The columns left and right of the picture, for
+// every ringed row, go through the closed form, four cells per thread and store.
+__global__ void __launch_bounds__(256) k_ring_bands(uint8_t *U, long long plane_stride, int pitch, int Yd, int Xd,
+                                                    int ring) {
   uint8_t *P = U + (long long)blockIdx.z * plane_stride;
-  const int W = Xd + 2 * ring;
-  const long long nA = 2LL * ring * W, nB = 2LL * ring * Yd;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nA + nB; i += (long long)gridDim.x * blockDim.x) {
-    int y, x;
-    if (i < nA) {
-      const int r = (int)(i / W);
-      x = (int)(i - (long long)r * W) - ring;
-      y = r < ring ? r - ring : Yd + (r - ring);
-    } else {
-      const long long j = i - nA;
-      y = (int)(j / (2 * ring));
-      const int k = (int)(j - (long long)y * (2 * ring));
-      x = k < ring ? k - ring : Xd + (k - ring);
-    }
-    P[(long long)y * pitch + x] = (uint8_t)bordered_ref_u8(P, pitch, Yd, Xd, b, padh, y, x);
+  const int per_row = Xd >> 3, total = 2 * ring * per_row;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / per_row, k = i - r * per_row;
+    const int y = r < ring ? r - ring : Yd + (r - ring);
+    reinterpret_cast<uint2 *>(P + (long long)y * pitch)[k] =
+        reinterpret_cast<const uint2 *>(P + (long long)(y < 0 ? 0 : Yd - 1) * pitch)[k];
+  }
+}
+__global__ void __launch_bounds__(256) k_ring_sides(uint8_t *U, long long plane_stride, int pitch, int Yd, int Xd,
+                                                    int ring, int b, int padh) {
+  uint8_t *P = U + (long long)blockIdx.z * plane_stride;
+  const int per_row = ring >> 1, total = (Yd + 2 * ring) * per_row;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / per_row, g = i - r * per_row, y = r - ring;
+    // groups of four cells: the first ring / 4 on the left, the others on the right
+    const int x0 = g < (ring >> 2) ? 4 * g - ring : Xd + 4 * (g - (ring >> 2));
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) w |= (unsigned)bordered_ref_u8(P, pitch, Yd, Xd, b, padh, y, x0 + k) << (8 * k);
+    *reinterpret_cast<unsigned *>(P + (long long)y * pitch + x0) = w;
   }
 }
 
 void launch_fill_ring(const Launch &L, uint8_t *U, long long plane_stride, int pitch, int nplanes, int Yd, int Xd,
                       int ring, int b, int padh) {
   if (nplanes <= 0 || ring <= 0) return;
-  const long long cells = 2LL * ring * (Xd + 2 * ring) + 2LL * ring * Yd;
-  int blocks = (int)((cells + 1023) / 1024);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  ProfScope ps_(L, KC_IMG);
-  k_fill_ring<<<dim3(blocks, 1, nplanes), 256, 0, L.stream>>>(U, plane_stride, pitch, Yd, Xd, ring, b, padh);
-  COUNT(L);
+  auto blocks_for = [](long long items) { return (int)std::max<long long>(1, std::min<long long>((items + 1023) / 1024, 64)); };
+  for (int z0 = 0; z0 < nplanes; z0 += 65535) {
+    const int nz = nplanes - z0 < 65535 ? nplanes - z0 : 65535;
+    uint8_t *Uz = U + (long long)z0 * plane_stride;
+    {
+      ProfScope ps_(L, KC_IMG);
+      k_ring_bands<<<dim3(blocks_for(2LL * ring * (Xd >> 3)), 1, nz), 256, 0, L.stream>>>(Uz, plane_stride, pitch, Yd, Xd, ring);
+      COUNT(L);
+    }
+    ProfScope ps_(L, KC_IMG);
+    k_ring_sides<<<dim3(blocks_for((long long)(Yd + 2 * ring) * (ring >> 1)), 1, nz), 256, 0, L.stream>>>(
+        Uz, plane_stride, pitch, Yd, Xd, ring, b, padh);
+    COUNT(L);
+  }
 }
 
 __device__ __forceinline__ unsigned load_u32_unaligned(const uint8_t *p) {
