@@ -88,6 +88,7 @@ struct qsvc_ctx {
   int cur_level = 0;  // temporal level of the running resident analysis / synthesis
   int tma_mode = 1;  // 0: plain loads in the sub-pixel fast path (env QSVC_TMA=0)
   int mc_mode = 0;  // same three values for the decorrelate / correlate path
+  int me_fuse0 = 1;  // fused ME path: first pyramid level straight from the frames (env QSVC_ME_FUSE0=0: off)
   int mc_ring = 1;  // byte-plane path: materialised border ring around the reference planes (env QSVC_MC_RING=0: off)
   int mc_kernel = 0;  // byte-plane path: 0 register march (k_mc_march, default: faster), 1 banded shared-memory pipeline (k_mc_tile); env QSVC_MC_KERNEL
   int me_mode = 0;  // 0: automatic, 1: literal (materialised) path only, 2: fused path required
@@ -333,9 +334,19 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     CU(cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(raw, 0, slot_shorts * nslots * sizeof(short), c->stream));
     CU(cudaMemsetAsync(d_flags, 0, (size_t)nslots * tiles_per_slot + 16, c->stream));
-    launch_load_u8(Lh, img, 0, m + 1, even, even_stride, 0, i0, 1, Y, X);
-    launch_load_u8(Lh, img, m + 1, m, odd, odd_stride, 0, i0, 1, Y, X);
-    launch_fill_border(Lh, img, 0, m + 1, Y, X, B);
+    // invertible pyramid of an even-sized picture: the first analysis level is computed straight
+    // from the frames (load, row pass and column pass fused), the border ring likewise, and the
+    // descent restores level 0 by loading the frames again -- no level-0 snapshot
+    const bool fuse0 = pr && L > 0 && (Y % 2 == 0) && c->me_fuse0 != 0;
+    if (fuse0) {
+      launch_ring_u8(Lh, img, 0, m + 1, even, even_stride, i0, Y, X, B);
+      launch_dwt0_u8(Lh, img, 0, m + 1, even, even_stride, i0, Y, X);
+      launch_dwt0_u8(Lh, img, m + 1, m, odd, odd_stride, i0, Y, X);
+    } else {
+      launch_load_u8(Lh, img, 0, m + 1, even, even_stride, 0, i0, 1, Y, X);
+      launch_load_u8(Lh, img, m + 1, m, odd, odd_stride, 0, i0, 1, Y, X);
+      launch_fill_border(Lh, img, 0, m + 1, Y, X, B);
+    }
     if (n_copy > 0) {
       launch_load_u8(Lh, img, 2 * m + 1, n_copy, even, even_stride, 0, i0 + 1, 1, Y, X);
       launch_fill_border(Lh, img, 2 * m + 1, n_copy, Y, X, B);
@@ -378,13 +389,14 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     std::vector<int> snap_pitch(L + 1, 0);
     size_t snap_per_slot = 0;
     if (pr && L > 0) {
-      for (int l = 0; l < L; l++) {
+      const int l0 = fuse0 ? 1 : 0;  // first level that needs a snapshot
+      for (int l = l0; l < L; l++) {
         snap_off[l] = snap_per_slot;
         snap_pitch[l] = ((X >> l) + 7) & ~7;
         snap_per_slot += (size_t)(Y >> l) * snap_pitch[l];
       }
-      TRY(s.get(snap_per_slot * nslots * sizeof(short), (void **)&snap));
-      for (int l = 0; l < L; l++) {
+      TRY(s.get(std::max<size_t>(snap_per_slot, 8) * nslots * sizeof(short), (void **)&snap));
+      for (int l = l0; l < L; l++) {
         launch_region_copy(Lh, img, 0, nslots, Y >> l, X >> l, snap + snap_off[l], (long long)snap_per_slot,
                            snap_pitch[l], true);
         launch_dwt_level(Lh, img, 0, nslots, Y >> l, X >> l, false);
@@ -394,7 +406,10 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     }
     run_search(ME_INIT, desp(BY, L), desp(BX, L), 0);
     for (int l = L - 1; l >= 0; --l) {
-      if (snap)
+      if (snap && l == 0 && fuse0) {
+        launch_load_u8(Lh, img, 0, m + 1, even, even_stride, 0, i0, 1, Y, X);
+        launch_load_u8(Lh, img, m + 1, m, odd, odd_stride, 0, i0, 1, Y, X);
+      } else if (snap)
         launch_region_copy(Lh, img, 0, nslots, Y >> l, X >> l, snap + snap_off[l], (long long)snap_per_slot,
                            snap_pitch[l], false);
       else
@@ -1053,6 +1068,7 @@ qsvc_ctx *qsvc_create(int device) {
   if (const char *e = getenv("QSVC_TMA")) c->tma_mode = atoi(e);
   if (const char *e = getenv("QSVC_MC_KERNEL")) c->mc_kernel = atoi(e);
   if (const char *e = getenv("QSVC_MC_RING")) c->mc_ring = atoi(e);
+  if (const char *e = getenv("QSVC_ME_FUSE0")) c->me_fuse0 = atoi(e);
   if (const char *e = getenv("QSVC_OVERLAP")) c->overlap = atoi(e);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->me_budget = std::min<size_t>((size_t)64 << 30, free_b / 3);

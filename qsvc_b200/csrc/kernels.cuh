@@ -49,6 +49,10 @@ void launch_fill_border(const Launch &L, Plane p, int slot0, int nslots, int y_d
 void launch_store_u8(const Launch &L, Plane src, int slot0, int nslots, uint8_t *dst,
                      long long frame_stride, long long comp_off, int f0, int fstep, int h, int w);
 
+// fill_border ring of a plain bordered plane straight from the frames' luma (one launch)
+void launch_ring_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8_t *src, long long frame_stride,
+                    int f0, int Y, int X, int b);
+
 void launch_region_copy(const Launch &L, Plane p, int slot0, int nslots, int h, int w, short *snap,
                         long long snap_slot_stride, int pitch, bool to_snapshot);
 
@@ -57,6 +61,9 @@ int dwt_init_attributes();
 // one level on the top-left ny x nx of each slot
 void launch_dwt_level(const Launch &L, Plane p, int slot0, int nslots, int ny, int nx,
                       bool synth);
+// first analysis level of even-sized pictures straight from the frames' luma (load + rows + columns fused)
+void launch_dwt0_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8_t *src, long long frame_stride,
+                    int f0, int Y, int X);
 // dwt2d::analyze(sig, y, x, levels) / dwt2d::synthesize(sig, y, x, levels)
 void dwt_analyze(const Launch &L, Plane p, int slot0, int nslots, int y, int x, int levels);
 void dwt_synthesize(const Launch &L, Plane p, int slot0, int nslots, int y, int x, int levels);

@@ -159,6 +159,76 @@ __global__ void __launch_bounds__(1024) k_dwt_cols(Plane p, int slot0, int ny, i
   }
 }
 
+// ---- first pyramid level straight from the frames ----
+// One level of dwt2d::analyze (rows, then all columns; dwt2d.cpp:76-119, 5_3.cpp:39-52, even
+// sizes) of the luma of frame f0 + z, read as bytes and written as the four sub-bands of the
+// in-place Mallat layout of slot slot0 + z.  A CTA produces D0_TR x D0_TC coefficient pairs per
+// sub-band from a (2 D0_TR + 3) x (2 D0_TC + 3) pixel tile: row pass into shared memory, column
+// pass to the plane.  Replaces load + row pass + column pass of the level (and the snapshot the
+// descent would restore it from: the frame itself is that snapshot).
+static constexpr int D0_TR = 16, D0_TC = 64, D0_ROWS = 2 * D0_TR + 3, D0_WORDS = (2 * D0_TC + 8) / 4;
+__global__ void __launch_bounds__(256) k_dwt0_u8(Plane p, int slot0, const uint8_t *__restrict__ src,
+                                                  long long frame_stride, int f0, int Y, int X) {
+  __shared__ unsigned sin[D0_ROWS][D0_WORDS];  // pixel columns 2 cx0 - 4 .. 2 cx0 + 2 D0_TC + 3
+  __shared__ short RL[D0_ROWS][D0_TC], RH[D0_ROWS][D0_TC];
+  const int slot = slot0 + blockIdx.z;
+  const uint8_t *frame = src + (long long)(f0 + blockIdx.z) * frame_stride;
+  const int halfx = X >> 1, halfy = Y >> 1;
+  const int cx0 = blockIdx.x * D0_TC, ry0 = blockIdx.y * D0_TR;
+  for (int it = threadIdx.x; it < D0_ROWS * D0_WORDS; it += 256) {
+    const int r = it / D0_WORDS, w = it - r * D0_WORDS;
+    const int y = 2 * ry0 - 2 + r, x = 2 * cx0 - 4 + 4 * w;
+    unsigned v = 0;
+    if (y >= 0 && y < Y && x >= 0 && x < X) v = *reinterpret_cast<const unsigned *>(frame + (long long)y * X + x);
+    sin[r][w] = v;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < D0_ROWS * D0_TC; it += 256) {
+    const int r = it / D0_TC, i = it - r * D0_TC, gi = cx0 + i;
+    if (gi >= halfx) continue;
+    const uint8_t *s = reinterpret_cast<const uint8_t *>(sin[r]) + 2 * i + 4;  // s[k] = pixel 2 gi + k
+    const int s0 = s[0], s1 = s[1];
+    const int h = (short)(gi == halfx - 1 ? s1 - s0 : s1 - tdiv2(s0 + s[2]));
+    int l;
+    if (gi == 0) {
+      l = (short)(s0 + tdiv2(h));
+    } else {
+      const int hp = (short)(s[-1] - tdiv2(s[-2] + s0));
+      l = (short)(s0 + tdiv4(h + hp));
+    }
+    RL[r][i] = (short)l;
+    RH[r][i] = (short)h;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < D0_TR * 2 * D0_TC; it += 256) {
+    const int j = it / (2 * D0_TC), c = it - j * (2 * D0_TC), gj = ry0 + j;
+    const int which = c >= D0_TC, i = which ? c - D0_TC : c, gi = cx0 + i;
+    if (gj >= halfy || gi >= halfx) continue;
+    const short(*col)[D0_TC] = which ? RH : RL;  // col[r][i]: row-transformed sample of pixel row 2 ry0 - 2 + r
+    const int t0 = col[2 * j + 2][i], t1 = col[2 * j + 3][i];
+    const int h = (short)(gj == halfy - 1 ? t1 - t0 : t1 - tdiv2(t0 + col[2 * j + 4][i]));
+    int l;
+    if (gj == 0) {
+      l = (short)(t0 + tdiv2(h));
+    } else {
+      const int hp = (short)(col[2 * j + 1][i] - tdiv2(col[2 * j][i] + t0));
+      l = (short)(t0 + tdiv4(h + hp));
+    }
+    const int x = (which ? halfx : 0) + gi;
+    p.row(slot, gj)[x] = (short)l;
+    p.row(slot, halfy + gj)[x] = (short)h;
+  }
+}
+
+void launch_dwt0_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8_t *src, long long frame_stride,
+                    int f0, int Y, int X) {
+  if (nslots <= 0) return;
+  dim3 grid(((X >> 1) + D0_TC - 1) / D0_TC, ((Y >> 1) + D0_TR - 1) / D0_TR, nslots);
+  ProfScope ps_(L, KC_DWT_ROWS);
+  k_dwt0_u8<<<grid, 256, 0, L.stream>>>(p, slot0, src, frame_stride, f0, Y, X);
+  COUNT(L);
+}
+
 int dwt_init_attributes() {
   cudaError_t e;
   e = cudaFuncSetAttribute(k_dwt_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);

@@ -148,6 +148,45 @@ void launch_fill_border(const Launch &L, Plane p, int slot0, int nslots, int Y, 
   }
 }
 
+// texture::fill_border(data, Y, X, b) of a plain bordered plane (every row pointer shifted: no
+// aliasing) whose interior would hold the luma of frame f0 + z: the ring straight from the frame's
+// bytes, one launch (edge replication; the bottom-left corner takes the bottom-RIGHT pixel,
+// texture.cpp:92-97).  The interior itself is not touched.
+__global__ void __launch_bounds__(256) k_ring_u8(Plane p, int slot0, const uint8_t *__restrict__ src,
+                                                  long long frame_stride, int f0, int Y, int X, int b) {
+  const int slot = slot0 + blockIdx.z;
+  const uint8_t *frame = src + (long long)(f0 + blockIdx.z) * frame_stride;
+  const int W = X + 2 * b, nA = 2 * b * W, nB = 2 * b * Y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nA + nB; i += gridDim.x * blockDim.x) {
+    int y, x;
+    if (i < nA) {
+      const int r = i / W;
+      x = i - r * W - b;
+      y = r < b ? r - b : Y + (r - b);
+    } else {
+      const int j = i - nA;
+      y = j / (2 * b);
+      const int k = j - y * (2 * b);
+      x = k < b ? k - b : X + (k - b);
+    }
+    const int sy = y < 0 ? 0 : (y >= Y ? Y - 1 : y);
+    int sx = x < 0 ? 0 : (x >= X ? X - 1 : x);
+    if (y >= Y && x < 0) sx = X - 1;
+    p.row(slot, y)[x] = frame[(long long)sy * X + sx];
+  }
+}
+
+void launch_ring_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8_t *src, long long frame_stride,
+                    int f0, int Y, int X, int b) {
+  if (nslots <= 0 || b <= 0) return;
+  const long long cells = 2LL * b * (X + 2 * b) + 2LL * b * Y;
+  int blocks = (int)((cells + 1023) / 1024);
+  if (blocks > 64) blocks = 64;
+  ProfScope ps_(L, KC_IMG);
+  k_ring_u8<<<dim3(blocks, 1, nslots), 256, 0, L.stream>>>(p, slot0, src, frame_stride, f0, Y, X, b);
+  COUNT(L);
+}
+
 // Copies the top-left h x w region of every slot between the planes and a dense
 // snapshot buffer (row pitch `pitch` shorts, `snap_slot_stride` shorts per slot).
 __global__ void k_region_copy(Plane p, int slot0, int h, int w, short *snap, long long snap_slot_stride,
