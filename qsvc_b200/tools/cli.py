@@ -227,7 +227,9 @@ def _default_bs(X, Y):  # analyze.py:79-83 (evaluated on the default 352x288: al
 
 
 def t_analyze(argv):
-    """analyze.py:107-153, fused: frames stay resident in HBM across levels."""
+    """analyze.py:107-153, fused: frames stay resident in HBM across levels.  Writes every file
+    the reference chain leaves except the prediction_even_<t> side files (written by
+    decorrelate under GET_PREDICTION, read by nothing; `analyze_step` writes them)."""
     a = _driver_parser("analyze").parse(argv)
     X, Y = a.pixels_in_x, a.pixels_in_y
     bs = a.block_size if a.block_size is not None else _default_bs(X, Y)
@@ -235,6 +237,10 @@ def t_analyze(argv):
     uf = 0.0 if a.update_factor is None else a.update_factor  # analyze.py default 0
     pictures = a.GOPs * gop_size(a.TRLs) + 1
     low0 = _read_frames("analyze", "low_0", X, Y, pictures)
+    # motion_estimate exits 1 without computing when its motion file exists
+    # (motion_estimate.cpp:659-682): analyze.py's chain stops at the first such level, after
+    # that level's split, and turns the failure into exit -1
+    stop_at = next((t for t in range(1, a.TRLs) if os.path.exists(f"motion_{t}")), None)
     with _ctx() as c:
         out = c.analyze(low0, X, Y, a.GOPs, a.TRLs, bs, a.search_range, a.subpixel_accuracy, uf,
                         a.always_B, a.block_overlaping, a.border_size, bs_min)
@@ -244,6 +250,8 @@ def t_analyze(argv):
         even, odd = split(low)
         yuv.write_frames(f"even_{t}", even)
         yuv.write_frames(f"odd_{t}", odd)
+        if t == stop_at:
+            return 255
         yuv.write_motion(f"motion_{t}", out[f"motion_{t}"])
         yuv.write_motion(f"motion_filtered_{t}", out[f"motion_filtered_{t}"])
         open(f"frame_types_{t}", "wb").write(out[f"frame_types_{t}"])

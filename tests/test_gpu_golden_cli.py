@@ -174,3 +174,23 @@ def test_cli_synthesize_with_per_level_picture_sizes_matches_reference(tmp_path)
            f"--update_factor={g['uf']}"], str(d))
     X1, Y1, _ = g["geo"][1]
     assert np.array_equal(yuv.read_frames(str(d / "low_0"), X1, Y1), g["syn_low_0"])
+
+
+def test_cli_analyze_stops_at_an_existing_motion_file(tmp_path):
+    """motion_estimate exits 1 without computing when its motion file exists
+    (motion_estimate.cpp:659-682); analyze.py turns that into exit -1 after the levels
+    before it (and that level's split) have run."""
+    g = load("quarter_pel")
+    X, Y, bs, T, GOPs = g["X"], g["Y"], g["bs"], g["TRLs"], g["GOPs"]
+    d = tmp_path
+    yuv.write_frames(str(d / "low_0"), g["low_0"])
+    (d / "motion_2").write_bytes(b"stale")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([MCTF, "analyze", f"--GOPs={GOPs}", f"--TRLs={T}", f"--block_size={bs}",
+                        f"--block_size_min={bs}", f"--search_range={g['sr']}",
+                        f"--subpixel_accuracy={g['a']}", f"--pixels_in_x={X}", f"--pixels_in_y={Y}",
+                        f"--update_factor={g['uf']}"], cwd=str(d), env=env, capture_output=True)
+    assert r.returncode == 255
+    assert np.array_equal(yuv.read_frames(str(d / "high_1"), X, Y), g["high_1"])   # level 1 ran
+    assert (d / "even_2").exists() and (d / "odd_2").exists()                      # level 2's split ran
+    assert not (d / "high_2").exists() and (d / "motion_2").read_bytes() == b"stale"
