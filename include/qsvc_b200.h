@@ -169,6 +169,14 @@ int qsvc_interlevel_motion_decorrelate(qsvc_ctx *ctx, int inverse, const int16_t
                                        int n_fields, const int16_t *reference, int n_reference,
                                        int blocks_in_y, int blocks_in_x, int16_t *fields_out);
 
+/* The step after the hot path on the texture side: the distortion between
+ * two frame files that psnr.py:78-90 obtains from the external program `snr --type=uchar --peak=255
+ * --block_size=<bytes per picture>` (not part of the reference tree: parity unpinned).  Sum of squared
+ * byte differences per block of block_bytes bytes, exact 64-bit integers;
+ * PSNR = 10 log10(peak^2 * block_bytes / sse) is left to the caller. */
+int qsvc_sse(qsvc_ctx *ctx, const uint8_t *a, const uint8_t *b, long long block_bytes, int n_blocks,
+             unsigned long long *sse_out);
+
 /* Whole-sequence temporal analysis with the frames kept resident in HBM between
  * levels: the device-side equivalent of analyze.py:107-153 driving
  * analyze_step.py:115-232 (split -> motion_estimate -> decorrelate -> update per

@@ -76,6 +76,7 @@ SIGNATURES = {
     "qsvc_bidirectional_motion_decorrelate": (_i, [C.c_void_p, _i, i16p, _i, _i, _i, i16p]),
     "qsvc_interlevel_motion_decorrelate": (_i, [C.c_void_p, _i, i16p, _i, i16p, _i, _i, _i, i16p]),
     "qsvc_resident_fetch_motion_residue": (_i, [C.c_void_p, _i, i16p]),
+    "qsvc_sse": (_i, [C.c_void_p, u8p, u8p, C.c_longlong, _i, C.POINTER(C.c_ulonglong)]),
     "qsvc_resident_load": (_i, [C.c_void_p, u8p, _i, _i, _i]),
     "qsvc_resident_analyze": (_i, [C.c_void_p, C.POINTER(AnalyzeParams)]),
     "qsvc_analyze": (_i, [C.c_void_p, C.POINTER(AnalyzeParams), u8p, _i, C.POINTER(LevelOut)]),

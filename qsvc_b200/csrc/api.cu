@@ -1391,6 +1391,34 @@ int qsvc_interlevel_motion_decorrelate(qsvc_ctx *c, int inverse, const int16_t *
   return QSVC_OK;
 }
 
+// Distortion between two byte streams per block (psnr.py:78-90 calls the external `snr` with
+// --block_size = bytes per picture): sum of squared differences per block, exact.
+int qsvc_sse(qsvc_ctx *c, const uint8_t *a, const uint8_t *b, long long block_bytes, int n_blocks,
+             unsigned long long *sse_out) {
+  ENTER(c);
+  if (!a || !b || !sse_out || block_bytes <= 0 || n_blocks < 0) return fail(QSVC_EINVAL, "bad arguments");
+  if (n_blocks == 0) return QSVC_OK;
+  Scratch s(c);
+  uint8_t *d_a, *d_b;
+  unsigned long long *d_out;
+  // chunks of at most 1 GiB per stream keep any file size inside the pool
+  const int per = (int)std::max<long long>(1, std::min<long long>(n_blocks, ((long long)1 << 30) / block_bytes));
+  TRY(s.get((size_t)per * block_bytes, (void **)&d_a));
+  TRY(s.get((size_t)per * block_bytes, (void **)&d_b));
+  TRY(s.get((size_t)n_blocks * sizeof(unsigned long long), (void **)&d_out));
+  CU(cudaMemsetAsync(d_out, 0, (size_t)n_blocks * sizeof(unsigned long long), c->stream));
+  for (int k0 = 0; k0 < n_blocks; k0 += per) {
+    const int m = std::min(per, n_blocks - k0);
+    CU(cudaMemcpyAsync(d_a, a + (long long)k0 * block_bytes, (size_t)m * block_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_b, b + (long long)k0 * block_bytes, (size_t)m * block_bytes, cudaMemcpyHostToDevice, c->stream));
+    launch_sse_u8(c->L(), d_a, d_b, block_bytes, m, d_out + k0);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(sse_out, d_out, (size_t)n_blocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QSVC_OK;
+}
+
 // ------------------------------------------------------ resident sequence
 
 int qsvc_resident_load(qsvc_ctx *c, const uint8_t *low0, int n_frames, int X, int Y) {

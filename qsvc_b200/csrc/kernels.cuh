@@ -177,6 +177,9 @@ void launch_mv_hist(const Launch &L, const short *mv, int n, int *hist);
 void launch_mv_bidirectional(const Launch &L, const short *in, short *out, int n_fields, int plane, int inverse);
 void launch_mv_interlevel(const Launch &L, const short *in, const short *ref, short *out, int n_fields, int n_ref,
                           int plane, int inverse);
+// out[k] += sum of squared byte differences of block k (out zeroed by the caller)
+void launch_sse_u8(const Launch &L, const uint8_t *a, const uint8_t *b, long long block, int nblocks,
+                   unsigned long long *out);
 void launch_copy_bytes(const Launch &L, void *dst, const void *src, size_t n);
 void launch_copy_strided(const Launch &L, void *dst, long long dst_stride, const void *src,
                          long long src_stride, size_t n, int count);

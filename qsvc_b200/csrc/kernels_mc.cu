@@ -214,6 +214,48 @@ void launch_mv_hist(const Launch &L, const short *mv, int n, int *hist) {
   COUNT(L);
 }
 
+// Sum of squared differences of two byte streams per block of `block` bytes (the distortion side of
+// psnr.py:78-90, which shells out to the external `snr --type=uchar --block_size=<bytes per picture>`):
+// exact 64-bit integer sums, one CTA column per block, 16 bytes per thread and step.
+__global__ void __launch_bounds__(256) k_sse_u8(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
+                                                long long block, unsigned long long *out) {
+  const uint8_t *pa = a + (long long)blockIdx.y * block, *pb = b + (long long)blockIdx.y * block;
+  unsigned long long acc = 0;
+  const bool al = ((((uintptr_t)pa) | ((uintptr_t)pb)) & 15) == 0;
+  const long long nv = al ? block >> 4 : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 x = reinterpret_cast<const uint4 *>(pa)[i], y = reinterpret_cast<const uint4 *>(pb)[i];
+    const unsigned xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned d = __vabsdiffu4(xs[k], ys[k]);  // |x - y| per byte
+      s = __dp4a(d, d, s);                           // + sum of squares of the four bytes
+    }
+    acc += s;
+  }
+  for (long long i = (nv << 4) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < block;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)pa[i] - (int)pb[i];
+    acc += (unsigned)(d * d);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&out[blockIdx.y], acc);
+}
+
+void launch_sse_u8(const Launch &L, const uint8_t *a, const uint8_t *b, long long block, int nblocks,
+                   unsigned long long *out) {
+  if (nblocks <= 0 || block <= 0) return;
+  int bx = (int)((block / 16 + 255) / 256);
+  bx = bx < 1 ? 1 : (bx > 64 ? 64 : bx);
+  for (int k0 = 0; k0 < nblocks; k0 += 65535) {
+    const int nb = nblocks - k0 < 65535 ? nblocks - k0 : 65535;
+    ProfScope ps_(L, KC_IMG);
+    k_sse_u8<<<dim3(bx, nb), 256, 0, L.stream>>>(a + (long long)k0 * block, b + (long long)k0 * block, block, out + k0);
+    COUNT(L);
+  }
+}
+
 // Motion-field (de)correlation, the step after the analysis on the motion side.
 // bidirectional (bidirectional_motion_decorrelate.cpp:25-52): NEXT -= PREV (+= when inverse);
 // interlevel (interlevel_motion_decorrelate.cpp:32-69, 250-297): field k of level t is predicted

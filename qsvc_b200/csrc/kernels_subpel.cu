@@ -157,70 +157,98 @@ void launch_upsample2x(const Launch &L, const uint8_t *in, int n, int m, int pit
 // streams the last one to global memory; intermediate planes are written only where a consumer
 // exists (outs[k] != nullptr).  Same arithmetic as k_upsample2x per stage, so the results are
 // identical to chaining it; the traffic is one read of the input and one write per wanted plane.
+// Every stage works on PAIRS of output rows (2i, 2i+1) and 16-byte output groups: the two source
+// rows i, i+1 are read once, the even row is the horizontal expansion of row i, the odd row that of
+// their packed-byte average.
 struct UpChainOut {
   uint8_t *p[3];          // plane of stage k + 1 (k = 0 .. NST-1), nullptr: not materialised
   int pitch[3];
   long long slot_stride[3];
 };
 
-// sixteen samples (columns 16g .. 16g+15) of row y of the next stage from the stage buffer `src`
-// (row pitch sp, a multiple of 8): source columns 8g .. 8g+8 of source row y/2 (and y/2 + 1)
-__device__ __forceinline__ uint4 up_row16(const uint8_t *src, int sp, int y, int g) {
-  const uint8_t *r0 = src + (y >> 1) * sp + 8 * g;
-  uint2 a = *reinterpret_cast<const uint2 *>(r0);
-  unsigned an = r0[8];
-  if (y & 1) {
-    const uint2 b = *reinterpret_cast<const uint2 *>(r0 + sp);
-    a.x = __vhaddu4(a.x, b.x);
-    a.y = __vhaddu4(a.y, b.y);
-    an = (an + r0[sp + 8]) >> 1;
-  }
-  const unsigned h0 = __vhaddu4(a.x, __funnelshift_r(a.x, a.y, 8)), h1 = __vhaddu4(a.y, __funnelshift_r(a.y, an, 8));
-  return make_uint4(__byte_perm(a.x, h0, 0x5140), __byte_perm(a.x, h0, 0x7362), __byte_perm(a.y, h1, 0x5140),
-                    __byte_perm(a.y, h1, 0x7362));
+// horizontal expansion of eight samples (two words) + the sample to their right
+__device__ __forceinline__ uint4 up_expand(unsigned ax, unsigned ay, unsigned an) {
+  const unsigned h0 = __vhaddu4(ax, __funnelshift_r(ax, ay, 8)), h1 = __vhaddu4(ay, __funnelshift_r(ay, an, 8));
+  return make_uint4(__byte_perm(ax, h0, 0x5140), __byte_perm(ax, h0, 0x7362), __byte_perm(ay, h1, 0x5140),
+                    __byte_perm(ay, h1, 0x7362));
+}
+// output rows 2i and 2i+1, columns 16g .. 16g+15, from source rows i and i+1 (row pitch sp, a multiple of 8)
+__device__ __forceinline__ void up_pair16(const uint8_t *src, int sp, int i, int g, uint4 &even, uint4 &odd) {
+  const uint8_t *r0 = src + i * sp + 8 * g;
+  const uint2 a = *reinterpret_cast<const uint2 *>(r0), b = *reinterpret_cast<const uint2 *>(r0 + sp);
+  const unsigned an = r0[8], bn = r0[sp + 8];
+  even = up_expand(a.x, a.y, an);
+  odd = up_expand(__vhaddu4(a.x, b.x), __vhaddu4(a.y, b.y), (an + bn) >> 1);
 }
 
 template <int NST>
 __global__ void __launch_bounds__(256) k_upsample_chain(const uint8_t *__restrict__ in, int n, int m, int pitch_in,
                                                         long long in_slot_stride, UpChainOut o) {
-  constexpr int TH = 64 >> NST, TW = 256 >> NST;  // input tile; the last stage emits 64 x 256
+  constexpr int TH = 64 >> NST, TW = 512 >> NST;  // input tile; the last stage emits 64 x 512
   constexpr int P0 = TW + 16, P1 = 2 * TW + 16, P2 = 4 * TW + 16;  // stage buffer pitches (bytes, % 16 == 0)
-  __shared__ __align__(16) uint8_t s0[(TH + 1) * P0];
-  __shared__ __align__(16) uint8_t s1[(2 * TH + 1) * P1];
-  __shared__ __align__(16) uint8_t s2[NST == 3 ? (4 * TH + 1) * P2 : 16];
+  __shared__ __align__(16) uint8_t s0[(TH + 2) * P0];
+  __shared__ __align__(16) uint8_t s1[(2 * TH + 2) * P1];
+  __shared__ __align__(16) uint8_t s2[NST == 3 ? (4 * TH + 2) * P2 : 16];
   const int slot = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
   const uint8_t *src = in + (long long)slot * in_slot_stride;
-  for (int i = threadIdx.x; i < (TH + 1) * P0; i += 256) {
-    const int r = i / P0, c = i - r * P0;
-    const int y = min(y0 + r, n - 1), x = min(x0 + c, m - 1);
-    s0[i] = c <= TW ? src[(long long)y * pitch_in + x] : (uint8_t)0;
+  {
+    // input tile rows y0 .. y0 + TH (halo row), columns x0 .. x0 + TW + 15, clamped to the picture
+    constexpr int G0 = P0 / 16;
+    const bool al = ((((uintptr_t)src) | (unsigned)pitch_in | (unsigned)x0) & 15) == 0;
+    for (int i = threadIdx.x; i < (TH + 1) * G0; i += 256) {
+      const int r = i / G0, c = (i - r * G0) * 16;
+      const int y = min(y0 + r, n - 1);
+      const uint8_t *row = src + (long long)y * pitch_in;
+      uint4 v;
+      if (al && x0 + c + 16 <= m) {
+        v = *reinterpret_cast<const uint4 *>(row + x0 + c);
+      } else {
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          w[k] = 0;
+#pragma unroll
+          for (int b = 0; b < 4; b++) w[k] |= (unsigned)row[min(x0 + c + 4 * k + b, m - 1)] << (8 * b);
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      *reinterpret_cast<uint4 *>(s0 + r * P0 + c) = v;
+    }
   }
   __syncthreads();
   const uint8_t *cur = s0;
   int cp = P0;
 #pragma unroll
   for (int k = 0; k < NST; k++) {
-    constexpr int dummy = 0;
-    (void)dummy;
-    const int rows = TH << (k + 1), cols = TW << (k + 1);  // this stage's tile (without halo)
+    const int srows = TH << k, scols = TW << k;           // this stage's SOURCE tile (without halo)
     const int gy0 = y0 << (k + 1), gx0 = x0 << (k + 1), gn = n << (k + 1), gm = m << (k + 1);
     uint8_t *g = o.p[k] ? o.p[k] + (long long)slot * o.slot_stride[k] + (long long)gy0 * o.pitch[k] + gx0 : nullptr;
     const bool al16 = (o.pitch[k] & 15) == 0 && (gm & 15) == 0;
+    const int pk = o.pitch[k];
     if (k < NST - 1) {
       uint8_t *nxt = k == 0 ? s1 : s2;
       const int np = k == 0 ? P1 : P2;
-      const int gr = cols / 16 + 1;  // one more group: the halo column
-      for (int i = threadIdx.x; i < (rows + 1) * gr; i += 256) {
-        const int y = i / gr, q = i - y * gr;
-        const uint4 v = up_row16(cur, cp, y, q);
-        *reinterpret_cast<uint4 *>(nxt + y * np + 16 * q) = v;
-        if (g && y < rows && q < gr - 1 && gy0 + y < gn && gx0 + 16 * q < gm) {
-          uint8_t *d = g + (long long)y * o.pitch[k] + 16 * q;
-          if (al16) {
-            *reinterpret_cast<uint4 *>(d) = v;
-          } else {  // picture width a multiple of 8 only
-            *reinterpret_cast<uint2 *>(d) = make_uint2(v.x, v.y);
-            if (gx0 + 16 * q + 8 < gm) *reinterpret_cast<uint2 *>(d + 8) = make_uint2(v.z, v.w);
+      // source row pairs (i, i+1) for i = 0 .. srows - 1 give output rows 0 .. 2 srows - 1; the halo row
+      // 2 srows of the output is the even row of source pair srows (whose odd row nobody reads)
+      const int gr = scols / 8 + 1;  // 16-byte output groups per row, one more for the halo column
+      for (int t = threadIdx.x; t < (srows + 1) * gr; t += 256) {
+        const int i = t / gr, q = t - i * gr;
+        uint4 ev, od;
+        up_pair16(cur, cp, i, q, ev, od);
+        *reinterpret_cast<uint4 *>(nxt + (2 * i) * np + 16 * q) = ev;
+        *reinterpret_cast<uint4 *>(nxt + (2 * i + 1) * np + 16 * q) = od;
+        if (g && i < srows && q < gr - 1 && gx0 + 16 * q < gm) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            if (gy0 + 2 * i + h >= gn) break;
+            uint8_t *d = g + (long long)(2 * i + h) * pk + 16 * q;
+            const uint4 v = h ? od : ev;
+            if (al16) {
+              *reinterpret_cast<uint4 *>(d) = v;
+            } else {  // picture width a multiple of 8 only
+              *reinterpret_cast<uint2 *>(d) = make_uint2(v.x, v.y);
+              if (gx0 + 16 * q + 8 < gm) *reinterpret_cast<uint2 *>(d + 8) = make_uint2(v.z, v.w);
+            }
           }
         }
       }
@@ -228,34 +256,28 @@ __global__ void __launch_bounds__(256) k_upsample_chain(const uint8_t *__restric
       cur = nxt;
       cp = np;
     } else {
-      // 256 threads = 16 rows x 16 column groups of 16 bytes; each thread walks down four rows of
-      // the same parity: source and destination pointers advance by constants
-      const int q = threadIdx.x & 15, ty = threadIdx.x >> 4;
+      // last stage: 32 source rows x 32 groups of 8 source bytes; 256 threads = 8 source rows x 32 groups,
+      // each thread walks down four source rows: pointers advance by constants
+      const int q = threadIdx.x & 31, ti = threadIdx.x >> 5;
       if (gx0 + 16 * q < gm) {
-        const uint8_t *sp = cur + (ty >> 1) * cp + 8 * q;
-        uint8_t *d = g + (long long)ty * o.pitch[k] + 16 * q;
-        const long long dstep = 16LL * o.pitch[k];
-        const bool odd = ty & 1, tail8 = gx0 + 16 * q + 8 < gm;
+        uint8_t *d = g + (long long)(2 * ti) * pk + 16 * q;
+        const long long dstep = 16LL * pk;
+        const bool tail8 = gx0 + 16 * q + 8 < gm;
 #pragma unroll
-        for (int y = ty; y < rows; y += 16, sp += 8 * cp, d += dstep) {
-          if (gy0 + y >= gn) break;
-          uint2 a = *reinterpret_cast<const uint2 *>(sp);
-          unsigned an = sp[8];
-          if (odd) {
-            const uint2 b = *reinterpret_cast<const uint2 *>(sp + cp);
-            a.x = __vhaddu4(a.x, b.x);
-            a.y = __vhaddu4(a.y, b.y);
-            an = (an + sp[cp + 8]) >> 1;
-          }
-          const unsigned h0 = __vhaddu4(a.x, __funnelshift_r(a.x, a.y, 8));
-          const unsigned h1 = __vhaddu4(a.y, __funnelshift_r(a.y, an, 8));
-          const uint4 v = make_uint4(__byte_perm(a.x, h0, 0x5140), __byte_perm(a.x, h0, 0x7362),
-                                     __byte_perm(a.y, h1, 0x5140), __byte_perm(a.y, h1, 0x7362));
+        for (int i = ti; i < srows; i += 8, d += dstep) {
+          if (gy0 + 2 * i >= gn) break;
+          uint4 ev, od;
+          up_pair16(cur, cp, i, q, ev, od);
           if (al16) {
-            *reinterpret_cast<uint4 *>(d) = v;
+            *reinterpret_cast<uint4 *>(d) = ev;
+            if (gy0 + 2 * i + 1 < gn) *reinterpret_cast<uint4 *>(d + pk) = od;
           } else {
-            *reinterpret_cast<uint2 *>(d) = make_uint2(v.x, v.y);
-            if (tail8) *reinterpret_cast<uint2 *>(d + 8) = make_uint2(v.z, v.w);
+            *reinterpret_cast<uint2 *>(d) = make_uint2(ev.x, ev.y);
+            if (tail8) *reinterpret_cast<uint2 *>(d + 8) = make_uint2(ev.z, ev.w);
+            if (gy0 + 2 * i + 1 < gn) {
+              *reinterpret_cast<uint2 *>(d + pk) = make_uint2(od.x, od.y);
+              if (tail8) *reinterpret_cast<uint2 *>(d + pk + 8) = make_uint2(od.z, od.w);
+            }
           }
         }
       }
@@ -277,10 +299,10 @@ void launch_upsample_chain(const Launch &L, const uint8_t *in, int n, int m, int
   }
   ProfScope ps_(L, KC_IMG);
   if (nst == 3) {
-    dim3 grid((m + 31) / 32, (n + 7) / 8, nslots);
+    dim3 grid((m + 63) / 64, (n + 7) / 8, nslots);
     k_upsample_chain<3><<<grid, 256, 0, L.stream>>>(in, n, m, pitch_in, in_slot_stride, o);
   } else {
-    dim3 grid((m + 63) / 64, (n + 15) / 16, nslots);
+    dim3 grid((m + 127) / 128, (n + 15) / 16, nslots);
     k_upsample_chain<2><<<grid, 256, 0, L.stream>>>(in, n, m, pitch_in, in_slot_stride, o);
   }
   COUNT(L);

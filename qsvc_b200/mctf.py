@@ -269,6 +269,25 @@ class Context:
         check(self._L.qsvc_resident_fetch_motion_residue(self._h, t, _i16(out)))
         return out
 
+    def sse(self, a, b, block_bytes):
+        """Sum of squared byte differences per block of block_bytes bytes of two equally long
+        uint8 streams (the distortion behind psnr.py:78-90): uint64 array, one entry per block."""
+        a = np.ascontiguousarray(a, np.uint8).ravel()
+        b = np.ascontiguousarray(b, np.uint8).ravel()
+        n = min(a.size, b.size) // int(block_bytes)
+        out = np.zeros(n, np.uint64)
+        check(self._L.qsvc_sse(self._h, _u8(a), _u8(b), int(block_bytes), n,
+                               out.ctypes.data_as(C.POINTER(C.c_ulonglong))))
+        return out
+
+    def psnr(self, a, b, block_bytes, peak=255.0):
+        """(per-block PSNR in dB, overall PSNR in dB); identical blocks give inf."""
+        sse = self.sse(a, b, block_bytes).astype(np.float64)
+        with np.errstate(divide="ignore"):
+            per = 10.0 * np.log10(peak * peak * float(block_bytes) / sse)
+            tot = 10.0 * np.log10(peak * peak * float(block_bytes) * max(len(sse), 1) / sse.sum()) if len(sse) else np.inf
+        return per, float(tot)
+
     def update(self, frames_in, high, motion, frame_types, X, Y, block_size=16,
                update_factor=0.25, inverse=False):
         frames_in = np.ascontiguousarray(frames_in, np.uint8)

@@ -426,7 +426,63 @@ def t_interlevel(argv, inverse=False):
     return 0
 
 
+def t_demux(argv):
+    """`demux <record_bytes> <offset> <length> < in > out`: the byte range [offset, offset +
+    length) of every record of the input, the external filter the reference's texture and
+    motion coders pipe frame files through to pull one component out of every picture
+    (texture_compress_fb_j2k.py:155-163,255-257; motion_compress_j2k.py:103).  Host-side byte
+    slicing: its source is not part of the reference tree (contract restated from the call sites)."""
+    if len(argv) != 3:
+        sys.stderr.write("usage: demux <record_bytes> <offset> <length> < input > output\n")
+        return 1
+    rec, off, ln = (int(v) for v in argv)
+    data = np.frombuffer(sys.stdin.buffer.read(), np.uint8)
+    n = data.size // rec
+    sys.stdout.buffer.write(np.ascontiguousarray(data[: n * rec].reshape(n, rec)[:, off:off + ln]).tobytes())
+    tail = data[n * rec:]  # a trailing partial record contributes what it holds of the range
+    if tail.size > off:
+        sys.stdout.buffer.write(tail[off:off + ln].tobytes())
+    return 0
+
+
+def t_snr(argv):
+    """`snr --type=uchar --peak=255 --file_A=a --file_B=b --block_size=<bytes>`: the external
+    distortion meter psnr.py:78-90 greps for its `PSNR ... dB` line (third blank-separated
+    field).  Sums of squared differences per block on the GPU (qsvc_sse), PSNR on the host.
+    Its source is not part of the reference tree: only the contract of the call site is kept."""
+    p = _Parser("snr")
+    p.opt("type", "t", "uchar")
+    p.opt("peak", "p", 255.0, float)
+    p.opt("file_A", "a", "")
+    p.opt("file_B", "b", "")
+    p.opt("block_size", "s", 0, int)
+    a = p.parse(argv)
+    if a.type != "uchar":
+        sys.stderr.write("snr: only --type=uchar is supported\n")
+        return 1
+    for fn in (a.file_A, a.file_B):
+        if not os.path.exists(fn):
+            _abort("snr", f'unable to read "{fn}"')
+    A, B = np.fromfile(a.file_A, np.uint8), np.fromfile(a.file_B, np.uint8)
+    n = min(A.size, B.size)
+    block = a.block_size if a.block_size > 0 else n
+    with _ctx() as c:
+        sse = c.sse(A[:n], B[:n], block)
+    tot = float(sse.sum())
+    samples = float(len(sse) * block)
+    for k, v in enumerate(sse):
+        mse = float(v) / block
+        print(f"block {k}: MSE = {mse:.6f} RMSE = {mse ** 0.5:.6f}")
+    mse = tot / samples if samples else 0.0
+    psnr = float("inf") if mse == 0 else 10.0 * np.log10(a.peak * a.peak / mse)
+    print(f"MSE = {mse:.6f}")
+    print(f"PSNR = {psnr:.6f} dB")
+    return 0
+
+
 TOOLS = {
+    "demux": t_demux,
+    "snr": t_snr,
     "bidirectional_motion_decorrelate": t_bidirectional,
     "bidirectional_motion_correlate": lambda argv: t_bidirectional(argv, inverse=True),
     "interlevel_motion_decorrelate": t_interlevel,
