@@ -163,10 +163,10 @@ __global__ void __launch_bounds__(1024) k_dwt_cols(Plane p, int slot0, int ny, i
 // One level of dwt2d::analyze (rows, then all columns; dwt2d.cpp:76-119, 5_3.cpp:39-52, even
 // sizes) of the luma of frame f0 + z, read as bytes and written as the four sub-bands of the
 // in-place Mallat layout of slot slot0 + z.  A CTA produces D0_TR x D0_TC coefficient pairs per
-// sub-band from a (2 D0_TR + 3) x (2 D0_TC + 3) pixel tile: row pass into shared memory, column
+// sub-band from a (2 D0_TR + 3) x (2 D0_TC + 3) pixel tile (67 x 131: 5 % of halo rows): row pass into shared memory, column
 // pass to the plane.  Replaces load + row pass + column pass of the level (and the snapshot the
 // descent would restore it from: the frame itself is that snapshot).
-static constexpr int D0_TR = 16, D0_TC = 64, D0_ROWS = 2 * D0_TR + 3, D0_WORDS = (2 * D0_TC + 8) / 4;
+static constexpr int D0_TR = 32, D0_TC = 64, D0_ROWS = 2 * D0_TR + 3, D0_WORDS = (2 * D0_TC + 8) / 4;
 __global__ void __launch_bounds__(256) k_dwt0_u8(Plane p, int slot0, const uint8_t *__restrict__ src,
                                                   long long frame_stride, int f0, int Y, int X) {
   __shared__ unsigned sin[D0_ROWS][D0_WORDS];  // pixel columns 2 cx0 - 4 .. 2 cx0 + 2 D0_TC + 3

@@ -553,18 +553,25 @@ __device__ __forceinline__ void shifted3(const unsigned *rw, unsigned sh[3], con
   }
 }
 
-template <int W, int S, bool EX, bool FM = false>
+// COLS adjacent word columns per thread: their window words overlap, so the loads (and the fixed
+// cost per thread) are shared.
+template <int W, int S, bool EX, bool FM = false, int COLS = 1>
 __device__ __forceinline__ void sad_rows(const unsigned *P4, const unsigned *R4, const unsigned *E4, int rp,
                                          unsigned acc[9], const unsigned *km = nullptr) {
   constexpr int WPR = W / 4, RPT = W / 4;
-  unsigned p[RPT];
+  unsigned p[RPT][COLS];
 #pragma unroll
-  for (int r = 0; r < RPT; r++) p[r] = P4[r * WPR];
+  for (int r = 0; r < RPT; r++)
+#pragma unroll
+    for (int cc = 0; cc < COLS; cc++) p[r][cc] = P4[r * WPR + cc];
 #pragma unroll
   for (int rr = 0; rr < RPT + 2; rr++) {
-    unsigned sh[3], se[3];
-    shifted3<S, FM>(R4 + rr * rp, sh, km);
-    if (EX) shifted3<S, FM>(E4 + rr * rp, se, km);
+    unsigned sh[COLS][3], se[COLS][3];
+#pragma unroll
+    for (int cc = 0; cc < COLS; cc++) {
+      shifted3<S, FM>(R4 + rr * rp + cc, sh[cc], km);
+      if (EX) shifted3<S, FM>(E4 + rr * rp + cc, se[cc], km);
+    }
 #pragma unroll
     for (int wdy = -1; wdy <= 1; wdy++) {
       const int r = rr - 1 - wdy;  // block row paired with window row rr under vertical shift wdy
@@ -572,8 +579,11 @@ __device__ __forceinline__ void sad_rows(const unsigned *P4, const unsigned *R4,
 #pragma unroll
         for (int wdx = -1; wdx <= 1; wdx++) {
           const int a = (wdy + 1) * 3 + wdx + 1;
-          acc[a] = __vsadu4(p[r], sh[wdx + 1]) + acc[a];
-          if (EX) acc[a] = __vsadu4(se[wdx + 1], 0u) + acc[a];
+#pragma unroll
+          for (int cc = 0; cc < COLS; cc++) {
+            acc[a] = __vsadu4(p[r][cc], sh[cc][wdx + 1]) + acc[a];
+            if (EX) acc[a] = __vsadu4(se[cc][wdx + 1], 0u) + acc[a];
+          }
         }
       }
     }
@@ -582,10 +592,11 @@ __device__ __forceinline__ void sad_rows(const unsigned *P4, const unsigned *R4,
 
 // Warp sums -> block sums per direction -> arg-min with the reference's `<=` rule -> vectors.
 // s_err: [2 * W / 32][9]; one direction per warp (W >= 32).
-template <int W>
+template <int W, int COLS = 1>
 __device__ __forceinline__ void sad_finish(const SubpelParams &q, const unsigned acc[9], int (*s_err)[9], int pair,
                                            int by, int bx, const short c[4]) {
-  constexpr int WPD = W / 32;  // warps per direction
+  constexpr int WPD = W / 32 / COLS;  // warps per direction
+  static_assert(WPD >= 1, "one direction per warp at least");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < 9; k++) {
@@ -641,10 +652,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar) {
   }
 }
 
-template <int W, int ALIGNED, bool FM>
-__global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __grid_constant__ CUtensorMap tmP,
-                                                      const __grid_constant__ CUtensorMap tmR) {
-  constexpr int WPR = W / 4, RPT = W / 4, NT = 2 * W;
+template <int W, int ALIGNED, int COLS>
+__global__ void __launch_bounds__(2 * W / COLS) k_subpel_tma(SubpelParams q, const __grid_constant__ CUtensorMap tmP,
+                                                             const __grid_constant__ CUtensorMap tmR) {
+  constexpr bool FM = false;
+  constexpr int WPR = W / 4, RPT = W / 4, NT = 2 * W / COLS, NTD = W / COLS, WPRC = WPR / COLS;
   constexpr int BOXW = ALIGNED ? W + 32 : W + 16;  // TMA landing pitch in bytes
   constexpr int TP = BOXW / 4;
   constexpr int TBYTES = BOXW * (W + 2);
@@ -739,8 +751,8 @@ __global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __gr
     return;
   }
   mbar_wait(&bar);
-  const int d = threadIdx.x / W, t = threadIdx.x % W;  // one direction per warp
-  const int j = t % WPR, g = t / WPR;
+  const int d = threadIdx.x / NTD, t = threadIdx.x % NTD;  // whole warps per direction
+  const int j = (t % WPRC) * COLS, g = t / WPRC;
   const unsigned *P4 = reinterpret_cast<const unsigned *>(sP) + (g * RPT) * WPR + j;
   const unsigned *R4 = reinterpret_cast<const unsigned *>(sT[d]) + (g * RPT) * TP + j;
   unsigned acc[9];
@@ -749,16 +761,16 @@ __global__ void __launch_bounds__(2 * W) k_subpel_tma(SubpelParams q, const __gr
   if (ALIGNED) {
     R4 += (wx[d] & 15) >> 2;
     switch (wx[d] & 3) {
-      case 0: sad_rows<W, 0, false, FM>(P4, R4, nullptr, TP, acc, q.kmul); break;
-      case 1: sad_rows<W, 1, false, FM>(P4, R4, nullptr, TP, acc, q.kmul); break;
-      case 2: sad_rows<W, 2, false, FM>(P4, R4, nullptr, TP, acc, q.kmul); break;
-      default: sad_rows<W, 3, false, FM>(P4, R4, nullptr, TP, acc, q.kmul); break;
+      case 0: sad_rows<W, 0, false, FM, COLS>(P4, R4, nullptr, TP, acc, q.kmul); break;
+      case 1: sad_rows<W, 1, false, FM, COLS>(P4, R4, nullptr, TP, acc, q.kmul); break;
+      case 2: sad_rows<W, 2, false, FM, COLS>(P4, R4, nullptr, TP, acc, q.kmul); break;
+      default: sad_rows<W, 3, false, FM, COLS>(P4, R4, nullptr, TP, acc, q.kmul); break;
     }
   } else {
-    sad_rows<W, 0, false, FM>(P4, R4, nullptr, TP, acc, q.kmul);
+    sad_rows<W, 0, false, FM, COLS>(P4, R4, nullptr, TP, acc, q.kmul);
   }
   short c[4] = {(short)blk[0], (short)blk[1], (short)blk[2], (short)blk[3]};
-  sad_finish<W>(q, acc, s_err, pair, by, bx, c);
+  sad_finish<W, COLS>(q, acc, s_err, pair, by, bx, c);
 }
 
 // ------------------------------------------------------------ exact path
@@ -1336,14 +1348,16 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
     const dim3 ggrid(q.BX, q.BY * qg.pair_group, (npairs + qg.pair_group - 1) / qg.pair_group);
     const CUtensorMap &tp = *reinterpret_cast<const CUtensorMap *>(q.tm_p);
     const CUtensorMap &tr = *reinterpret_cast<const CUtensorMap *>(q.tm_r);
-    static const int fm = getenv("QSVC_SUBPEL_FM") ? atoi(getenv("QSVC_SUBPEL_FM")) : 0;  // measured: no gain (the kernel is not ALU-bound)
-    qg.kmul[0] = 1u << 24;  // >> 8
-    qg.kmul[1] = 1u << 16;  // >> 16
-    qg.kmul[2] = 1u << 8;   // >> 24
-    if (q.use_tma && fm)
-      k_subpel_tma<W, 1, true><<<ggrid, 2 * W, 0, L.stream>>>(qg, tp, tr);
+    // two word columns per thread for 64 x 64 blocks (64 threads per block: half the fixed cost per
+    // block, shared window loads); env QSVC_SUBPEL_COLS=1: one column per thread as for 32 x 32
+    static const int cols2 = getenv("QSVC_SUBPEL_COLS") ? atoi(getenv("QSVC_SUBPEL_COLS")) : 2;
+    qg.kmul[0] = 1u << 24;  // >> 8 (the FMA-pipe funnel shift of fshr<true>: measured without effect, not instantiated)
+    qg.kmul[1] = 1u << 16;
+    qg.kmul[2] = 1u << 8;
+    if (q.use_tma && W == 64 && cols2 == 2)
+      k_subpel_tma<W, 1, (W == 64 ? 2 : 1)><<<ggrid, W, 0, L.stream>>>(qg, tp, tr);
     else if (q.use_tma)
-      k_subpel_tma<W, 1, false><<<ggrid, 2 * W, 0, L.stream>>>(qg, tp, tr);
+      k_subpel_tma<W, 1, 1><<<ggrid, 2 * W, 0, L.stream>>>(qg, tp, tr);
     else
       k_subpel_fast<W><<<grid, (W / 4) * (W / 8), 0, L.stream>>>(q);
     COUNT(L);
