@@ -1227,34 +1227,41 @@ __global__ void __launch_bounds__(256) k_level1_tile(B0View v, int slot0, int Y0
 // rows [Y0, Y1) x columns [0, W) of the level-2 image: the row's two source rows and the kind of
 // storage they live in are resolved once per CTA, a thread produces one sample.
 static constexpr int STRIP2_ROWS = 16;
+// One thread per level-1 column j: it produces the level-2 samples 2j and 2j + 1 of each of the CTA's
+// rows from the column-pass values T(j) and T(j + 1) (the second one is the neighbour's first).
 __global__ void __launch_bounds__(256) k_strip2(int Y, int X, const short *top1, long long top1_stride,
                                                 const short *left1, long long left1_stride, int clean1,
                                                 const uint8_t *v1, long long v1_slot_stride, int v1_pitch,
                                                 short *dst, long long dst_stride, int slot0, int Y0, int Y1, int W) {
   const int slot = slot0 + blockIdx.z;
   const int X1 = 2 * X, Y2 = 4 * Y, X2 = 4 * X;
-  const int x = blockIdx.x * 256 + threadIdx.x;
-  if (x >= W) return;
-  // STRIP2_ROWS rows per CTA: narrow regions would otherwise be bound by the CTA launch rate
-  for (int y = Y0 + blockIdx.y * STRIP2_ROWS; y < min(Y0 + (blockIdx.y + 1) * STRIP2_ROWS, Y1); y++) {
-  const int ya = y >> 1;
-  const bool vavg = (y & 1) && y != Y2 - 1;
-  // source row yy of the level-1 image: int16 top strip, or int16 left strip + bytes
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (2 * j >= W) return;
+  const bool has_next = 2 * j + 1 < W;             // W odd: the region's last column stands alone
+  const bool avg_next = 2 * j + 1 != X2 - 1;       // last odd column of the image = last column
   const short *t1 = top1 + slot * top1_stride, *l1 = left1 + slot * left1_stride;
   const uint8_t *b1 = v1 + slot * v1_slot_stride;
-  const bool topA = ya < clean1, topB = ya + 1 < clean1;
-  const short *sA = topA ? t1 + (long long)ya * X1 : l1 + (long long)(ya - clean1) * clean1;
-  const short *sB = topB ? t1 + (long long)(ya + 1) * X1 : l1 + (long long)(ya + 1 - clean1) * clean1;
-  const uint8_t *bA = b1 + (long long)ya * v1_pitch, *bB = bA + v1_pitch;
-  auto T2 = [&](int xp) -> int {
-    const int a0 = (topA || xp < clean1) ? (int)sA[xp] : (int)bA[xp];
-    if (!vavg) return a0;
-    const int a1 = (topB || xp < clean1) ? (int)sB[xp] : (int)bB[xp];
-    return (short)tdiv2(a0 + a1);
-  };
-  const int a0 = T2(x >> 1);
-  dst[slot * dst_stride + (long long)(y - Y0) * W + x] =
-      (!(x & 1) || x == X2 - 1) ? (short)a0 : (short)tdiv2(a0 + T2((x >> 1) + 1));
+  short *out = dst + slot * dst_stride;
+  // level-1 sample (row ya, column xp): int16 top strip, int16 left strip, or a byte of V_1
+  const bool c0 = j < clean1, c1 = j + 1 < clean1;  // columns inside the left strip
+  for (int y = Y0 + blockIdx.y * STRIP2_ROWS; y < min(Y0 + (blockIdx.y + 1) * STRIP2_ROWS, Y1); y++) {
+    const int ya = y >> 1;
+    const bool vavg = (y & 1) && y != Y2 - 1;
+    const bool topA = ya < clean1, topB = ya + 1 < clean1;
+    const short *sA = topA ? t1 + (long long)ya * X1 : l1 + (long long)(ya - clean1) * clean1;
+    const short *sB = topB ? t1 + (long long)(ya + 1) * X1 : l1 + (long long)(ya + 1 - clean1) * clean1;
+    const uint8_t *bA = b1 + (long long)ya * v1_pitch, *bB = bA + v1_pitch;
+    int a0 = (topA || c0) ? (int)sA[j] : (int)bA[j];
+    if (vavg) a0 = (short)tdiv2(a0 + ((topB || c0) ? (int)sB[j] : (int)bB[j]));
+    int o1 = a0;
+    if (has_next && avg_next) {
+      int a1 = (topA || c1) ? (int)sA[j + 1] : (int)bA[j + 1];
+      if (vavg) a1 = (short)tdiv2(a1 + ((topB || c1) ? (int)sB[j + 1] : (int)bB[j + 1]));
+      o1 = (short)tdiv2(a0 + a1);
+    }
+    short *d = out + (long long)(y - Y0) * W + 2 * j;
+    d[0] = (short)a0;
+    if (has_next) d[1] = (short)o1;
   }
 }
 
@@ -1295,7 +1302,7 @@ void launch_strips(const Launch &L, const SubpelParams &q, int level, int slot0,
   auto run = [&](short *dst, long long dst_stride, int Y0, int Y1, int W) {
     if (Y1 <= Y0 || W <= 0) return;
     ProfScope ps_(L, KC_SEARCH_EXACT);
-    k_strip2<<<dim3((W + 255) / 256, (Y1 - Y0 + STRIP2_ROWS - 1) / STRIP2_ROWS, nslots), 256, 0, L.stream>>>(
+    k_strip2<<<dim3(((W + 1) / 2 + 255) / 256, (Y1 - Y0 + STRIP2_ROWS - 1) / STRIP2_ROWS, nslots), 256, 0, L.stream>>>(
         q.Y, q.X, top1, top1_stride, left1, left1_stride, clean1, v1, v1_slot_stride, v1_pitch, dst, dst_stride,
         slot0, Y0, Y1, W);
     COUNT(L);
@@ -1350,7 +1357,7 @@ static void launch_subpel_w(const Launch &L, const SubpelParams &q, int npairs) 
     const CUtensorMap &tr = *reinterpret_cast<const CUtensorMap *>(q.tm_r);
     // two word columns per thread for 64 x 64 blocks (64 threads per block: half the fixed cost per
     // block, shared window loads); env QSVC_SUBPEL_COLS=1: one column per thread as for 32 x 32
-    static const int cols2 = getenv("QSVC_SUBPEL_COLS") ? atoi(getenv("QSVC_SUBPEL_COLS")) : 2;
+    static const int cols2 = getenv("QSVC_SUBPEL_COLS") ? atoi(getenv("QSVC_SUBPEL_COLS")) : 1;  // measured: no gain (latency per block, not instructions)
     qg.kmul[0] = 1u << 24;  // >> 8 (the FMA-pipe funnel shift of fshr<true>: measured without effect, not instantiated)
     qg.kmul[1] = 1u << 16;
     qg.kmul[2] = 1u << 8;
