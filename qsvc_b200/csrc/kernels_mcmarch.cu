@@ -86,24 +86,29 @@ __device__ __forceinline__ void hpass(const int *v, int *out, bool first, bool l
   for (int i = 1; i < N / 2; i++) out[i] = v[2 * i] + tq4(h[i] + h[i - 1]);
 }
 
-// Level-0 row pass on the 8 prediction bytes of a lane.
+// Level-0 row pass on the 8 prediction bytes of a lane (s[0..7] = lo, hi; s[-2], s[-1] from the lane
+// on the left, s[8] from the lane on the right).  The kernel is bound by the ALU pipe (LOP3 / SHF /
+// PRMT / IADD3 / LEA.HI share it, profiles/r2_pipe_probe.txt), so the byte sums go through IDP.4A on
+// the FMA pipe: for output i the window U = (s[2i-1], s[2i], s[2i+1], s[2i+2]) gives the halved even
+// pair sum A_i, the odd pair sum d_{i-1} + d_i and the centre sample:
+//   l_i = s[2i] + (h_{i-1} + h_i) / 4,  h_{i-1} + h_i = d_{i-1} + d_i - A_{i-1} - A_i.
+// The line ends are mirror extensions: x[n] := x[n-2] on the right, and h[-1] := h[0] on the left is
+// s[-1] := s[1], s[-2] := s[2].
+__device__ __forceinline__ int dp4(unsigned a, unsigned w, int acc) { return (int)__dp4a(a, w, (unsigned)acc); }
 __device__ __forceinline__ void hpass_u8(unsigned lo, unsigned hi, int *out, bool first, bool last) {
-  const unsigned nlo = __shfl_down_sync(FULL, lo, 1);
-  int s[9];
+  unsigned nlo = __shfl_down_sync(FULL, lo, 1), phi = __shfl_up_sync(FULL, hi, 1);
+  if (last) nlo = hi >> 16;                      // s[8] := s[6]
+  if (first) phi = __byte_perm(lo, 0, 0x1200);   // s[-2] := s[2], s[-1] := s[1]
+  const unsigned U[4] = {__byte_perm(phi, lo, 0x6543), __byte_perm(lo, hi, 0x4321), __byte_perm(lo, hi, 0x6543),
+                         __byte_perm(hi, nlo, 0x4321)};
+  int ap = dp4(__byte_perm(phi, lo, 0x5432), 0x00010001u, 0) >> 1;  // A_{-1} = (s[-2] + s[0]) >> 1
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    s[k] = (lo >> (8 * k)) & 0xff;
-    s[4 + k] = (hi >> (8 * k)) & 0xff;
+  for (int i = 0; i < 4; i++) {
+    const int a = dp4(U[i], 0x01000100u, 0) >> 1;
+    const int t = dp4(U[i], 0x00010001u, 0) - a - ap;
+    out[i] = dp4(U[i], 0x00000100u, tq4(t));
+    ap = a;
   }
-  s[8] = last ? s[6] : (int)(nlo & 0xff);
-  int h[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) h[i] = s[2 * i + 1] - ((s[2 * i] + s[2 * i + 2]) >> 1);
-  int hp = __shfl_up_sync(FULL, h[3], 1);
-  if (first) hp = h[0];
-  out[0] = s[0] + tq4(h[0] + hp);
-#pragma unroll
-  for (int i = 1; i < 4; i++) out[i] = s[2 * i] + tq4(h[i] + h[i - 1]);
 }
 
 // Raw words of the two prediction rows of one step (both rows lie in the same block row).
