@@ -431,16 +431,26 @@ def main():
                 pass
         dist.broadcast(ok, 0)
         if int(ok.item()):
-            registered = True
             for k, (sh, dt) in shapes.items():
                 maps[k] = np.memmap(os.path.join(shm_dir, k), dtype=dt, mode="r+", shape=sh)
-                registered = ctx.host_register(maps[k]) and registered
             out_bufs = {}
             for s_ in sched:
                 t_, ppg = s_["t"], G >> s_["t"]  # pairs per GOP at this level
                 for name in ("high", "motion", "motion_filtered"):
                     out_bufs[f"{name}_{t_}"] = maps[f"{name}_{t_}"][g0 * ppg:g1 * ppg]
             out_bufs[f"low_{T-1}"] = maps[f"low_{T-1}"][g0:g1 + 1]
+            # first touch: every rank (already bound to its GPU's NUMA node) faults in ITS slices before anyone
+            # page-locks the files, so a rank's device-to-host copies land in memory next to its GPU instead
+            # of wherever the first registering rank put the whole file
+            for k, v in out_bufs.items():
+                if k != f"low_{T-1}" or rank == 0:
+                    v[...] = 0
+                else:
+                    v[1:] = 0  # frame g0 belongs to the previous shard
+            barrier()
+            registered = True
+            for k in shapes:
+                registered = ctx.host_register(maps[k]) and registered
             gather_note = (f"rank slices written in place into shared sub-band files in {shm_dir} "
                            f"({need / 1e6:.0f} MB, reference file layout), "
                            + ("page-locked by every rank: the device-to-host copies are the gather"

@@ -8,9 +8,9 @@
 #include <cstdio>
 #include <cstring>
 
-enum Op { VABS4, LOP3, PRMT, SHF, IADD3, IMAD, DP4A, HFMA2, VIADD2, VMNMX2, LEAHI, NOPS };
+enum Op { VABS4, LOP3, PRMT, SHF, IADD3, IMAD, DP4A, HFMA2, VIADD2, VMNMX2, LEAHI, IMADHI, NOPS };
 static const char *names[] = {"VABSDIFF4.U8.ACC", "LOP3", "PRMT", "SHF", "IADD3", "IMAD", "IDP.4A", "HFMA2",
-                              "VIADD.16x2", "VIMNMX.S16x2", "LEA.HI"};
+                              "VIADD.16x2", "VIMNMX.S16x2", "LEA.HI", "IMAD.HI.U32"};
 
 template <int OP>
 __device__ __forceinline__ void one(unsigned &d, unsigned a, unsigned b) {
@@ -25,6 +25,7 @@ __device__ __forceinline__ void one(unsigned &d, unsigned a, unsigned b) {
   if (OP == VIADD2) d = __vadd2(d, a);
   if (OP == VMNMX2) d = __vmaxs2(d, a) ^ b;
   if (OP == LEAHI) d = d + (d >> 30) + a;
+  if (OP == IMADHI) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(a), "r"(b));
 }
 
 // NA instructions of kind A and NB of kind B per iteration, on 8 independent chains
@@ -84,7 +85,8 @@ int main() {
   cudaMalloc(&d_cyc, 256 * sizeof(long long));
   printf("%s, %d SMs; one CTA of 1024 threads per SM, 8 independent chains per thread\n", p.name, nsm);
   SOLO(VABS4) SOLO(LOP3) SOLO(PRMT) SOLO(SHF) SOLO(IADD3) SOLO(IMAD) SOLO(DP4A) SOLO(HFMA2) SOLO(VIADD2)
-  SOLO(VMNMX2) SOLO(LEAHI)
+  SOLO(VMNMX2) SOLO(LEAHI) SOLO(IMADHI)
+  PAIR(IMADHI, LOP3) PAIR(IMADHI, IMAD) PAIR(IMADHI, DP4A)
   PAIR(VABS4, LOP3) PAIR(VABS4, PRMT) PAIR(VABS4, SHF) PAIR(VABS4, IMAD) PAIR(VABS4, DP4A) PAIR(VABS4, HFMA2)
   PAIR(LOP3, IMAD) PAIR(LOP3, DP4A) PAIR(LOP3, HFMA2) PAIR(IMAD, DP4A) PAIR(IMAD, HFMA2) PAIR(PRMT, SHF)
   printf("%-18s x3 + IMAD x1     : %7.1f thread-instr/clk/SM\n", names[VABS4], run<VABS4, IMAD, 3, 1>(d_out, d_cyc, nsm));

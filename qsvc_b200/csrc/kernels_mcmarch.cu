@@ -139,8 +139,7 @@ struct Marcher {
   uint8_t *out;
   int *h_pred, *h_res;
   int is_I;
-  unsigned in_pre;  // input bytes of output row in_pre_row, loaded one output row ahead
-  int in_pre_row;
+  unsigned in_pre;  // input bytes of the next output row, loaded one output row ahead
   // plane pointers are recomputed where the (rare) general paths need them
   __device__ __forceinline__ const uint8_t *V0() const {
     return q.v + ((long long)(q.f0 + pair) * 3 + c) * q.v_plane_stride;
@@ -306,11 +305,10 @@ struct Marcher {
         sw[1] = t.y;
       }
     } else {
-      sw[0] = in_pre_row == e ? in_pre : load_in<NOUT>(e);
-      if (e + 1 < og1) {  // the next output row's input is in flight until it is needed
-        in_pre = load_in<NOUT>(e + 1);
-        in_pre_row = e + 1;
-      }
+      // output rows arrive in order from og0 (run() loaded that one): the next row's input is in flight
+      // until it is needed, and no load sits between the scoreboard wait and this row's bytes
+      sw[0] = in_pre;
+      if (e + 1 < og1) in_pre = load_in<NOUT>(e + 1);
     }
     if (!owner) return;
 #pragma unroll
@@ -421,7 +419,6 @@ struct Marcher {
     half3 = q.Ya >> 3;
     cur_by = -1;
     in_pre = 0;
-    in_pre_row = -1 << 30;
     my0 = my1 = col0 = col1 = sa = sb = 0;
     xin0 = xin1 = true;
     fastrow = false;
@@ -452,6 +449,7 @@ struct Marcher {
       }
       return;
     }
+    in_pre = load_in<(8 >> NLEV)>(og0);
     int t0, t_last;
     if (NLEV == 1) {
       t0 = max(0, og0 - 1);

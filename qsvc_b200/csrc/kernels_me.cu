@@ -142,18 +142,40 @@ __global__ void __launch_bounds__(128) k_search16(SearchParams q) {
   const int y = lane >> 1, xh = (lane & 1) * 8;
   int p[8];
   {
+    // 16 bytes per lane; the row origin is only short-aligned in general (texture::alloc's shifted rows)
     const short *row = q.img.row(ps, luby + y) + lubx + xh;
+    const unsigned al = (unsigned)(uintptr_t)row & 15u;
+    if (al == 0) {
+      const uint4 t = *reinterpret_cast<const uint4 *>(row);
+      const unsigned w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-    for (int i = 0; i < 8; i++) p[i] = row[i];
+      for (int i = 0; i < 4; i++) {
+        p[2 * i] = (short)(w[i] & 0xffffu);
+        p[2 * i + 1] = (int)w[i] >> 16;
+      }
+    } else if ((al & 3u) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const unsigned w = *reinterpret_cast<const unsigned *>(row + 2 * i);
+        p[2 * i] = (short)(w & 0xffffu);
+        p[2 * i + 1] = (int)w >> 16;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = row[i];
+    }
   }
-  if (lane < 18) {
-    const short *row0 = q.img.row(r0, luby + c[MV_PREV_Y] - 1 + lane) + lubx + c[MV_PREV_X] - 1;
-    const short *row1 = q.img.row(r1, luby + c[MV_NEXT_Y] - 1 + lane) + lubx + c[MV_NEXT_X] - 1;
-    short *d0 = sR[warp][0] + lane * RP, *d1 = sR[warp][1] + lane * RP;
+  // the two 18 x 18 windows, one window row per instruction: lanes 0..17 read consecutive samples (one
+  // or two sectors per load instead of eighteen rows)
+  {
+    const int wy0 = luby + c[MV_PREV_Y] - 1, wx0 = lubx + c[MV_PREV_X] - 1 + lane;
+    const int wy1 = luby + c[MV_NEXT_Y] - 1, wx1 = lubx + c[MV_NEXT_X] - 1 + lane;
+    if (lane < 18) {
 #pragma unroll
-    for (int i = 0; i < 18; i++) {
-      d0[i] = row0[i];
-      d1[i] = row1[i];
+      for (int r = 0; r < 18; r++) {
+        sR[warp][0][r * RP + lane] = q.img.row(r0, wy0 + r)[wx0];
+        sR[warp][1][r * RP + lane] = q.img.row(r1, wy1 + r)[wx1];
+      }
     }
   }
   __syncwarp();
