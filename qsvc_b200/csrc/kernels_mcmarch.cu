@@ -287,7 +287,7 @@ struct Marcher {
   template <int NOUT>
   __device__ __forceinline__ unsigned load_in(int e) const {
     if (!owner) return 0;
-    const uint8_t *p = in + (long long)e * OW + (x >> NLEV);
+    const uint8_t *p = in + (unsigned)(e * OW + (x >> NLEV));  // a component plane is far below 4 GB
     if (NOUT == 1) return *p;
     if (NOUT == 2) return *reinterpret_cast<const unsigned short *>(p);
     return *reinterpret_cast<const unsigned *>(p);
@@ -300,7 +300,7 @@ struct Marcher {
     unsigned sw[2] = {0, 0}, ow[2] = {0, 0}, pw[2] = {0, 0};
     if (NOUT == 8) {
       if (owner) {
-        const uint2 t = *reinterpret_cast<const uint2 *>(in + (long long)e * OW + x);
+        const uint2 t = *reinterpret_cast<const uint2 *>(in + (unsigned)(e * OW + x));
         sw[0] = t.x;
         sw[1] = t.y;
       }
@@ -332,7 +332,7 @@ struct Marcher {
       ow[k >> 2] |= (unsigned)o << (8 * (k & 3));
       pw[k >> 2] |= (unsigned)(p[k] & 0xff) << (8 * (k & 3));
     }
-    const long long idx = (long long)e * OW + (x >> NLEV);
+    const unsigned idx = (unsigned)(e * OW + (x >> NLEV));
     uint8_t *po = pout();
     if (NOUT == 1) {
       out[idx] = (uint8_t)ow[0];
