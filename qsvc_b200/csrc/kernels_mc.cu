@@ -3,6 +3,8 @@
 // Reference: decorrelate.cpp:69-189 (predict, with and without block_overlaping),
 // :841-848 (clip), :920-929 / :1009-1022 / :1038-1066 (residue, re-bias,
 // inverse), :799-816 / :940-953 (histograms); update.cpp:71-148 (update).
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 #define COUNT(L) (++*(L).counter)
@@ -615,6 +617,211 @@ __global__ void __launch_bounds__(256) k_update_batch(UpdateBatchParams q) {
   if (active) *target = cur;
 }
 
+// ---- the same for a dyadic factor (uf * 256 integral: the codec's 0.25) ----
+// With uf = j / 256 every step of the reference's chain  ref = (short)clamp(float(ref) +- residue * uf, 0, 255)
+// is exact in float and equals the integer saturating add  ref = clamp(ref + ((+-residue * j) >> 8), 0, 255):
+// ref is integral, so truncating a non-negative sum is its floor and the floor moves onto the addend, and a
+// negative sum clamps to 0 either way.  Saturating adds compose -- a run of them is x -> clamp(x + A, L, H), and
+// run g after run f is (Af + Ag, clamp(Lf + Ag, Lg, Hg), clamp(Hf + Ag, Lg, Hg)) -- so the long chains of the
+// targets on the picture edge (every source that clip() folds onto them, in order) are evaluated by a warp: a
+// lane composes one block's contributions, an ordered tree of shuffles composes the lanes.  Targets inside the
+// picture take at most one contribution per block.  One CTA = one 16x16 tile of one frame, all three components
+// (they share the block lists and the geometry), both passes.
+struct SatAdd {
+  int A, L, H;
+};
+static constexpr int SAT_BIG = 1 << 24;
+__device__ __forceinline__ void sat_push(SatAdd &f, int k) {  // ... then x -> clamp(x + k, 0, 255)
+  f.A += k;
+  f.L = min(max(f.L + k, 0), 255);
+  f.H = min(max(f.H + k, 0), 255);
+}
+__device__ __forceinline__ SatAdd sat_then(const SatAdd &f, const SatAdd &g) {  // g after f
+  SatAdd r;
+  r.A = f.A + g.A;
+  r.L = min(max(f.L + g.A, g.L), g.H);
+  r.H = min(max(f.H + g.A, g.L), g.H);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_update_dyadic(UpdateBatchParams q, int j256) {
+  __shared__ int4 s_geo[256];  // per listed block, raster order: displaced origin (oy, ox), source origin (sy0, sx0)
+  __shared__ int s_ids[256];
+  __shared__ int s_warp[8];
+  __shared__ int s_count, s_nheavy;
+  __shared__ int s_hp[64];       // threads that own a target on the picture edge
+  __shared__ int s_hcur[3][64];  // ... and the running values of those targets
+  const int frame = q.frame0 + blockIdx.z;
+  const int tile_x0 = blockIdx.x * 16, tile_y0 = blockIdx.y * 16;
+  const int tx = tile_x0 + (threadIdx.x & 15), ty = tile_y0 + (threadIdx.x >> 4);
+  const int tile_x1 = min(tile_x0 + 15, q.X - 1), tile_y1 = min(tile_y0 + 15, q.Y - 1);
+  const bool active = tx < q.X && ty < q.Y;
+  const bool heavy = active && (tx == 0 || ty == 0 || tx == q.X - 1 || ty == q.Y - 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long plane = (long long)q.BY * q.BX;
+  const int ntiles = q.tiles_x * q.tiles_y, tile = blockIdx.y * q.tiles_x + blockIdx.x;
+  const int cw = q.X >> 1, ch = q.Y >> 1;  // residue[1|2] only exists in its top-left quarter
+  const long long coff1 = (long long)q.X * q.Y, coff2 = coff1 + (long long)cw * ch;
+  const int jj = q.inverse ? -j256 : j256;
+
+  short *target[3] = {nullptr, nullptr, nullptr};
+  int cur[3] = {0, 0, 0};
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      target[c] = q.ref.row(c * q.slots_per_comp + (frame - q.frame0), ty) + tx;
+      cur[c] = *target[c];
+    }
+  }
+  // ordered list of the edge targets of this tile (at most 60)
+  int my_h = -1;
+  {
+    const unsigned m = __ballot_sync(0xffffffffu, heavy);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int prefix = 0;
+    for (int w = 0; w < warp; w++) prefix += s_warp[w];
+    if (heavy) {
+      my_h = prefix + __popc(m & ((1u << lane) - 1));
+      s_hp[my_h] = threadIdx.x;
+#pragma unroll
+      for (int c = 0; c < 3; c++) s_hcur[c][my_h] = cur[c];
+    }
+    if (threadIdx.x == 255) s_nheavy = prefix + __popc(m);
+    __syncthreads();
+  }
+  const int nheavy = s_nheavy;
+
+  for (int pass = 0; pass < 2; pass++) {
+    // frame k first receives pair k-1's NEXT update, then pair k's PREV update
+    const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
+    if (pair < 0 || pair >= q.n_pairs || q.types[pair] != 'B') continue;  // uniform per CTA
+    const int pd = pair * 2 + dir;
+    const short *mvx = q.mv + (long long)pair * 4 * plane + (long long)(dir ? MV_NEXT_X : MV_PREV_X) * plane;
+    const short *mvy = mvx + plane;
+    const uint8_t *res = q.high + (long long)pair * q.high_stride;
+    // addend of source sample (ry, rx) of component c
+    auto addend = [&](int c, int ry, int rx) -> int {
+      int r = 0;
+      if (c == 0) r = (int)res[(long long)ry * q.X + rx] - 128;
+      else if (ry < ch && rx < cw) r = (int)res[(c == 1 ? coff1 : coff2) + (long long)ry * cw + rx] - 128;
+      return (r * jj) >> 8;
+    };
+    auto geometry = [&](int b) -> int4 {
+      const int byy = b / q.BX, bxx = b - byy * q.BX;
+      return make_int4(byy * q.bs + mvy[b], bxx * q.bs + mvx[b], byy * q.bs, bxx * q.bs);
+    };
+    // n listed blocks (s_geo, raster order) onto this tile's targets
+    auto apply = [&](int n) {
+      if (active && !heavy) {
+        for (int k = 0; k < n; k++) {
+          const int4 g = s_geo[k];
+          const int y = ty - g.x, x = tx - g.y;
+          if ((unsigned)y < (unsigned)q.bs && (unsigned)x < (unsigned)q.bs) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) cur[c] = min(max(cur[c] + addend(c, g.z + y, g.w + x), 0), 255);
+          }
+        }
+      }
+      for (int h = warp; h < nheavy; h += 8) {  // warp-uniform
+        const int tid = s_hp[h];
+        const int hx = tile_x0 + (tid & 15), hy = tile_y0 + (tid >> 4);
+        SatAdd acc[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) acc[c] = SatAdd{0, -SAT_BIG, SAT_BIG};
+        for (int base = 0; base < n; base += 32) {
+          SatAdd f[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) f[c] = SatAdd{0, -SAT_BIG, SAT_BIG};
+          if (base + lane < n) {
+            const int4 g = s_geo[base + lane];
+            // source rows y in [0,bs) with clip(oy + y) == hy, in increasing order (edge targets collect every
+            // source that clip() folds onto them); the same for the columns
+            int ylo = (hy == 0) ? 0 : hy - g.x, yhi = (hy == q.Y - 1) ? q.bs - 1 : hy - g.x;
+            int xlo = (hx == 0) ? 0 : hx - g.y, xhi = (hx == q.X - 1) ? q.bs - 1 : hx - g.y;
+            ylo = max(ylo, 0), yhi = min(yhi, q.bs - 1);
+            xlo = max(xlo, 0), xhi = min(xhi, q.bs - 1);
+            for (int y = ylo; y <= yhi; y++)
+              for (int x = xlo; x <= xhi; x++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) sat_push(f[c], addend(c, g.z + y, g.w + x));
+              }
+          }
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              SatAdd g;
+              g.A = __shfl_down_sync(0xffffffffu, f[c].A, off);
+              g.L = __shfl_down_sync(0xffffffffu, f[c].L, off);
+              g.H = __shfl_down_sync(0xffffffffu, f[c].H, off);
+              if ((lane & (2 * off - 1)) == 0) f[c] = sat_then(f[c], g);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 3; c++) acc[c] = sat_then(acc[c], f[c]);  // lane 0 holds the 32 blocks' run
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) s_hcur[c][h] = min(max(s_hcur[c][h] + acc[c].A, acc[c].L), acc[c].H);
+        }
+      }
+    };
+
+    const int total = q.cnt[(long long)pd * ntiles + tile];
+    __syncthreads();  // the previous pass is done with s_geo
+    if (total <= q.cap) {
+      // short list: rank sort back into raster order (ids are distinct)
+      if ((int)threadIdx.x < total) s_ids[threadIdx.x] = q.list[((long long)pd * ntiles + tile) * q.cap + threadIdx.x];
+      __syncthreads();
+      if ((int)threadIdx.x < total) {
+        const int me = s_ids[threadIdx.x];
+        int rank = 0;
+        for (int k = 0; k < total; k++) rank += s_ids[k] < me;
+        s_geo[rank] = geometry(me);
+      }
+      __syncthreads();
+      apply(total);
+    } else {
+      // overflow: ordered scan of every block within reach of the tile (blocks folded onto an edge)
+      const int reach = q.reach[pd];
+      const int by_lo = max(0, (tile_y0 - reach - q.bs + 1 + (q.bs - 1) * (tile_y0 - reach - q.bs + 1 > 0)) / q.bs);
+      const int by_hi = min(q.BY - 1, (tile_y1 + reach) / q.bs);
+      const int bx_lo = max(0, (tile_x0 - reach - q.bs + 1 + (q.bs - 1) * (tile_x0 - reach - q.bs + 1 > 0)) / q.bs);
+      const int bx_hi = min(q.BX - 1, (tile_x1 + reach) / q.bs);
+      const int nbw = max(bx_hi - bx_lo + 1, 0), nbh = max(by_hi - by_lo + 1, 0);
+      const int nblocks = nbw * nbh;
+      for (int base = 0; base < nblocks; base += 256) {
+        __syncthreads();
+        bool hit = false;
+        int4 g = make_int4(0, 0, 0, 0);
+        if (base + (int)threadIdx.x < nblocks) {
+          const int k = base + threadIdx.x;
+          const int cby = by_lo + k / nbw, cbx = bx_lo + k % nbw;
+          g = geometry(cby * q.BX + cbx);
+          const int fy0 = iclamp(g.x, 0, q.Y - 1), fy1 = iclamp(g.x + q.bs - 1, 0, q.Y - 1);
+          const int fx0 = iclamp(g.y, 0, q.X - 1), fx1 = iclamp(g.y + q.bs - 1, 0, q.X - 1);
+          hit = fy0 <= tile_y1 && fy1 >= tile_y0 && fx0 <= tile_x1 && fx1 >= tile_x0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int prefix = 0;
+        for (int w = 0; w < warp; w++) prefix += s_warp[w];
+        if (hit) s_geo[prefix + __popc(m & ((1u << lane) - 1))] = g;
+        if (threadIdx.x == 255) s_count = prefix + __popc(m);
+        __syncthreads();
+        apply(s_count);
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) *target[c] = (short)(heavy ? s_hcur[c][my_h] : cur[c]);
+  }
+}
+
 void launch_update_bin(const Launch &L, const UpdateBatchParams &q) {
   if (q.n_pairs <= 0) return;
   ProfScope ps_(L, KC_UPDATE);
@@ -623,9 +830,24 @@ void launch_update_bin(const Launch &L, const UpdateBatchParams &q) {
   COUNT(L);
 }
 
+// uf = j / 256 with a small integral j: every product and sum of the reference's float chain is exact
+static bool update_dyadic(float uf, int *j256) {
+  const float j = uf * 256.0f;
+  if (!(j == (float)(int)j) || j > 1024.0f || j < -1024.0f) return false;
+  *j256 = (int)j;
+  return true;
+}
+
 void launch_update_batch(const Launch &L, const UpdateBatchParams &q, int nframes) {
   if (nframes <= 0) return;
   ProfScope ps_(L, KC_UPDATE);
+  int j256 = 0;
+  static const int allow = getenv("QSVC_UPDATE_DYADIC") ? atoi(getenv("QSVC_UPDATE_DYADIC")) : 1;
+  if (allow && update_dyadic(q.uf, &j256)) {
+    k_update_dyadic<<<dim3(q.tiles_x, q.tiles_y, nframes), 256, 0, L.stream>>>(q, j256);
+    COUNT(L);
+    return;
+  }
   k_update_batch<<<dim3(q.tiles_x, q.tiles_y, nframes * 3), 256, 0, L.stream>>>(q);
   COUNT(L);
 }

@@ -237,3 +237,32 @@ def test_pinned_upload_overlap_does_not_race_the_decorrelate(fused, ref):
         for t in range(1, TRLs):
             for name in ("motion", "motion_filtered", "high", "low", "frame_types"):
                 _same(f"{name}_{t}", got[f"{name}_{t}"], want[f"{name}_{t}"])
+
+
+def _random_update_case(X, Y, bs, n, reach, seed, types):
+    """Random frames, residues and motion fields with vectors of up to `reach` "pixels" (update applies
+    the quarter-pel vectors of the upper levels as whole pixels, A.4): most blocks near the picture
+    borders fold onto the edge rows / columns, whose targets then take long ordered chains."""
+    rng = np.random.default_rng(seed)
+    fb = X * Y * 3 // 2
+    frames = rng.integers(0, 256, (n + 1, fb), dtype=np.uint8)
+    # residues around 128 with a heavy tail, so that chains really saturate at both ends
+    high = np.clip(rng.normal(128, 40, (n, fb)), 0, 255).astype(np.uint8)
+    mv = rng.integers(-reach, reach + 1, (n, 4, Y // bs, X // bs)).astype(np.int16)
+    mv[0, :, ::2] //= 8  # one field with moderate vectors in every other block row: short lists and long ones
+    return frames, high, mv, types.encode()
+
+
+@pytest.mark.parametrize("uf", [0.25, 0.5, 1.0, 0.3])
+@pytest.mark.parametrize("X,Y,reach", [(640, 352, 511), (320, 176, 127), (1920, 1080, 511)])
+def test_update_with_long_vectors_matches_oracle(ctx, X, Y, reach, uf):
+    """Tile lists that overflow into the ordered scan, targets on the picture edge that collect
+    thousands of contributions (the composed saturating adds of the dyadic kernel), 'I' pairs."""
+    from oracle import oracle as orc
+    orc.build()
+    n = 2 if X > 1000 else 4
+    frames, high, mv, types = _random_update_case(X, Y, 16, n, reach, 1000 + X + reach, "BIBB"[:n] if n > 2 else "BB")
+    want = orc.update(frames, high, mv, types, X, Y, 16, uf)
+    _same(f"update uf={uf}", ctx.update(frames, high, mv, types, X, Y, 16, uf), want)
+    back = orc.update(want, high, mv, types, X, Y, 16, uf, inverse=True)
+    _same(f"un_update uf={uf}", ctx.un_update(want, high, mv, types, X, Y, 16, uf), back)
