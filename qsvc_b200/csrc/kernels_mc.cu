@@ -644,9 +644,11 @@ __device__ __forceinline__ SatAdd sat_then(const SatAdd &f, const SatAdd &g) {  
   return r;
 }
 
-__global__ void __launch_bounds__(256) k_update_dyadic(UpdateBatchParams q, int j256) {
-  __shared__ int4 s_geo[256];  // per listed block, raster order: displaced origin (oy, ox), source origin (sy0, sx0)
-  __shared__ int s_ids[256];
+__global__ void __launch_bounds__(256, 4) k_update_dyadic(UpdateBatchParams q, int j256) {
+  // per listed block, raster order: displaced origin (oy, ox), source origin (sy0, sx0)
+  __shared__ int4 s_geo[64];    // the short lists of the two passes (cap <= 32 each)
+  __shared__ int4 s_scan[256];  // one round of the overflow scan
+  __shared__ int s_ids[64];
   __shared__ int s_warp[8];
   __shared__ int s_count, s_nheavy;
   __shared__ int s_hp[64];       // threads that own a target on the picture edge
@@ -692,14 +694,48 @@ __global__ void __launch_bounds__(256) k_update_dyadic(UpdateBatchParams q, int 
   }
   const int nheavy = s_nheavy;
 
+  // frame k first receives pair k-1's NEXT update (pass 0), then pair k's PREV update (pass 1).  The short
+  // lists of both passes are fetched, sorted and resolved to block geometry together (warp 0: pass 0,
+  // warp 1: pass 1), so that the chain of dependent loads (count -> list -> vectors -> residues) is paid once.
+  int total[2];
+  bool valid[2];
+  const short *mvx_[2];
+  const uint8_t *res_[2];
+#pragma unroll
   for (int pass = 0; pass < 2; pass++) {
-    // frame k first receives pair k-1's NEXT update, then pair k's PREV update
     const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
-    if (pair < 0 || pair >= q.n_pairs || q.types[pair] != 'B') continue;  // uniform per CTA
-    const int pd = pair * 2 + dir;
-    const short *mvx = q.mv + (long long)pair * 4 * plane + (long long)(dir ? MV_NEXT_X : MV_PREV_X) * plane;
-    const short *mvy = mvx + plane;
-    const uint8_t *res = q.high + (long long)pair * q.high_stride;
+    valid[pass] = pair >= 0 && pair < q.n_pairs && q.types[pair] == 'B';  // uniform per CTA
+    const int pc = valid[pass] ? pair : 0;
+    total[pass] = valid[pass] ? q.cnt[(long long)(pc * 2 + dir) * ntiles + tile] : 0;
+    mvx_[pass] = q.mv + (long long)pc * 4 * plane + (long long)(dir ? MV_NEXT_X : MV_PREV_X) * plane;
+    res_[pass] = q.high + (long long)pc * q.high_stride;
+  }
+  auto geometry = [&](int pass, int b) -> int4 {
+    const int byy = b / q.BX, bxx = b - byy * q.BX;
+    return make_int4(byy * q.bs + mvx_[pass][plane + b], bxx * q.bs + mvx_[pass][b], byy * q.bs, bxx * q.bs);
+  };
+  if (warp < 2) {
+    const int pass = warp, n = total[pass];
+    const bool mine = valid[pass] && n <= q.cap && lane < n;
+    int me = 0;
+    if (mine) {
+      const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
+      me = q.list[((long long)(pair * 2 + dir) * ntiles + tile) * q.cap + lane];
+      s_ids[pass * 32 + lane] = me;
+    }
+    __syncwarp();
+    if (mine) {
+      // rank sort back into raster order (ids are distinct)
+      int rank = 0;
+      for (int k = 0; k < n; k++) rank += s_ids[pass * 32 + k] < me;
+      s_geo[pass * 32 + rank] = geometry(pass, me);
+    }
+  }
+  __syncthreads();
+
+  for (int pass = 0; pass < 2; pass++) {
+    if (!valid[pass]) continue;
+    const uint8_t *res = res_[pass];
     // addend of source sample (ry, rx) of component c
     auto addend = [&](int c, int ry, int rx) -> int {
       int r = 0;
@@ -707,15 +743,11 @@ __global__ void __launch_bounds__(256) k_update_dyadic(UpdateBatchParams q, int 
       else if (ry < ch && rx < cw) r = (int)res[(c == 1 ? coff1 : coff2) + (long long)ry * cw + rx] - 128;
       return (r * jj) >> 8;
     };
-    auto geometry = [&](int b) -> int4 {
-      const int byy = b / q.BX, bxx = b - byy * q.BX;
-      return make_int4(byy * q.bs + mvy[b], bxx * q.bs + mvx[b], byy * q.bs, bxx * q.bs);
-    };
-    // n listed blocks (s_geo, raster order) onto this tile's targets
-    auto apply = [&](int n) {
+    // n listed blocks (geo, raster order) onto this tile's targets
+    auto apply = [&](int n, const int4 *geo) {
       if (active && !heavy) {
         for (int k = 0; k < n; k++) {
-          const int4 g = s_geo[k];
+          const int4 g = geo[k];
           const int y = ty - g.x, x = tx - g.y;
           if ((unsigned)y < (unsigned)q.bs && (unsigned)x < (unsigned)q.bs) {
 #pragma unroll
@@ -734,7 +766,7 @@ __global__ void __launch_bounds__(256) k_update_dyadic(UpdateBatchParams q, int 
 #pragma unroll
           for (int c = 0; c < 3; c++) f[c] = SatAdd{0, -SAT_BIG, SAT_BIG};
           if (base + lane < n) {
-            const int4 g = s_geo[base + lane];
+            const int4 g = geo[base + lane];
             // source rows y in [0,bs) with clip(oy + y) == hy, in increasing order (edge targets collect every
             // source that clip() folds onto them); the same for the columns
             int ylo = (hy == 0) ? 0 : hy - g.x, yhi = (hy == q.Y - 1) ? q.bs - 1 : hy - g.x;
@@ -768,23 +800,12 @@ __global__ void __launch_bounds__(256) k_update_dyadic(UpdateBatchParams q, int 
       }
     };
 
-    const int total = q.cnt[(long long)pd * ntiles + tile];
-    __syncthreads();  // the previous pass is done with s_geo
-    if (total <= q.cap) {
-      // short list: rank sort back into raster order (ids are distinct)
-      if ((int)threadIdx.x < total) s_ids[threadIdx.x] = q.list[((long long)pd * ntiles + tile) * q.cap + threadIdx.x];
-      __syncthreads();
-      if ((int)threadIdx.x < total) {
-        const int me = s_ids[threadIdx.x];
-        int rank = 0;
-        for (int k = 0; k < total; k++) rank += s_ids[k] < me;
-        s_geo[rank] = geometry(me);
-      }
-      __syncthreads();
-      apply(total);
+    if (total[pass] <= q.cap) {
+      apply(total[pass], s_geo + pass * 32);
     } else {
       // overflow: ordered scan of every block within reach of the tile (blocks folded onto an edge)
-      const int reach = q.reach[pd];
+      const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
+      const int reach = q.reach[pair * 2 + dir];
       const int by_lo = max(0, (tile_y0 - reach - q.bs + 1 + (q.bs - 1) * (tile_y0 - reach - q.bs + 1 > 0)) / q.bs);
       const int by_hi = min(q.BY - 1, (tile_y1 + reach) / q.bs);
       const int bx_lo = max(0, (tile_x0 - reach - q.bs + 1 + (q.bs - 1) * (tile_x0 - reach - q.bs + 1 > 0)) / q.bs);
@@ -798,7 +819,7 @@ __global__ void __launch_bounds__(256) k_update_dyadic(UpdateBatchParams q, int 
         if (base + (int)threadIdx.x < nblocks) {
           const int k = base + threadIdx.x;
           const int cby = by_lo + k / nbw, cbx = bx_lo + k % nbw;
-          g = geometry(cby * q.BX + cbx);
+          g = geometry(pass, cby * q.BX + cbx);
           const int fy0 = iclamp(g.x, 0, q.Y - 1), fy1 = iclamp(g.x + q.bs - 1, 0, q.Y - 1);
           const int fx0 = iclamp(g.y, 0, q.X - 1), fx1 = iclamp(g.y + q.bs - 1, 0, q.X - 1);
           hit = fy0 <= tile_y1 && fy1 >= tile_y0 && fx0 <= tile_x1 && fx1 >= tile_x0;
@@ -808,10 +829,10 @@ __global__ void __launch_bounds__(256) k_update_dyadic(UpdateBatchParams q, int 
         __syncthreads();
         int prefix = 0;
         for (int w = 0; w < warp; w++) prefix += s_warp[w];
-        if (hit) s_geo[prefix + __popc(m & ((1u << lane) - 1))] = g;
+        if (hit) s_scan[prefix + __popc(m & ((1u << lane) - 1))] = g;
         if (threadIdx.x == 255) s_count = prefix + __popc(m);
         __syncthreads();
-        apply(s_count);
+        apply(s_count, s_scan);
       }
     }
   }
@@ -843,7 +864,7 @@ void launch_update_batch(const Launch &L, const UpdateBatchParams &q, int nframe
   ProfScope ps_(L, KC_UPDATE);
   int j256 = 0;
   static const int allow = getenv("QSVC_UPDATE_DYADIC") ? atoi(getenv("QSVC_UPDATE_DYADIC")) : 1;
-  if (allow && update_dyadic(q.uf, &j256)) {
+  if (allow && q.cap <= 32 && update_dyadic(q.uf, &j256)) {
     k_update_dyadic<<<dim3(q.tiles_x, q.tiles_y, nframes), 256, 0, L.stream>>>(q, j256);
     COUNT(L);
     return;
