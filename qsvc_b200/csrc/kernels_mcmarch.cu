@@ -523,7 +523,7 @@ __device__ __forceinline__ void mc_march(const MarchParams &q, int pair, int c, 
 // chunks of KC CTAs (about one segment) -> pair of the group -> component -> CTA of the chunk, so
 // that the even frame shared by pairs i-1 (NEXT) and i (PREV) is fetched from DRAM once.
 template <int NLEV, bool EXTRA>
-__global__ void __launch_bounds__(128, 5) k_mc_march(MarchParams q, int c0, int nc, int npairs, int G, int KC,
+__global__ void __launch_bounds__(128, 6) k_mc_march(MarchParams q, int c0, int nc, int npairs, int G, int KC,
                                                      int nb) {
   __shared__ int h_pred[EXTRA ? 256 : 1], h_res[EXTRA ? 256 : 1];
   const int per_chunk = G * nc * KC;
