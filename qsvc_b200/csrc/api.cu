@@ -696,11 +696,14 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
   if (ov < 0) return fail(QSVC_EINVAL, "bad block_overlaping");
   int ov_levels = 0;
   if (ov > 0) {
-    // decorrelate.cpp:84-88: levels of the per-block transform.  Areas no block covers would keep
-    // the previous pair's transformed leftovers and then go through the picture synthesis (A.2.6);
-    // that history is not reproduced for the overlapped mode: refuse such geometries.
-    if (X % bs != 0 || Y % bs != 0)
-      return fail(QSVC_EINVAL, "block_overlaping > 0 needs pictures that are multiples of the block size");
+    // decorrelate.cpp:84-88: levels of the per-block transform.  Areas no block covers keep the
+    // previous pair's transformed leftovers and then go through the picture synthesis (A.2.6): the
+    // literal path below replays exactly that (one prediction buffer per call, pairs in order), so
+    // ragged pictures are exact within one call; a later GOP shard would need the whole buffer of
+    // its left neighbour, which no exchange carries.
+    if ((X % bs != 0 || Y % bs != 0) && c->tail_fn)
+      return fail(QSVC_EINVAL, "block_overlaping > 0 on a picture that is not a multiple of the block size cannot be "
+                               "GOP-sharded (the whole prediction buffer is carried from pair to pair)");
     if (!predict_obmc_supported(bs << a, ov << a))
       return fail(QSVC_EINVAL, "block_overlaping=%d: extended block does not fit shared memory", ov);
     ov_levels = (int)rint(log((double)(ov << a)) / log(2.0));

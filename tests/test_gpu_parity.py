@@ -181,16 +181,49 @@ def test_overlapped_block_prediction_matches_oracle(ctx, X, Y, bs, sr, a, ov):
     assert np.array_equal(odd_g, odd_o)
 
 
-def test_overlapped_prediction_refuses_ragged_pictures(ctx):
-    """Areas no block covers would carry the previous pair's leftovers through the picture
-    synthesis; the library refuses instead of inventing them."""
-    from qsvc_b200._lib import QsvcError, QSVC_EINVAL
-    X, Y, bs = 64, 40, 16
-    clip = yuv.synthetic_clip(X, Y, 3, 1)
-    mv = np.zeros((1, 4, Y // bs, X // bs), np.int16)
-    with pytest.raises(QsvcError) as e:
-        ctx.decorrelate(clip[0::2], clip[1::2], mv, X, Y, bs, 4, 0, block_overlaping=2)
-    assert e.value.code == QSVC_EINVAL
+#                   X    Y  bs sr  a  ov
+OBMC_RAGGED_CASES = [
+    (96, 72, 16, 4, 0, 2),     # Y % bs != 0: uncovered rows in every sub-band go through the picture synthesis
+    (88, 64, 16, 4, 1, 2),     # X % bs != 0
+    (88, 72, 16, 4, 2, 4),     # both, quarter-pel, four levels
+    (104, 56, 16, 4, 1, 3),    # overlap that is not a power of two
+]
+
+
+@pytest.mark.parametrize("X,Y,bs,sr,a,ov", OBMC_RAGGED_CASES)
+def test_overlapped_prediction_on_ragged_pictures_matches_oracle(ctx, X, Y, bs, sr, a, ov):
+    """Areas no block covers carry the previous pair's analysed leftovers through the picture
+    synthesis (SURVEY.md A.2.6 with A.2.2): four pairs in one call, so that the carried buffer
+    matters, analysis and synthesis."""
+    clip = yuv.synthetic_clip(X, Y, 9, 37, max_shift=min(24, 3 * sr))
+    even, odd = clip[0::2], clip[1::2]
+    mv = orc.motion_estimate(even, odd, X, Y, bs, sr, a)
+    high_o, types_o, mvf_o, pred_o, rc = orc.decorrelate(even, odd, mv, X, Y, bs, sr, a, ov)
+    assert rc == 0
+    high_g, types_g, mvf_g, pred_g = ctx.decorrelate(even, odd, mv, X, Y, bs, sr, a, block_overlaping=ov,
+                                                     want_prediction=True)
+    assert types_g == types_o
+    bad = np.argwhere(pred_g != pred_o)
+    assert bad.size == 0, f"prediction: {len(bad)} differ, first {bad[:4].tolist()}"
+    assert np.array_equal(high_g, high_o) and np.array_equal(mvf_g, mvf_o)
+    odd_o, _ = orc.correlate(even, high_o, mvf_o, types_o, X, Y, bs, sr, a, ov)
+    odd_g, _ = ctx.correlate(even, high_o, mvf_o, types_o, X, Y, bs, sr, a, block_overlaping=ov)
+    assert np.array_equal(odd_g, odd_o)
+
+
+def test_overlapped_ragged_analysis_chain_matches_oracle(ctx):
+    """The same through the whole resident analysis and synthesis (update included)."""
+    X, Y, GOPs, TRLs, bs, sr, a, uf, ov = 88, 72, 1, 4, 16, 4, 1, 0.25, 2
+    clip = yuv.synthetic_clip(X, Y, GOPs * 2 ** (TRLs - 1) + 1, 41, max_shift=12)
+    ref = orc.analyze(clip, X, Y, TRLs, bs, sr, a, uf, block_overlaping=ov, block_size_min=bs)
+    got = ctx.analyze(clip, X, Y, GOPs, TRLs, bs, sr, a, uf, block_overlaping=ov, block_size_min=bs)
+    assert any(k.startswith("high_") for k in got)
+    for k, g in got.items():
+        v = ref[k]
+        if isinstance(v, (bytes, bytearray)):
+            assert bytes(g) == bytes(v), k
+        else:
+            assert np.array_equal(np.asarray(g), v), k
 
 
 def test_gop_shards_with_tail_exchange_match_the_whole_sequence(ctx):

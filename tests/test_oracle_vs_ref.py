@@ -46,6 +46,10 @@ OBMC_CASES = [
     (64, 48, 3, 16, 4, 1, 0.0, 2),
     (64, 64, 3, 16, 4, 2, 0.25, 4),
     (64, 48, 2, 16, 4, 1, 0.0, 3),
+    (96, 72, 4, 16, 4, 0, 0.25, 2),    # ragged pictures: uncovered areas carry the previous pair's leftovers
+    (88, 64, 3, 16, 4, 1, 0.25, 2),    #   through the picture synthesis (A.2.6 with A.2.2)
+    (88, 72, 3, 16, 4, 2, 0.0, 4),
+    (104, 56, 4, 16, 4, 1, 0.0, 3),
 ]
 
 
