@@ -89,6 +89,7 @@ struct qsvc_ctx {
   int tma_mode = 1;  // 0: plain loads in the sub-pixel fast path (env QSVC_TMA=0)
   int mc_mode = 0;  // same three values for the decorrelate / correlate path
   int me_fuse0 = 1;  // fused ME path: first pyramid level straight from the frames (env QSVC_ME_FUSE0=0: off)
+  int me_bytes0 = 1;  // fused ME path: level-0 search of invertible pyramids on byte planes (env QSVC_ME_BYTES0=0: off)
   int mc_ring = 1;  // byte-plane path: materialised border ring around the reference planes (env QSVC_MC_RING=0: off)
   int mc_kernel = 0;  // byte-plane path: 0 register march (k_mc_march, default: faster), 1 banded shared-memory pipeline (k_mc_tile); env QSVC_MC_KERNEL
   int me_mode = 0;  // 0: automatic, 1: literal (materialised) path only, 2: fused path required
@@ -364,8 +365,24 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     }
     short *bufs[2] = {mv_out + (long long)i0 * field, mv_tmp};
     int j = 0;
-    auto run_search = [&](int mode, int nby, int nbx, int lim) {
+    // invertible pyramid: level 0 is the frames' luma, which the sub-pixel levels need as byte planes
+    // anyway -- made here, so that the level-0 search can run on bytes too
+    const bool bytes0 = pr && bs == 16 && c->me_bytes0 != 0;
+    if (pr) {
+      launch_luma_to_plane(Lh, even + (long long)i0 * even_stride, even_stride, m + 1, Y, X, v[0],
+                           (long long)vbytes[0], pitch[0]);
+      launch_luma_to_plane(Lh, odd + (long long)i0 * odd_stride, odd_stride, m, Y, X,
+                           v[0] + (size_t)(m + 1) * vbytes[0], (long long)vbytes[0], pitch[0]);
+    }
+    auto run_search = [&](int mode, int nby, int nbx, int lim, bool level0 = false) {
       SearchParams q;
+      if (level0 && bytes0) {
+        q.v0 = v[0];
+        q.v0_slot_stride = (long long)vbytes[0];
+        q.v0_pitch = pitch[0];
+        q.v0_Y = Y;
+        q.v0_X = X;
+      }
       q.img = img;
       q.slots = d_slots;
       q.mv_out = bufs[(j + n_search - 1) & 1];
@@ -404,7 +421,7 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     } else {
       dwt_analyze(Lh, img, 0, nslots, Y, X, L);
     }
-    run_search(ME_INIT, desp(BY, L), desp(BX, L), 0);
+    run_search(ME_INIT, desp(BY, L), desp(BX, L), 0, L == 0);
     for (int l = L - 1; l >= 0; --l) {
       if (snap && l == 0 && fuse0) {
         launch_load_u8(Lh, img, 0, m + 1, even, even_stride, 0, i0, 1, Y, X);
@@ -414,15 +431,11 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
                            snap_pitch[l], false);
       else
         dwt_synthesize(Lh, img, 0, nslots, desp(Y, l), desp(X, l), 1);
-      run_search(ME_DESCEND, desp(BY, l), desp(BX, l), sr);
+      run_search(ME_DESCEND, desp(BY, l), desp(BX, l), sr, l == 0);
     }
     // byte planes of the level-0 interiors and their zero-high-band interpolations
     if (pr) {
-      // the descent restored the pictures exactly: V_0 is the frames' luma, every tile holds bytes
-      launch_luma_to_plane(Lh, even + (long long)i0 * even_stride, even_stride, m + 1, Y, X, v[0],
-                           (long long)vbytes[0], pitch[0]);
-      launch_luma_to_plane(Lh, odd + (long long)i0 * odd_stride, odd_stride, m, Y, X,
-                           v[0] + (size_t)(m + 1) * vbytes[0], (long long)vbytes[0], pitch[0]);
+      // the descent restored the pictures exactly: V_0 is the frames' luma (made above), every tile holds bytes
     } else {
       launch_plane_to_u8(Lh, img, 0, nslots, Y, X, v[0], (long long)vbytes[0], pitch[0], d_flags, tiles_x,
                          tiles_per_slot);
@@ -1072,6 +1085,7 @@ qsvc_ctx *qsvc_create(int device) {
   if (const char *e = getenv("QSVC_MC_KERNEL")) c->mc_kernel = atoi(e);
   if (const char *e = getenv("QSVC_MC_RING")) c->mc_ring = atoi(e);
   if (const char *e = getenv("QSVC_ME_FUSE0")) c->me_fuse0 = atoi(e);
+  if (const char *e = getenv("QSVC_ME_BYTES0")) c->me_bytes0 = atoi(e);
   if (const char *e = getenv("QSVC_OVERLAP")) c->overlap = atoi(e);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->me_budget = std::min<size_t>((size_t)64 << 30, free_b / 3);

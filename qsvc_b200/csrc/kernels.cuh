@@ -79,6 +79,11 @@ struct SearchParams {
   int nby, nbx;  // blocks searched at this level
   int bs, bd;    // block size and block border at this level
   int mode, lim;
+  // optional: the same level as dense byte planes (level 0 of an invertible pyramid: the frames' luma).
+  // Blocks whose two windows lie inside the picture are searched on bytes (VABSDIFF4); nullptr: never.
+  const uint8_t *v0 = nullptr;
+  long long v0_slot_stride = 0;
+  int v0_pitch = 0, v0_Y = 0, v0_X = 0;
 };
 void launch_search(const Launch &L, const SearchParams &q, int npairs);
 // sub-pixel search levels without materialised up-sampled images (kernels_subpel.cu)

@@ -140,7 +140,46 @@ __global__ void __launch_bounds__(128) k_search16(SearchParams q) {
   const int r0 = q.slots[3 * pair], r1 = q.slots[3 * pair + 1], ps = q.slots[3 * pair + 2];
   const int luby = by * 16, lubx = bx * 16;
   const int y = lane >> 1, xh = (lane & 1) * 8;
+  unsigned acc[18];  // [direction][window row shift 0..2][window column shift 0..2]
+#pragma unroll
+  for (int k = 0; k < 18; k++) acc[k] = 0;
+  // Byte planes of this level and both windows inside the picture (warp-uniform): the lane's eight block
+  // pixels are two words, each window row is four aligned words + funnel shifts, four SAD-ops per instruction.
+  bool packed = false;
+  if (q.v0) {
+    const int wy0 = luby + c[MV_PREV_Y] - 1, wx0 = lubx + c[MV_PREV_X] - 1;
+    const int wy1 = luby + c[MV_NEXT_Y] - 1, wx1 = lubx + c[MV_NEXT_X] - 1;
+    packed = wy0 >= 0 && wy0 + 18 <= q.v0_Y && wx0 >= 0 && wx0 + 18 <= q.v0_X && wy1 >= 0 && wy1 + 18 <= q.v0_Y &&
+             wx1 >= 0 && wx1 + 18 <= q.v0_X;
+    if (packed) {
+      const uint2 pw = *reinterpret_cast<const uint2 *>(q.v0 + (long long)ps * q.v0_slot_stride +
+                                                        (long long)(luby + y) * q.v0_pitch + lubx + xh);
+#pragma unroll
+      for (int d = 0; d < 2; d++) {
+        const int wy = d ? wy1 : wy0, wx = (d ? wx1 : wx0) + xh;
+        const uint8_t *base = q.v0 + (long long)(d ? r1 : r0) * q.v0_slot_stride + (long long)(wy + y) * q.v0_pitch;
+        const int o = wx & 3;  // bytes o .. o + 9 of the aligned words are the ten window samples of a row
+        const unsigned *w4 = reinterpret_cast<const unsigned *>(base + (wx - o));
+        const unsigned pw4 = (unsigned)q.v0_pitch >> 2;
+#pragma unroll
+        for (int wr = 0; wr < 3; wr++) {
+          unsigned w[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) w[k] = w4[wr * pw4 + k];  // the plane has 16 spare bytes per row
+#pragma unroll
+          for (int wc = 0; wc < 3; wc++) {
+            // byte offset o + wc in [0, 5]: words (o + wc) >> 2 .., shift 8 * ((o + wc) & 3)
+            const int b = o + wc, sh = 8 * (b & 3);
+            const unsigned a0 = b < 4 ? w[0] : w[1], a1 = b < 4 ? w[1] : w[2], a2 = b < 4 ? w[2] : w[3];
+            const unsigned lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+            acc[d * 9 + wr * 3 + wc] = __vsadu4(pw.x, lo) + __vsadu4(pw.y, hi);
+          }
+        }
+      }
+    }
+  }
   int p[8];
+  if (!packed) {
   {
     // 16 bytes per lane; the row origin is only short-aligned in general (texture::alloc's shifted rows)
     const short *row = q.img.row(ps, luby + y) + lubx + xh;
@@ -179,9 +218,6 @@ __global__ void __launch_bounds__(128) k_search16(SearchParams q) {
     }
   }
   __syncwarp();
-  unsigned acc[18];  // [direction][window row shift 0..2][window column shift 0..2]
-#pragma unroll
-  for (int k = 0; k < 18; k++) acc[k] = 0;
 #pragma unroll
   for (int d = 0; d < 2; d++) {
 #pragma unroll
@@ -195,6 +231,7 @@ __global__ void __launch_bounds__(128) k_search16(SearchParams q) {
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[d * 9 + wr * 3 + wc] = __sad(p[i], v[i + wc], acc[d * 9 + wr * 3 + wc]);
     }
+  }
   }
 #pragma unroll
   for (int k = 0; k < 18; k++) acc[k] = __reduce_add_sync(0xffffffffu, acc[k]);
