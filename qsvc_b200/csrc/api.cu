@@ -877,6 +877,8 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
     TRY(s.get((size_t)n_pairs + 16, (void **)&d_types));
     TRY(s.get((size_t)2 * n_pairs * ntiles * sizeof(int), (void **)&d_cnt));
     TRY(s.get((size_t)2 * n_pairs * ntiles * CAP * sizeof(int), (void **)&d_list));
+    int4 *d_geo = nullptr;  // the dyadic kernel reads the listed blocks' geometry instead of their vectors
+    if (update_is_dyadic(uf)) TRY(s.get((size_t)2 * n_pairs * ntiles * CAP * sizeof(int4), (void **)&d_geo));
     TRY(s.get((size_t)2 * n_pairs * sizeof(int) + 16, (void **)&d_reach));
     CU(cudaMemcpyAsync(d_types, types, (size_t)n_pairs, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(d_cnt, 0, (size_t)2 * n_pairs * ntiles * sizeof(int), c->stream));
@@ -888,6 +890,7 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
     q.types = d_types;
     q.cnt = d_cnt;
     q.list = d_list;
+    q.geo = d_geo;
     q.reach = d_reach;
     q.cap = CAP;
     q.n_pairs = n_pairs;
@@ -906,7 +909,29 @@ static int update_level(qsvc_ctx *c, int inverse, const uint8_t *in, long long i
     launch_update_bin(Lh, q);
     const size_t per_frame = (size_t)3 * Y * ((X + 7) & ~7) * sizeof(short);
     int max_frames = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pairs + 1, (c->me_budget / 4) / per_frame));
-    for (int k0 = 0; k0 <= n_pairs; k0 += max_frames) {
+    // dyadic factor, 4:2:0 geometry with word-aligned rows: luma is updated on the frames' own bytes, the chroma
+    // components go to luma-sized planes and back in one pass each (no generic transform passes, no luma planes)
+    const bool lean = update_is_dyadic(uf) && CAP <= 32 && X % 8 == 0 && Y % 2 == 0;
+    for (int k0 = 0; lean && k0 <= n_pairs; k0 += max_frames) {
+      const int m = std::min(max_frames, n_pairs + 1 - k0);
+      Scratch sc(c);
+      PlaneAlloc planes;
+      TRY(alloc_dense_planes(sc, 2 * m, Y, X, &planes));
+      launch_chroma_up_s16(Lh, planes.p, 0, m, in, in_stride, comp_offset(X, Y, 1), k0, Y, X);
+      launch_chroma_up_s16(Lh, planes.p, m, m, in, in_stride, comp_offset(X, Y, 2), k0, Y, X);
+      q.ref = planes.p;
+      q.ref.base -= (long long)m * planes.p.slot_stride;  // component c >= 1 of frame f: slot (c - 1) * m + f
+      q.slots_per_comp = m;
+      q.frame0 = k0;
+      q.luma_in = in;
+      q.luma_in_stride = in_stride;
+      q.luma_out = out;
+      q.luma_out_stride = out_stride;
+      launch_update_batch(Lh, q, m);
+      launch_ll1_store_u8(Lh, planes.p, 0, m, out, out_stride, comp_offset(X, Y, 1), k0, Y, X);
+      launch_ll1_store_u8(Lh, planes.p, m, m, out, out_stride, comp_offset(X, Y, 2), k0, Y, X);
+    }
+    for (int k0 = 0; !lean && k0 <= n_pairs; k0 += max_frames) {
       const int m = std::min(max_frames, n_pairs + 1 - k0);
       Scratch sc(c);
       PlaneAlloc planes;

@@ -209,11 +209,26 @@ struct UpdateBatchParams {
   const short *mv;           // the level's fields
   const char *types;         // device: frame types of the pairs
   int *cnt, *list, *reach;   // per (pair, direction): per tile block count and ids; largest |vector component|
+  int4 *geo = nullptr;       // optional, parallel to list: (displaced origin y, x, source origin y, x) of the listed blocks
   int cap;                   // list capacity per tile
   int n_pairs, BY, BX, bs, Y, X, tiles_x, tiles_y;
   float uf;
   int inverse;
+  // dyadic kernel only: the luma targets are the bytes of the frames themselves (frame f at luma_in + f *
+  // luma_in_stride, result to luma_out likewise) instead of int16 planes; nullptr: planes for all components
+  const uint8_t *luma_in = nullptr;
+  uint8_t *luma_out = nullptr;
+  long long luma_in_stride = 0, luma_out_stride = 0;
 };
+bool update_is_dyadic(float uf);  // launch_update_batch takes the integer kernel (which honours luma_in / luma_out)
+// chroma component of frames f0 .. f0 + n - 1 (bytes, (Y/2) x (X/2) at src + f * frame_stride + comp_off) -> planes
+// slot0 .. : the one-level zero-high-band 5/3 synthesis to Y x X (update.cpp's 4:2:0 -> 4:4:4), columns, then rows
+void launch_chroma_up_s16(const Launch &L, Plane dst, int slot0, int n, const uint8_t *src, long long frame_stride,
+                          long long comp_off, int f0, int Y, int X);
+// ... and back: the LL band of the one-level 5/3 analysis (rows, then columns) of planes slot0 .. stored as bytes
+// (truncating store, texture.cpp:139-141)
+void launch_ll1_store_u8(const Launch &L, Plane src, int slot0, int n, uint8_t *dst, long long frame_stride,
+                         long long comp_off, int f0, int Y, int X);
 void launch_update_bin(const Launch &L, const UpdateBatchParams &q);  // cnt and reach zeroed by the caller
 void launch_update_batch(const Launch &L, const UpdateBatchParams &q, int nframes);
 void launch_mv_reach(const Launch &L, const short *mv, int n, int *out);

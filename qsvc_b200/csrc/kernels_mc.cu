@@ -505,7 +505,10 @@ __global__ void __launch_bounds__(256) k_update_bin(UpdateBatchParams q) {
       for (int tx = fx0; tx <= fx1; tx++) {
         const int t = ty * q.tiles_x + tx;
         const int pos = atomicAdd(&cnt[t], 1);
-        if (pos < q.cap) list[(long long)t * q.cap + pos] = b;
+        if (pos < q.cap) {
+          list[(long long)t * q.cap + pos] = b;
+          if (q.geo) q.geo[((long long)pd * ntiles + t) * q.cap + pos] = make_int4(oy, ox, by * q.bs, bx * q.bs);
+        }
       }
   }
   reach = __reduce_max_sync(0xffffffffu, reach);
@@ -671,13 +674,18 @@ __global__ void __launch_bounds__(256, 4) k_update_dyadic(UpdateBatchParams q, i
   if (active) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      target[c] = q.ref.row(c * q.slots_per_comp + (frame - q.frame0), ty) + tx;
-      cur[c] = *target[c];
+      if (c == 0 && q.luma_in) {
+        cur[0] = q.luma_in[(long long)frame * q.luma_in_stride + (long long)ty * q.X + tx];
+      } else {
+        target[c] = q.ref.row(c * q.slots_per_comp + (frame - q.frame0), ty) + tx;
+        cur[c] = *target[c];
+      }
     }
   }
-  // ordered list of the edge targets of this tile (at most 60)
+  // ordered list of the edge targets of this tile (at most 60); none in the 97 % of tiles inside the picture
   int my_h = -1;
-  {
+  const bool edge_tile = tile_x0 == 0 || tile_y0 == 0 || tile_x1 == q.X - 1 || tile_y1 == q.Y - 1;  // CTA-uniform
+  if (edge_tile) {
     const unsigned m = __ballot_sync(0xffffffffu, heavy);
     if (lane == 0) s_warp[warp] = __popc(m);
     __syncthreads();
@@ -692,7 +700,7 @@ __global__ void __launch_bounds__(256, 4) k_update_dyadic(UpdateBatchParams q, i
     if (threadIdx.x == 255) s_nheavy = prefix + __popc(m);
     __syncthreads();
   }
-  const int nheavy = s_nheavy;
+  const int nheavy = edge_tile ? s_nheavy : 0;
 
   // frame k first receives pair k-1's NEXT update (pass 0), then pair k's PREV update (pass 1).  The short
   // lists of both passes are fetched, sorted and resolved to block geometry together (warp 0: pass 0,
@@ -715,20 +723,30 @@ __global__ void __launch_bounds__(256, 4) k_update_dyadic(UpdateBatchParams q, i
     return make_int4(byy * q.bs + mvx_[pass][plane + b], bxx * q.bs + mvx_[pass][b], byy * q.bs, bxx * q.bs);
   };
   if (warp < 2) {
-    const int pass = warp, n = total[pass];
-    const bool mine = valid[pass] && n <= q.cap && lane < n;
+    // the list entries are fetched before the counts are known (lanes beyond a count read unused slots), with
+    // their geometry when the binning pass stored it: count and list cost one memory round trip, not three
+    const int pass = warp;
+    const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
     int me = 0;
-    if (mine) {
-      const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
-      me = q.list[((long long)(pair * 2 + dir) * ntiles + tile) * q.cap + lane];
-      s_ids[pass * 32 + lane] = me;
+    int4 g = make_int4(0, 0, 0, 0);
+    if (valid[pass] && lane < q.cap) {
+      const long long at = ((long long)(pair * 2 + dir) * ntiles + tile) * q.cap + lane;
+      if (q.geo) {
+        g = q.geo[at];
+        me = (g.z << 16) | g.w;  // raster order of the blocks = order of their source origins (X <= 16384)
+      } else {
+        me = q.list[at];
+      }
     }
+    const int n = total[pass];
+    const bool mine = valid[pass] && n <= q.cap && lane < n;
+    if (mine) s_ids[pass * 32 + lane] = me;
     __syncwarp();
     if (mine) {
-      // rank sort back into raster order (ids are distinct)
+      // rank sort back into raster order (keys are distinct)
       int rank = 0;
       for (int k = 0; k < n; k++) rank += s_ids[pass * 32 + k] < me;
-      s_geo[pass * 32 + rank] = geometry(pass, me);
+      s_geo[pass * 32 + rank] = q.geo ? g : geometry(pass, me);
     }
   }
   __syncthreads();
@@ -839,8 +857,119 @@ __global__ void __launch_bounds__(256, 4) k_update_dyadic(UpdateBatchParams q, i
   __syncthreads();
   if (active) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) *target[c] = (short)(heavy ? s_hcur[c][my_h] : cur[c]);
+    for (int c = 0; c < 3; c++) {
+      const int v = heavy ? s_hcur[c][my_h] : cur[c];
+      if (c == 0 && q.luma_in)  // a byte either way: untouched input or a clamped sum
+        q.luma_out[(long long)frame * q.luma_out_stride + (long long)ty * q.X + tx] = (uint8_t)v;
+      else
+        *target[c] = (short)v;
+    }
   }
+}
+
+// ---- chroma 4:2:0 <-> luma-sized planes around the update (update.cpp:506-656) ----
+// Zero-high-band synthesis (5_3.cpp:81-94 with h = 0; dwt2d.cpp:139-172: columns, then rows) of a byte
+// component: T[2i] = c[i], T[2i+1] = (c[i] + c[i+1]) / 2, last odd row = c[last]; the same along the rows.
+// One thread: source rows i, i + 1 and source columns 4g .. 4g + 4 -> output rows 2i, 2i + 1, columns 8g .. 8g + 7
+// (two 16-byte stores).  X % 8 == 0.
+__global__ void __launch_bounds__(256) k_chroma_up_s16(Plane dst, int slot0, const uint8_t *__restrict__ src,
+                                                        long long frame_stride, long long comp_off, int f0, int Y,
+                                                        int X) {
+  const int hw = X >> 1, hh = Y >> 1, groups = hw >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= hh * groups) return;
+  const int i = idx / groups, g = idx - i * groups;
+  const uint8_t *c = src + (long long)(f0 + blockIdx.z) * frame_stride + comp_off;
+  const uint8_t *ra = c + (unsigned)(i * hw + 4 * g), *rb = i < hh - 1 ? ra + hw : ra;  // last odd row = last source row
+  const unsigned a4 = *reinterpret_cast<const unsigned *>(ra), b4 = *reinterpret_cast<const unsigned *>(rb);
+  const int nx = 4 * g + 4 < hw ? 4 : 3;  // last odd column = last source column
+  int te[5], to[5];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    te[k] = (a4 >> (8 * k)) & 0xff;
+    to[k] = (te[k] + (int)((b4 >> (8 * k)) & 0xff)) >> 1;
+  }
+  te[4] = ra[nx];
+  to[4] = (te[4] + (int)rb[nx]) >> 1;
+  unsigned we[4], wo[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    we[k] = (unsigned)te[k] | ((unsigned)((te[k] + te[k + 1]) >> 1) << 16);
+    wo[k] = (unsigned)to[k] | ((unsigned)((to[k] + to[k + 1]) >> 1) << 16);
+  }
+  *reinterpret_cast<uint4 *>(dst.row(slot0 + blockIdx.z, 2 * i) + 8 * g) = make_uint4(we[0], we[1], we[2], we[3]);
+  *reinterpret_cast<uint4 *>(dst.row(slot0 + blockIdx.z, 2 * i + 1) + 8 * g) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+}
+
+void launch_chroma_up_s16(const Launch &L, Plane dst, int slot0, int n, const uint8_t *src, long long frame_stride,
+                          long long comp_off, int f0, int Y, int X) {
+  if (n <= 0) return;
+  ProfScope ps_(L, KC_IMG);
+  const int work = (Y >> 1) * (X >> 3);
+  k_chroma_up_s16<<<dim3((work + 255) / 256, 1, n), 256, 0, L.stream>>>(dst, slot0, src, frame_stride, comp_off, f0, Y, X);
+  COUNT(L);
+}
+
+// LL band of one analysis level (dwt2d.cpp:76-119: rows, then columns; 5_3.cpp:39-52, even sizes) of a
+// luma-sized int16 plane, stored as bytes.  A CTA produces LL1_TR x LL1_TC outputs from a (2 TR + 3) x (2 TC + 4)
+// sample tile: row pass (low band only) into shared memory, column pass (low band only) to the frame.
+static constexpr int LL1_TR = 32, LL1_TC = 64, LL1_ROWS = 2 * LL1_TR + 3, LL1_COLS = 2 * LL1_TC + 4;
+__global__ void __launch_bounds__(256) k_ll1_store_u8(Plane src, int slot0, uint8_t *__restrict__ dst,
+                                                       long long frame_stride, long long comp_off, int f0, int Y,
+                                                       int X) {
+  __shared__ short sin[LL1_ROWS][LL1_COLS];  // sample columns 2 cx0 - 2 .. 2 cx0 + 2 TC + 1
+  __shared__ short RL[LL1_ROWS][LL1_TC];
+  const int slot = slot0 + blockIdx.z;
+  const int halfx = X >> 1, halfy = Y >> 1;
+  const int cx0 = blockIdx.x * LL1_TC, ry0 = blockIdx.y * LL1_TR;
+  for (int it = threadIdx.x; it < LL1_ROWS * (LL1_COLS / 2); it += 256) {
+    const int r = it / (LL1_COLS / 2), w = it - r * (LL1_COLS / 2);
+    const int y = 2 * ry0 - 2 + r, x = 2 * cx0 - 2 + 2 * w;
+    unsigned v = 0;
+    if (y >= 0 && y < Y && x >= 0 && x < X) v = *reinterpret_cast<const unsigned *>(src.row(slot, y) + x);
+    *reinterpret_cast<unsigned *>(&sin[r][2 * w]) = v;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < LL1_ROWS * LL1_TC; it += 256) {
+    const int r = it / LL1_TC, i = it - r * LL1_TC, gi = cx0 + i;
+    if (gi >= halfx) continue;
+    const short *s = &sin[r][2 * i + 2];  // s[k] = sample 2 gi + k of the row
+    const int s0 = s[0], s1 = s[1];
+    const int h = (short)(gi == halfx - 1 ? s1 - s0 : s1 - tdiv2(s0 + s[2]));
+    int l;
+    if (gi == 0) {
+      l = (short)(s0 + tdiv2(h));
+    } else {
+      const int hp = (short)(s[-1] - tdiv2(s[-2] + s0));
+      l = (short)(s0 + tdiv4(h + hp));
+    }
+    RL[r][i] = (short)l;
+  }
+  __syncthreads();
+  uint8_t *out = dst + (long long)(f0 + blockIdx.z) * frame_stride + comp_off;
+  for (int it = threadIdx.x; it < LL1_TR * LL1_TC; it += 256) {
+    const int j = it / LL1_TC, i = it - j * LL1_TC, gj = ry0 + j, gi = cx0 + i;
+    if (gj >= halfy || gi >= halfx) continue;
+    const int t0 = RL[2 * j + 2][i], t1 = RL[2 * j + 3][i];  // row-transformed samples of rows 2 gj, 2 gj + 1
+    const int h = (short)(gj == halfy - 1 ? t1 - t0 : t1 - tdiv2(t0 + RL[2 * j + 4][i]));
+    int l;
+    if (gj == 0) {
+      l = (short)(t0 + tdiv2(h));
+    } else {
+      const int hp = (short)(RL[2 * j + 1][i] - tdiv2(RL[2 * j][i] + t0));
+      l = (short)(t0 + tdiv4(h + hp));
+    }
+    out[(long long)gj * halfx + gi] = (uint8_t)l;  // truncation mod 256, no clamp
+  }
+}
+
+void launch_ll1_store_u8(const Launch &L, Plane src, int slot0, int n, uint8_t *dst, long long frame_stride,
+                         long long comp_off, int f0, int Y, int X) {
+  if (n <= 0) return;
+  ProfScope ps_(L, KC_DWT_ROWS);
+  k_ll1_store_u8<<<dim3(((X >> 1) + LL1_TC - 1) / LL1_TC, ((Y >> 1) + LL1_TR - 1) / LL1_TR, n), 256, 0, L.stream>>>(
+      src, slot0, dst, frame_stride, comp_off, f0, Y, X);
+  COUNT(L);
 }
 
 void launch_update_bin(const Launch &L, const UpdateBatchParams &q) {
@@ -859,12 +988,17 @@ static bool update_dyadic(float uf, int *j256) {
   return true;
 }
 
+bool update_is_dyadic(float uf) {
+  int j256;
+  static const int allow = getenv("QSVC_UPDATE_DYADIC") ? atoi(getenv("QSVC_UPDATE_DYADIC")) : 1;
+  return allow && update_dyadic(uf, &j256);
+}
+
 void launch_update_batch(const Launch &L, const UpdateBatchParams &q, int nframes) {
   if (nframes <= 0) return;
   ProfScope ps_(L, KC_UPDATE);
   int j256 = 0;
-  static const int allow = getenv("QSVC_UPDATE_DYADIC") ? atoi(getenv("QSVC_UPDATE_DYADIC")) : 1;
-  if (allow && q.cap <= 32 && update_dyadic(q.uf, &j256)) {
+  if (q.cap <= 32 && update_is_dyadic(q.uf) && update_dyadic(q.uf, &j256)) {
     k_update_dyadic<<<dim3(q.tiles_x, q.tiles_y, nframes), 256, 0, L.stream>>>(q, j256);
     COUNT(L);
     return;
