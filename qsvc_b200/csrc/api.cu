@@ -346,11 +346,11 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
     } else {
       launch_load_u8(Lh, img, 0, m + 1, even, even_stride, 0, i0, 1, Y, X);
       launch_load_u8(Lh, img, m + 1, m, odd, odd_stride, 0, i0, 1, Y, X);
-      launch_fill_border(Lh, img, 0, m + 1, Y, X, B);
+      launch_ring_s16(Lh, img, 0, m + 1, Y, X, B);  // compact planes: fill_border without the alias, one launch
     }
     if (n_copy > 0) {
       launch_load_u8(Lh, img, 2 * m + 1, n_copy, even, even_stride, 0, i0 + 1, 1, Y, X);
-      launch_fill_border(Lh, img, 2 * m + 1, n_copy, Y, X, B);
+      launch_ring_s16(Lh, img, 2 * m + 1, n_copy, Y, X, B);
     }
     if (!pr) {
       // carried reference[0]: one pass of the non-invertible pyramid (the sub-pixel

@@ -50,6 +50,8 @@ void launch_store_u8(const Launch &L, Plane src, int slot0, int nslots, uint8_t 
                      long long frame_stride, long long comp_off, int f0, int fstep, int h, int w);
 
 // fill_border ring of a plain bordered plane straight from the frames' luma (one launch)
+// fill_border of a compact plane (no row-pointer alias) from its own interior, one launch
+void launch_ring_s16(const Launch &L, Plane p, int slot0, int nslots, int Y, int X, int b);
 void launch_ring_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8_t *src, long long frame_stride,
                     int f0, int Y, int X, int b);
 

@@ -176,6 +176,37 @@ __global__ void __launch_bounds__(256) k_ring_u8(Plane p, int slot0, const uint8
   }
 }
 
+// The same from the plane's own interior (planes whose interior is already loaded).  Only for planes without
+// the row-pointer alias (compact planes: every row pointer shifted), where no ring cell is anybody's source.
+__global__ void __launch_bounds__(256) k_ring_s16(Plane p, int slot0, int Y, int X, int b) {
+  const int slot = slot0 + blockIdx.z;
+  const int W = X + 2 * b, nA = 2 * b * W, nB = 2 * b * Y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nA + nB; i += gridDim.x * blockDim.x) {
+    int y, x;
+    if (i < nA) {
+      const int r = i / W;
+      x = i - r * W - b;
+      y = r < b ? r - b : Y + (r - b);
+    } else {
+      const int j = i - nA;
+      y = j / (2 * b);
+      const int k = j - y * (2 * b);
+      x = k < b ? k - b : X + (k - b);
+    }
+    const int sy = y < 0 ? 0 : (y >= Y ? Y - 1 : y);
+    int sx = x < 0 ? 0 : (x >= X ? X - 1 : x);
+    if (y >= Y && x < 0) sx = X - 1;
+    p.row(slot, y)[x] = p.row(slot, sy)[sx];
+  }
+}
+
+void launch_ring_s16(const Launch &L, Plane p, int slot0, int nslots, int Y, int X, int b) {
+  if (nslots <= 0 || b <= 0) return;
+  ProfScope ps_(L, KC_IMG);
+  k_ring_s16<<<dim3(64, 1, nslots), 256, 0, L.stream>>>(p, slot0, Y, X, b);
+  COUNT(L);
+}
+
 void launch_ring_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8_t *src, long long frame_stride,
                     int f0, int Y, int X, int b) {
   if (nslots <= 0 || b <= 0) return;
