@@ -1610,48 +1610,72 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
       c->me_events.push_back(e);
     }
   }
+  // per-level parameters (analyze.py:144-151)
+  struct LevelPlan {
+    int n, sr, bs;
+  };
+  std::vector<LevelPlan> plan(p->TRLs);
   for (int t = 1; t < p->TRLs; t++) {
-    const int n = pictures / 2;
+    plan[t] = {pictures / 2, sr, bs};
+    c->levels[t].search_range = sr;
+    pictures = (pictures + 1) / 2;
+    sr = std::min(sr * 2, 128);       // analyze.py:144-147
+    bs = std::max(bs / 2, bs_min);    // analyze.py:149-151
+  }
+  // motion estimation of level t (two lanes: on the ME stream, frames of the resident clip)
+  auto run_me = [&](int t, const uint8_t *low) -> int {
+    const int n = plan[t].n, bsz = plan[t].bs;
     LevelResult &lv = c->levels[t];
-    lv.search_range = sr;
-    const long long field = 4LL * (Y / bs) * (X / bs);
+    const long long field = 4LL * (Y / bsz) * (X / bsz);
     // split (split.cpp:229-341) is index arithmetic: even k = frame 2k, odd i = frame 2i+1 of low_{t-1}
     const long long in_stride = lanes ? (fb << t) : 2 * fb;
     const uint8_t *even = lanes ? c->low0 : low, *odd = even + in_stride / 2;
-    c->cur_level = t;
-    {
-      std::unique_ptr<MeLane> lane_guard;
-      if (lanes) lane_guard.reset(new MeLane(c));
-      if (t == 1 && c->upload_gops > 0) {
-        const int per_gop = c->upload_gop_frames / 2;  // pairs of a GOP at level 1
-        for (int g = 0; g < c->upload_gops; g++) {
-          CU(cudaStreamWaitEvent(c->stream, c->upload_events[g], 0));
-          const long long f0 = (long long)g * per_gop;
-          TRY(me_level(c, even + f0 * in_stride, in_stride, odd + f0 * in_stride, in_stride, per_gop, X, Y, bs,
-                       p->border_size, sr, p->subpixel_accuracy, g == 0 ? p->first_gop_is_global_first : 0,
-                       lv.motion + f0 * field));
-        }
-      } else {
-        TRY(me_level(c, even, in_stride, odd, in_stride, n, X, Y, bs, p->border_size, sr, p->subpixel_accuracy,
-                     p->first_gop_is_global_first, lv.motion));
+    std::unique_ptr<MeLane> lane_guard;
+    if (lanes) lane_guard.reset(new MeLane(c));
+    if (t == 1 && c->upload_gops > 0) {
+      const int per_gop = c->upload_gop_frames / 2;  // pairs of a GOP at level 1
+      for (int g = 0; g < c->upload_gops; g++) {
+        CU(cudaStreamWaitEvent(c->stream, c->upload_events[g], 0));
+        const long long f0 = (long long)g * per_gop;
+        TRY(me_level(c, even + f0 * in_stride, in_stride, odd + f0 * in_stride, in_stride, per_gop, X, Y, bsz,
+                     p->border_size, plan[t].sr, p->subpixel_accuracy, g == 0 ? p->first_gop_is_global_first : 0,
+                     lv.motion + f0 * field));
       }
-      if (lanes) CU(cudaEventRecord(c->me_events[t], c->stream));
+    } else {
+      TRY(me_level(c, even, in_stride, odd, in_stride, n, X, Y, bsz, p->border_size, plan[t].sr, p->subpixel_accuracy,
+                   p->first_gop_is_global_first, lv.motion));
     }
+    if (lanes) CU(cudaEventRecord(c->me_events[t], c->stream));
+    return QSVC_OK;
+  };
+  // Two lanes: the ME lane is enqueued one level ahead of the decorrelate lane, so that whatever blocks the host
+  // inside a decorrelate (the frame-type decision, a GOP shard waiting for its neighbour's prediction tail)
+  // leaves the GPU with the next level's motion estimation to run.
+  if (lanes && p->TRLs > 1) TRY(run_me(1, low));
+  for (int t = 1; t < p->TRLs; t++) {
+    const int n = plan[t].n, bsz = plan[t].bs;
+    LevelResult &lv = c->levels[t];
+    const long long field = 4LL * (Y / bsz) * (X / bsz);
+    const long long in_stride = lanes ? (fb << t) : 2 * fb;
+    const uint8_t *even = lanes ? c->low0 : low, *odd = even + in_stride / 2;
+    c->cur_level = t;
+    if (!lanes) TRY(run_me(t, low));
+    else if (t + 1 < p->TRLs) TRY(run_me(t + 1, low));
     if (lanes) c->mv_ready = c->me_events[t];  // awaited inside, after the reference planes are up-sampled
     if (t == 1 && c->upload_gops > 0)
       // the decorrelate of level 1 reads the clip on this stream before it meets the ME lane
       // (which is the one that waited GOP by GOP): the whole upload has to have landed
       CU(cudaStreamWaitEvent(c->stream, c->upload_events[c->upload_gops - 1], 0));
     {
-      const int rc = mc_level(c, 1, even, in_stride, odd, in_stride, lv.motion, n, X, Y, bs, p->block_overlaping, sr,
-                              p->subpixel_accuracy, p->always_B, nullptr, lv.high, fb, &lv.types,
+      const int rc = mc_level(c, 1, even, in_stride, odd, in_stride, lv.motion, n, X, Y, bsz, p->block_overlaping,
+                              plan[t].sr, p->subpixel_accuracy, p->always_B, nullptr, lv.high, fb, &lv.types,
                               lv.motion_filtered, nullptr);
       const int rw = await_motion(c);  // nothing read it (no pairs): the lanes still have to meet
       if (rc != QSVC_OK) return rc;
       if (rw != QSVC_OK) return rw;
     }
     TRY(update_level(c, 0, even, in_stride, lv.high, fb, lv.motion_filtered, lv.types.c_str(), n, X, Y,
-                     bs, p->update_factor, lv.low, fb));
+                     bsz, p->update_factor, lv.low, fb));
     if (outs) {
       // stream this level's results to the host behind the next level's compute
       while ((int)c->level_events.size() <= t) {
@@ -1671,9 +1695,6 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
       if (o.low) CU(cudaMemcpyAsync(o.low, lv.low, (size_t)fb * (n + 1), cudaMemcpyDeviceToHost, c->copy_stream));
     }
     low = lv.low;
-    pictures = (pictures + 1) / 2;
-    sr = std::min(sr * 2, 128);       // analyze.py:144-147
-    bs = std::max(bs / 2, bs_min);    // analyze.py:149-151
   }
   c->cur_level = 0;
   CU(cudaEventRecord(c->ev3, c->stream));
