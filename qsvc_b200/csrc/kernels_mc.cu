@@ -647,7 +647,9 @@ __device__ __forceinline__ SatAdd sat_then(const SatAdd &f, const SatAdd &g) {  
   return r;
 }
 
-__global__ void __launch_bounds__(256, 4) k_update_dyadic(UpdateBatchParams q, int j256) {
+// perimeter != 0: blockIdx.x enumerates the tiles on the picture's perimeter (top row, bottom row, then left / right
+// column pairs); the tiles inside go through k_update_quad
+__global__ void __launch_bounds__(256, 4) k_update_dyadic(UpdateBatchParams q, int j256, int perimeter) {
   // per listed block, raster order: displaced origin (oy, ox), source origin (sy0, sx0)
   __shared__ int4 s_geo[64];    // the short lists of the two passes (cap <= 32 each)
   __shared__ int4 s_scan[256];  // one round of the overflow scan
@@ -657,14 +659,26 @@ __global__ void __launch_bounds__(256, 4) k_update_dyadic(UpdateBatchParams q, i
   __shared__ int s_hp[64];       // threads that own a target on the picture edge
   __shared__ int s_hcur[3][64];  // ... and the running values of those targets
   const int frame = q.frame0 + blockIdx.z;
-  const int tile_x0 = blockIdx.x * 16, tile_y0 = blockIdx.y * 16;
+  int tbx = blockIdx.x, tby = blockIdx.y;
+  if (perimeter) {
+    const int e = blockIdx.x;
+    if (e < q.tiles_x) {
+      tbx = e, tby = 0;
+    } else if (e < 2 * q.tiles_x) {
+      tbx = e - q.tiles_x, tby = q.tiles_y - 1;
+    } else {
+      const int k = e - 2 * q.tiles_x;
+      tbx = (k & 1) ? q.tiles_x - 1 : 0, tby = 1 + (k >> 1);
+    }
+  }
+  const int tile_x0 = tbx * 16, tile_y0 = tby * 16;
   const int tx = tile_x0 + (threadIdx.x & 15), ty = tile_y0 + (threadIdx.x >> 4);
   const int tile_x1 = min(tile_x0 + 15, q.X - 1), tile_y1 = min(tile_y0 + 15, q.Y - 1);
   const bool active = tx < q.X && ty < q.Y;
   const bool heavy = active && (tx == 0 || ty == 0 || tx == q.X - 1 || ty == q.Y - 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long plane = (long long)q.BY * q.BX;
-  const int ntiles = q.tiles_x * q.tiles_y, tile = blockIdx.y * q.tiles_x + blockIdx.x;
+  const int ntiles = q.tiles_x * q.tiles_y, tile = tby * q.tiles_x + tbx;
   const int cw = q.X >> 1, ch = q.Y >> 1;  // residue[1|2] only exists in its top-left quarter
   const long long coff1 = (long long)q.X * q.Y, coff2 = coff1 + (long long)cw * ch;
   const int jj = q.inverse ? -j256 : j256;
@@ -867,6 +881,161 @@ __global__ void __launch_bounds__(256, 4) k_update_dyadic(UpdateBatchParams q, i
   }
 }
 
+// The tiles inside the picture (no target on the picture edge, always 16 x 16): 64 threads, four horizontally
+// adjacent targets per thread, so that the per-tile work that is not arithmetic on targets (counts, lists, sorting,
+// addresses: 70 % of k_update_dyadic's instructions) is spread over four times the targets.  Luma targets are the
+// frames' bytes (q.luma_in / q.luma_out; X % 8 == 0).  grid (tiles_x - 2, tiles_y - 2, frames).
+__global__ void __launch_bounds__(64) k_update_quad(UpdateBatchParams q, int j256) {
+  __shared__ int4 s_geo[64];   // the short lists of the two passes (cap <= 32 each), raster order
+  __shared__ int4 s_scan[64];  // one round of the overflow scan
+  __shared__ int s_ids[64];
+  __shared__ int s_w[2], s_count;
+  const int frame = q.frame0 + blockIdx.z;
+  const int tbx = blockIdx.x + 1, tby = blockIdx.y + 1;
+  const int tile_x0 = tbx * 16, tile_y0 = tby * 16, tile_x1 = tile_x0 + 15, tile_y1 = tile_y0 + 15;
+  const int ty = tile_y0 + (threadIdx.x >> 2), tx0 = tile_x0 + 4 * (threadIdx.x & 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long plane = (long long)q.BY * q.BX;
+  const int ntiles = q.tiles_x * q.tiles_y, tile = tby * q.tiles_x + tbx;
+  const int cw = q.X >> 1, ch = q.Y >> 1;
+  const long long coff1 = (long long)q.X * q.Y, coff2 = coff1 + (long long)cw * ch;
+  const int jj = q.inverse ? -j256 : j256;
+
+  int cur[3][4];
+  short *target[2];
+  {
+    const unsigned w = *reinterpret_cast<const unsigned *>(q.luma_in + (long long)frame * q.luma_in_stride +
+                                                           (unsigned)(ty * q.X + tx0));
+#pragma unroll
+    for (int k = 0; k < 4; k++) cur[0][k] = (w >> (8 * k)) & 0xff;
+#pragma unroll
+    for (int c = 1; c < 3; c++) {
+      target[c - 1] = q.ref.row(c * q.slots_per_comp + (frame - q.frame0), ty) + tx0;
+      const uint2 v = *reinterpret_cast<const uint2 *>(target[c - 1]);
+      cur[c][0] = (short)(v.x & 0xffff);
+      cur[c][1] = (int)v.x >> 16;
+      cur[c][2] = (short)(v.y & 0xffff);
+      cur[c][3] = (int)v.y >> 16;
+    }
+  }
+  int total[2];
+  bool valid[2];
+  const short *mvx_[2];
+  const uint8_t *res_[2];
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
+    valid[pass] = pair >= 0 && pair < q.n_pairs && q.types[pair] == 'B';
+    const int pc = valid[pass] ? pair : 0;
+    total[pass] = valid[pass] ? q.cnt[(long long)(pc * 2 + dir) * ntiles + tile] : 0;
+    mvx_[pass] = q.mv + (long long)pc * 4 * plane + (long long)(dir ? MV_NEXT_X : MV_PREV_X) * plane;
+    res_[pass] = q.high + (long long)pc * q.high_stride;
+  }
+  auto geometry = [&](int pass, int b) -> int4 {
+    const int byy = b / q.BX, bxx = b - byy * q.BX;
+    return make_int4(byy * q.bs + mvx_[pass][plane + b], bxx * q.bs + mvx_[pass][b], byy * q.bs, bxx * q.bs);
+  };
+  {
+    // warp 0: pass 0, warp 1: pass 1 (k_update_dyadic)
+    const int pass = warp;
+    const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
+    int me = 0;
+    int4 g = make_int4(0, 0, 0, 0);
+    if (valid[pass] && lane < q.cap) {
+      const long long at = ((long long)(pair * 2 + dir) * ntiles + tile) * q.cap + lane;
+      if (q.geo) {
+        g = q.geo[at];
+        me = (g.z << 16) | g.w;
+      } else {
+        me = q.list[at];
+      }
+    }
+    const int n = total[pass];
+    const bool mine = valid[pass] && n <= q.cap && lane < n;
+    if (mine) s_ids[pass * 32 + lane] = me;
+    __syncwarp();
+    if (mine) {
+      int rank = 0;
+      for (int k = 0; k < n; k++) rank += s_ids[pass * 32 + k] < me;
+      s_geo[pass * 32 + rank] = q.geo ? g : geometry(pass, me);
+    }
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 2; pass++) {
+    if (!valid[pass]) continue;
+    const uint8_t *res = res_[pass];
+    auto addend = [&](int c, int ry, int rx) -> int {
+      int r = 0;
+      if (c == 0) r = (int)res[(long long)ry * q.X + rx] - 128;
+      else if (ry < ch && rx < cw) r = (int)res[(c == 1 ? coff1 : coff2) + (long long)ry * cw + rx] - 128;
+      return (r * jj) >> 8;
+    };
+    auto apply = [&](int n, const int4 *geo) {
+      for (int k = 0; k < n; k++) {
+        const int4 g = geo[k];
+        const int y = ty - g.x, xb = tx0 - g.y;
+        if ((unsigned)y < (unsigned)q.bs && xb > -4 && xb < q.bs) {
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            const int x = xb + kk;
+            if ((unsigned)x < (unsigned)q.bs) {
+#pragma unroll
+              for (int c = 0; c < 3; c++) cur[c][kk] = min(max(cur[c][kk] + addend(c, g.z + y, g.w + x), 0), 255);
+            }
+          }
+        }
+      }
+    };
+    if (total[pass] <= q.cap) {
+      apply(total[pass], s_geo + pass * 32);
+    } else {
+      // overflow: ordered scan of every block within reach of the tile, 64 candidates per round
+      const int pair = pass == 0 ? frame - 1 : frame, dir = pass == 0 ? 1 : 0;
+      const int reach = q.reach[pair * 2 + dir];
+      const int by_lo = max(0, (tile_y0 - reach - q.bs + 1 + (q.bs - 1) * (tile_y0 - reach - q.bs + 1 > 0)) / q.bs);
+      const int by_hi = min(q.BY - 1, (tile_y1 + reach) / q.bs);
+      const int bx_lo = max(0, (tile_x0 - reach - q.bs + 1 + (q.bs - 1) * (tile_x0 - reach - q.bs + 1 > 0)) / q.bs);
+      const int bx_hi = min(q.BX - 1, (tile_x1 + reach) / q.bs);
+      const int nbw = max(bx_hi - bx_lo + 1, 0), nbh = max(by_hi - by_lo + 1, 0);
+      const int nblocks = nbw * nbh;
+      for (int base = 0; base < nblocks; base += 64) {
+        __syncthreads();
+        bool hit = false;
+        int4 g = make_int4(0, 0, 0, 0);
+        if (base + (int)threadIdx.x < nblocks) {
+          const int k = base + threadIdx.x;
+          const int cby = by_lo + k / nbw, cbx = bx_lo + k % nbw;
+          g = geometry(pass, cby * q.BX + cbx);
+          const int fy0 = iclamp(g.x, 0, q.Y - 1), fy1 = iclamp(g.x + q.bs - 1, 0, q.Y - 1);
+          const int fx0 = iclamp(g.y, 0, q.X - 1), fx1 = iclamp(g.y + q.bs - 1, 0, q.X - 1);
+          hit = fy0 <= tile_y1 && fy1 >= tile_y0 && fx0 <= tile_x1 && fx1 >= tile_x0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        const int prefix = warp ? s_w[0] : 0;
+        if (hit) s_scan[prefix + __popc(m & ((1u << lane) - 1))] = g;
+        if (threadIdx.x == 63) s_count = prefix + __popc(m);
+        __syncthreads();
+        apply(s_count, s_scan);
+      }
+    }
+  }
+  {
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) w |= (unsigned)cur[0][k] << (8 * k);  // bytes: untouched inputs or clamped sums
+    *reinterpret_cast<unsigned *>(q.luma_out + (long long)frame * q.luma_out_stride + (unsigned)(ty * q.X + tx0)) = w;
+#pragma unroll
+    for (int c = 1; c < 3; c++) {
+      uint2 v;
+      v.x = ((unsigned)cur[c][0] & 0xffffu) | ((unsigned)cur[c][1] << 16);
+      v.y = ((unsigned)cur[c][2] & 0xffffu) | ((unsigned)cur[c][3] << 16);
+      *reinterpret_cast<uint2 *>(target[c - 1]) = v;
+    }
+  }
+}
+
 // ---- chroma 4:2:0 <-> luma-sized planes around the update (update.cpp:506-656) ----
 // Zero-high-band synthesis (5_3.cpp:81-94 with h = 0; dwt2d.cpp:139-172: columns, then rows) of a byte
 // component: T[2i] = c[i], T[2i+1] = (c[i] + c[i+1]) / 2, last odd row = c[last]; the same along the rows.
@@ -999,7 +1168,15 @@ void launch_update_batch(const Launch &L, const UpdateBatchParams &q, int nframe
   ProfScope ps_(L, KC_UPDATE);
   int j256 = 0;
   if (q.cap <= 32 && update_is_dyadic(q.uf) && update_dyadic(q.uf, &j256)) {
-    k_update_dyadic<<<dim3(q.tiles_x, q.tiles_y, nframes), 256, 0, L.stream>>>(q, j256);
+    static const int quad = getenv("QSVC_UPDATE_QUAD") ? atoi(getenv("QSVC_UPDATE_QUAD")) : 1;
+    if (quad && q.luma_in && q.tiles_x >= 3 && q.tiles_y >= 3 && q.X % 8 == 0) {
+      k_update_quad<<<dim3(q.tiles_x - 2, q.tiles_y - 2, nframes), 64, 0, L.stream>>>(q, j256);
+      COUNT(L);
+      k_update_dyadic<<<dim3(2 * q.tiles_x + 2 * (q.tiles_y - 2), 1, nframes), 256, 0, L.stream>>>(q, j256, 1);
+      COUNT(L);
+      return;
+    }
+    k_update_dyadic<<<dim3(q.tiles_x, q.tiles_y, nframes), 256, 0, L.stream>>>(q, j256, 0);
     COUNT(L);
     return;
   }

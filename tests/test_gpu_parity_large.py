@@ -266,3 +266,28 @@ def test_update_with_long_vectors_matches_oracle(ctx, X, Y, reach, uf):
     _same(f"update uf={uf}", ctx.update(frames, high, mv, types, X, Y, 16, uf), want)
     back = orc.update(want, high, mv, types, X, Y, 16, uf, inverse=True)
     _same(f"un_update uf={uf}", ctx.un_update(want, high, mv, types, X, Y, 16, uf), back)
+
+
+@pytest.mark.parametrize("uf", [0.25, 0.3])
+@pytest.mark.parametrize("X,Y", [(640, 352), (1920, 1080)])
+def test_update_with_converging_vectors_matches_oracle(ctx, X, Y, uf):
+    """Every block displaced onto (almost) the same spot inside the picture: tiles far from the edges whose
+    block lists overflow, hundreds of ordered contributions per target that is NOT on the picture edge."""
+    from oracle import oracle as orc
+    orc.build()
+    bs, n = 16, 2
+    rng = np.random.default_rng(X + int(uf * 100))
+    fb = X * Y * 3 // 2
+    frames = rng.integers(0, 256, (n + 1, fb), dtype=np.uint8)
+    high = np.clip(rng.normal(128, 12, (n, fb)), 0, 255).astype(np.uint8)
+    by, bx = np.mgrid[0:Y // bs, 0:X // bs]
+    mv = np.zeros((n, 4, Y // bs, X // bs), np.int16)
+    for i in range(n):
+        for d, (cy, cx) in enumerate([(Y // 2 - 40, X // 2 + 24), (Y // 3, X // 4)]):
+            jy, jx = rng.integers(-6, 7, by.shape), rng.integers(-6, 7, bx.shape)
+            mv[i, 2 * d] = np.clip(cx - bx * bs + jx, -511, 511)      # x component
+            mv[i, 2 * d + 1] = np.clip(cy - by * bs + jy, -511, 511)  # y component
+    want = orc.update(frames, high, mv, b"BB", X, Y, bs, uf)
+    _same(f"update uf={uf}", ctx.update(frames, high, mv, b"BB", X, Y, bs, uf), want)
+    back = orc.update(want, high, mv, b"BB", X, Y, bs, uf, inverse=True)
+    _same(f"un_update uf={uf}", ctx.un_update(want, high, mv, b"BB", X, Y, bs, uf), back)
