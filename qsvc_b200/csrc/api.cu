@@ -1583,6 +1583,10 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
   // every level are frames of the resident clip (even_t[k] = low_0[k << t]) and the motion estimation of
   // level t+1 does not wait for the decorrelate of level t: two lanes, joined by one event per level.
   const bool lanes = c->overlap != 0 && p->update_factor == 0.0f && p->TRLs > 2 && c->me_stream != nullptr;
+  // update_factor != 0: level t+1 needs low_t, so the levels stay in order -- but the motion estimation of a level
+  // and the preparation of its decorrelate (up-sampled reference planes, border ring) are independent of each
+  // other and run on the two streams side by side
+  const bool side = !lanes && c->overlap != 0 && p->update_factor != 0.0f && c->me_stream != nullptr;
   {  // result buffers of every level first: nothing the pool hands out below is still in use elsewhere
     int pics = pictures, b = bs;
     for (int t = 1; t < p->TRLs; t++) {
@@ -1601,7 +1605,7 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
   }
   const uint8_t *low = c->low0;
   CU(cudaEventRecord(c->ev2, c->stream));
-  if (lanes) {
+  if (lanes || side) {
     // the ME lane starts where the main stream stands now
     CU(cudaStreamWaitEvent(c->me_stream, c->ev2, 0));
     while ((int)c->me_events.size() < p->TRLs) {
@@ -1630,8 +1634,18 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
     // split (split.cpp:229-341) is index arithmetic: even k = frame 2k, odd i = frame 2i+1 of low_{t-1}
     const long long in_stride = lanes ? (fb << t) : 2 * fb;
     const uint8_t *even = lanes ? c->low0 : low, *odd = even + in_stride / 2;
+    if (side && t > 1) {
+      // low_{t-1} is ready where the main stream stands now
+      while ((int)c->level_events.size() <= p->TRLs + t) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->level_events.push_back(e);
+      }
+      CU(cudaEventRecord(c->level_events[p->TRLs + t], c->stream));
+      CU(cudaStreamWaitEvent(c->me_stream, c->level_events[p->TRLs + t], 0));
+    }
     std::unique_ptr<MeLane> lane_guard;
-    if (lanes) lane_guard.reset(new MeLane(c));
+    if (lanes || side) lane_guard.reset(new MeLane(c));
     if (t == 1 && c->upload_gops > 0) {
       const int per_gop = c->upload_gop_frames / 2;  // pairs of a GOP at level 1
       for (int g = 0; g < c->upload_gops; g++) {
@@ -1645,7 +1659,7 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
       TRY(me_level(c, even, in_stride, odd, in_stride, n, X, Y, bsz, p->border_size, plan[t].sr, p->subpixel_accuracy,
                    p->first_gop_is_global_first, lv.motion));
     }
-    if (lanes) CU(cudaEventRecord(c->me_events[t], c->stream));
+    if (lanes || side) CU(cudaEventRecord(c->me_events[t], c->stream));
     return QSVC_OK;
   };
   // Two lanes: the ME lane is enqueued one level ahead of the decorrelate lane, so that whatever blocks the host
@@ -1661,7 +1675,7 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
     c->cur_level = t;
     if (!lanes) TRY(run_me(t, low));
     else if (t + 1 < p->TRLs) TRY(run_me(t + 1, low));
-    if (lanes) c->mv_ready = c->me_events[t];  // awaited inside, after the reference planes are up-sampled
+    if (lanes || side) c->mv_ready = c->me_events[t];  // awaited inside, after the reference planes are up-sampled
     if (t == 1 && c->upload_gops > 0)
       // the decorrelate of level 1 reads the clip on this stream before it meets the ME lane
       // (which is the one that waited GOP by GOP): the whole upload has to have landed
