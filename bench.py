@@ -649,14 +649,18 @@ def measure_extras(ctx, w, wname, clip_pinned, outs, kw):
     for _ in range(2):
         ctx.resident_analyze(**kw25)
     ms = ctx.timer_stop() / 2
+    ctx.set_overlap(False)  # per-class times: every kernel alone on one stream
     ctx.profile_enable(True)
     ctx.resident_analyze(**kw25)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
+    ctx.set_overlap(True)
     ex["update_factor_0.25"] = {"ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3),
                                 "kernel_ms": {k: v[0] for k, v in prof.items()},
                                 "dominant": max(prof, key=lambda k: prof[k][0]),
-                                "note": "device-resident analysis, one lane (level t+1 needs low_t)"}
+                                "note": "device-resident analysis; the levels run in order (level t+1 needs low_t), "
+                                        "motion estimation beside the decorrelate's plane preparation; kernel_ms "
+                                        "from a separate step with one stream"}
     # (b) synthesis of the headline analysis (update_factor 0), host sub-bands in, host frames out
     sub = {f"low_{T-1}": outs[f"low_{T-1}"]}
     for t in range(1, T):
