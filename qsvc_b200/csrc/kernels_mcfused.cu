@@ -60,28 +60,32 @@ __global__ void __launch_bounds__(256) k_ring_bands(uint8_t *U, long long plane_
 __global__ void __launch_bounds__(256) k_ring_sides(uint8_t *U, long long plane_stride, int pitch, int Yd, int Xd,
                                                     int ring, int b, int padh) {
   uint8_t *P = U + (long long)blockIdx.z * plane_stride;
-  const int per_row = ring >> 1, total = (Yd + 2 * ring) * per_row;
+  const int per_row = ring >> 3, total = (Yd + 2 * ring) * per_row;  // groups of 16 cells (ring % 16 == 0)
   const int y0 = Yd - b;  // the first row whose pointer the reference's alloc does not shift (heap alias, A.3)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / per_row, g = i - r * per_row, y = r - ring;
-    // groups of four cells: the first ring / 4 on the left, the others on the right
-    const bool left = g < (ring >> 2);
-    const int x0 = left ? 4 * g - ring : Xd + 4 * (g - (ring >> 2));
+    // the first ring / 16 groups on the left, the others on the right
+    const bool left = g < (ring >> 4);
+    const int x0 = left ? 16 * g - ring : Xd + 16 * (g - (ring >> 4));
     // Along a row the rule is constant on either side of the picture, except in the one row where the
     // heap alias (left, x < -padh) or its mirror case (b == Yd: row -1, right, x >= Xd + padh) applies.
     const bool quirk = b > padh && (left ? (y0 != 0 && y == y0) : (y0 == 0 && y == -1));
-    unsigned w;
+    unsigned w[4];
     if (!quirk) {
       const int cy = min(max(y, 0), Yd - 1);
       const unsigned v = left ? (y >= Yd ? P[(long long)(Yd - 1) * pitch + Xd - 1] : P[(long long)cy * pitch])
                               : P[(long long)cy * pitch + Xd - 1];
-      w = v * 0x01010101u;
+      w[0] = w[1] = w[2] = w[3] = v * 0x01010101u;
     } else {
-      w = 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) w |= (unsigned)bordered_ref_u8(P, pitch, Yd, Xd, b, padh, y, x0 + k) << (8 * k);
+      for (int j = 0; j < 4; j++) {
+        w[j] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          w[j] |= (unsigned)bordered_ref_u8(P, pitch, Yd, Xd, b, padh, y, x0 + 4 * j + k) << (8 * k);
+      }
     }
-    *reinterpret_cast<unsigned *>(P + (long long)y * pitch + x0) = w;
+    *reinterpret_cast<uint4 *>(P + (long long)y * pitch + x0) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -98,7 +102,7 @@ void launch_fill_ring(const Launch &L, uint8_t *U, long long plane_stride, int p
       COUNT(L);
     }
     ProfScope ps_(L, KC_IMG);
-    k_ring_sides<<<dim3(blocks_for((long long)(Yd + 2 * ring) * (ring >> 1)), 1, nz), 256, 0, L.stream>>>(
+    k_ring_sides<<<dim3(blocks_for((long long)(Yd + 2 * ring) * (ring >> 3)), 1, nz), 256, 0, L.stream>>>(
         Uz, plane_stride, pitch, Yd, Xd, ring, b, padh);
     COUNT(L);
   }
