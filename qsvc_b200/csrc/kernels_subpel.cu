@@ -1081,9 +1081,23 @@ __global__ void __launch_bounds__(2 * W) k_subpel_strip(SubpelParams q, B0View v
         const unsigned sa = 8 * (unsigned)((uintptr_t)vb & 3);
         const unsigned lo = __ldg(a4);
         cw = sa ? __funnelshift_r(lo, __ldg(a4 + 1), sa) : lo;
+      } else if (row_in && x >= 0 && (y < q.clean ? x + 3 < Xl : x + 3 < q.clean)) {
+        // four samples of one int16 strip row (top strip: any column; left strip: columns below `clean`)
+        const short *sp = y < q.clean
+                              ? q.strip_top + (long long)slot * q.strip_top_stride + (long long)y * Xl + x
+                              : q.strip_left + (long long)slot * q.strip_left_stride + (long long)(y - q.clean) * q.clean + x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int sv = sp[k];
+          const int cl = min(max(sv, 0), 255);
+          const int ex = abs(sv - cl);
+          if (4 * w + k < RW) flags |= (ex != 0) | ((ex > 255) << 1);
+          cw |= (unsigned)cl << (8 * k);
+          ew |= (unsigned)(ex & 255) << (8 * k);
+        }
       } else {
-        // One per-sample rule for every other word (strip words, words outside the level-l image,
-        // words that straddle two regions), with the row-dependent parts resolved once: inside the
+        // One per-sample rule for every other word (words outside the level-l image, words that
+        // straddle two regions), with the row-dependent parts resolved once: inside the
         // image the int16 strips or the byte plane; outside it the reference's level-0 buffer at
         // the same coordinates (b0_cell): the compact plane where it is materialised, the malloc
         // size field at x in [-4, 0) of the un-shifted rows, zeros (never-written heap) elsewhere.
