@@ -75,7 +75,8 @@ struct qsvc_ctx {
   int overlap = 1;
   std::vector<cudaEvent_t> level_events;
   std::vector<cudaEvent_t> upload_events;  // qsvc_analyze: one per GOP of the clip being uploaded
-  int upload_gops = 0, upload_gop_frames = 0;  // > 0: level 1 may start GOP by GOP behind the upload
+  int upload_gops = 0, upload_gop_frames = 0;  // > 0: level 1 may start segment by segment behind the upload
+  std::vector<int> upload_segs;                // end pair (exclusive) of every upload segment at level 1
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   long long launches = 0;
   Profiler prof;
@@ -1518,8 +1519,15 @@ int qsvc_analyze(qsvc_ctx *c, const qsvc_analyze_params *p, const uint8_t *low0,
     c->n_frames = n_frames;
     c->X = p->pixels_in_x;
     c->Y = p->pixels_in_y;
-    const int gops = (n_frames - 1) / G;
-    while ((int)c->upload_events.size() < gops) {
+    const int gops = (n_frames - 1) / G, per_gop = G / 2;  // pairs of a GOP at level 1
+    // upload segments = ranges of level-1 pairs: whole GOPs, except that the first GOP starts with a quarter of
+    // itself, so that the first motion estimation waits for a quarter of a GOP's frames, not a whole one
+    c->upload_segs.clear();
+    const int head = per_gop >= 16 ? per_gop / 4 : 0;
+    if (head > 0) c->upload_segs.push_back(head);
+    for (int g = 0; g < gops; g++) c->upload_segs.push_back((g + 1) * per_gop);  // end pair (exclusive) of each segment
+    const int nseg = (int)c->upload_segs.size();
+    while ((int)c->upload_events.size() < nseg) {
       cudaEvent_t e;
       CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       c->upload_events.push_back(e);
@@ -1527,13 +1535,15 @@ int qsvc_analyze(qsvc_ctx *c, const qsvc_analyze_params *p, const uint8_t *low0,
     // the pool hands out memory that earlier work on the compute stream may still be using
     CU(cudaEventRecord(c->ev3, c->stream));
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev3, 0));
-    for (int g = 0; g < gops; g++) {
-      const long long f0 = g == 0 ? 0 : (long long)g * G + 1, f1 = (long long)(g + 1) * G;  // inclusive
+    long long f0 = 0;
+    for (int sgm = 0; sgm < nseg; sgm++) {
+      const long long f1 = 2LL * c->upload_segs[sgm];  // last frame (inclusive) the segment's pairs read
       CU(cudaMemcpyAsync(c->low0 + f0 * fb, low0 + f0 * fb, (size_t)((f1 - f0 + 1) * fb), cudaMemcpyHostToDevice,
                          c->copy_stream));
-      CU(cudaEventRecord(c->upload_events[g], c->copy_stream));
+      CU(cudaEventRecord(c->upload_events[sgm], c->copy_stream));
+      f0 = f1 + 1;
     }
-    c->upload_gops = gops;
+    c->upload_gops = nseg;
     c->upload_gop_frames = G;
   } else {
     TRY(qsvc_resident_load(c, low0, n_frames, p->pixels_in_x, p->pixels_in_y));
@@ -1647,13 +1657,14 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
     std::unique_ptr<MeLane> lane_guard;
     if (lanes || side) lane_guard.reset(new MeLane(c));
     if (t == 1 && c->upload_gops > 0) {
-      const int per_gop = c->upload_gop_frames / 2;  // pairs of a GOP at level 1
+      long long p0 = 0;  // first pair of the segment
       for (int g = 0; g < c->upload_gops; g++) {
         CU(cudaStreamWaitEvent(c->stream, c->upload_events[g], 0));
-        const long long f0 = (long long)g * per_gop;
-        TRY(me_level(c, even + f0 * in_stride, in_stride, odd + f0 * in_stride, in_stride, per_gop, X, Y, bsz,
+        const int np = (int)(c->upload_segs[g] - p0);
+        TRY(me_level(c, even + p0 * in_stride, in_stride, odd + p0 * in_stride, in_stride, np, X, Y, bsz,
                      p->border_size, plan[t].sr, p->subpixel_accuracy, g == 0 ? p->first_gop_is_global_first : 0,
-                     lv.motion + f0 * field));
+                     lv.motion + p0 * field));
+        p0 = c->upload_segs[g];
       }
     } else {
       TRY(me_level(c, even, in_stride, odd, in_stride, n, X, Y, bsz, p->border_size, plan[t].sr, p->subpixel_accuracy,
