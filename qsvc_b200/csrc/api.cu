@@ -735,6 +735,8 @@ static int mc_level(qsvc_ctx *c, int analysis, const uint8_t *even, long long ev
   const bool fused = c->mc_mode != 1 && mc_fused_ok(X, Y, bs, ov, a);
   if (c->mc_mode == 2 && !fused) return fail(QSVC_EINVAL, "fused MC path requested but not applicable");
   if (!fused) TRY(await_motion(c));
+  if (!fused && analysis && c->upload_gops > 0 && c->cur_level == 1)
+    CU(cudaStreamWaitEvent(c->stream, c->upload_events[c->upload_gops - 1], 0));  // qsvc_analyze: the clip has landed
   int *d_hist = nullptr;
   const int HS = 1024;  // per pair: 256 predicted, 256 residue, 257 motion (+pad)
   const bool need_hist = analysis && !always_B;
@@ -1687,10 +1689,9 @@ static int analyze_levels(qsvc_ctx *c, const qsvc_analyze_params *p, const qsvc_
     if (!lanes) TRY(run_me(t, low));
     else if (t + 1 < p->TRLs) TRY(run_me(t + 1, low));
     if (lanes || side) c->mv_ready = c->me_events[t];  // awaited inside, after the reference planes are up-sampled
-    if (t == 1 && c->upload_gops > 0)
-      // the decorrelate of level 1 reads the clip on this stream before it meets the ME lane
-      // (which is the one that waited GOP by GOP): the whole upload has to have landed
-      CU(cudaStreamWaitEvent(c->stream, c->upload_events[c->upload_gops - 1], 0));
+    // (the decorrelate of level 1 reads the clip on this stream before it meets the ME lane, which is the one
+    // that waited segment by segment: mc_level waits for the upload itself -- the byte-plane path frame by
+    // frame as the segments land, the literal path for the whole clip)
     {
       const int rc = mc_level(c, 1, even, in_stride, odd, in_stride, lv.motion, n, X, Y, bsz, p->block_overlaping,
                               plan[t].sr, p->subpixel_accuracy, p->always_B, nullptr, lv.high, fb, &lv.types,
