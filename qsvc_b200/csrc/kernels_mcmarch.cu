@@ -566,10 +566,11 @@ void launch_mc_march(const Launch &L, MarchParams q, int npairs) {
   q.bs_shift = 0;
   while ((1 << q.bs_shift) < q.bsa) q.bs_shift++;
   q.nstrips = (q.Xa + 8 * MARCH_UL - 1) / (8 * MARCH_UL);
-  // enough warps to fill the machine several times over (measured: 12 rounds of 20 warps per SM beat 8;
-  // beyond 24 the warm-up rows of the extra segments cost more), segments as tall as that allows
+  // enough warps to fill the machine several times over (measured with 24 warps per SM resident: flat between
+  // 5 and 12 rounds of 20 warps per SM, 1 % worse at 24 where the warm-up rows of the extra segments cost more),
+  // segments as tall as that allows
   const long long cols = (long long)npairs * 3 * q.nstrips;
-  static const int seg_waves = getenv("QSVC_MARCH_WAVES") ? atoi(getenv("QSVC_MARCH_WAVES")) : 12;
+  static const int seg_waves = getenv("QSVC_MARCH_WAVES") ? atoi(getenv("QSVC_MARCH_WAVES")) : 8;
   long long want = (148LL * 20 * seg_waves + cols - 1) / cols;
   int seg_p = (int)((q.Ya + want - 1) / want);
   seg_p = (seg_p + 7) & ~7;
