@@ -55,12 +55,34 @@ __global__ void __launch_bounds__(256) k_dwt_rows(Plane p, int slot0, int ny, in
     }
     __syncthreads();
     if (!SYNTH) {
-      for (int i = threadIdx.x; i < half; i += blockDim.x) {
-        int l, h;
-        ana_pair(sm, 1, i, nx, l, h);
-        row[i] = (short)l;
-        row[nlow + i] = (short)h;
-        if ((nx & 1) && i == half - 1) row[half] = (short)(sm[nx - 1] + tdiv2(h));
+      if (!(nx & 3) && (((uintptr_t)row) & 3) == 0) {
+        // two output pairs per thread: the high-pass value in the middle is shared, the stores are 32-bit
+        unsigned *lo2 = reinterpret_cast<unsigned *>(row), *hi2 = reinterpret_cast<unsigned *>(row + nlow);
+        for (int k = threadIdx.x; k < (half >> 1); k += blockDim.x) {
+          const int i = 2 * k;
+          const short *s = sm + 2 * i;  // s[0..4]: samples 2i .. 2i+4
+          const int s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
+          const int h0 = (short)(s1 - tdiv2(s0 + s2));
+          const int h1 = (short)(i + 1 == half - 1 ? s3 - s2 : s3 - tdiv2(s2 + s[4]));
+          int l0;
+          if (i == 0) {
+            l0 = (short)(s0 + tdiv2(h0));
+          } else {
+            const int hp = (short)(s[-1] - tdiv2(s[-2] + s0));
+            l0 = (short)(s0 + tdiv4(h0 + hp));
+          }
+          const int l1 = (short)(s2 + tdiv4(h1 + h0));
+          lo2[k] = ((unsigned)(unsigned short)l0) | ((unsigned)(unsigned short)l1 << 16);
+          hi2[k] = ((unsigned)(unsigned short)h0) | ((unsigned)(unsigned short)h1 << 16);
+        }
+      } else {
+        for (int i = threadIdx.x; i < half; i += blockDim.x) {
+          int l, h;
+          ana_pair(sm, 1, i, nx, l, h);
+          row[i] = (short)l;
+          row[nlow + i] = (short)h;
+          if ((nx & 1) && i == half - 1) row[half] = (short)(sm[nx - 1] + tdiv2(h));
+        }
       }
     } else {
       const short *lo = sm, *hi = sm + nlow;
