@@ -1080,55 +1080,52 @@ void launch_chroma_up_s16(const Launch &L, Plane dst, int slot0, int n, const ui
 }
 
 // LL band of one analysis level (dwt2d.cpp:76-119: rows, then columns; 5_3.cpp:39-52, even sizes) of a
-// luma-sized int16 plane, stored as bytes.  A CTA produces LL1_TR x LL1_TC outputs from a (2 TR + 3) x (2 TC + 4)
-// sample tile: row pass (low band only) into shared memory, column pass (low band only) to the frame.
-static constexpr int LL1_TR = 32, LL1_TC = 64, LL1_ROWS = 2 * LL1_TR + 3, LL1_COLS = 2 * LL1_TC + 4;
-__global__ void __launch_bounds__(256) k_ll1_store_u8(Plane src, int slot0, uint8_t *__restrict__ dst,
+// luma-sized int16 plane, stored as bytes.  One thread owns output column gi and walks down LL1_SEG output rows:
+// the low-pass sample of an input row at that column is five samples = three aligned 32-bit loads (neighbouring
+// threads share two of them through L1), the column pass is a streaming lifting step (last even row, last
+// high-pass value carried in registers).  No shared memory, no barriers.
+static constexpr int LL1_SEG = 32;
+__global__ void __launch_bounds__(128) k_ll1_store_u8(Plane src, int slot0, uint8_t *__restrict__ dst,
                                                        long long frame_stride, long long comp_off, int f0, int Y,
                                                        int X) {
-  __shared__ short sin[LL1_ROWS][LL1_COLS];  // sample columns 2 cx0 - 2 .. 2 cx0 + 2 TC + 1
-  __shared__ short RL[LL1_ROWS][LL1_TC];
-  const int slot = slot0 + blockIdx.z;
   const int halfx = X >> 1, halfy = Y >> 1;
-  const int cx0 = blockIdx.x * LL1_TC, ry0 = blockIdx.y * LL1_TR;
-  for (int it = threadIdx.x; it < LL1_ROWS * (LL1_COLS / 2); it += 256) {
-    const int r = it / (LL1_COLS / 2), w = it - r * (LL1_COLS / 2);
-    const int y = 2 * ry0 - 2 + r, x = 2 * cx0 - 2 + 2 * w;
-    unsigned v = 0;
-    if (y >= 0 && y < Y && x >= 0 && x < X) v = *reinterpret_cast<const unsigned *>(src.row(slot, y) + x);
-    *reinterpret_cast<unsigned *>(&sin[r][2 * w]) = v;
-  }
-  __syncthreads();
-  for (int it = threadIdx.x; it < LL1_ROWS * LL1_TC; it += 256) {
-    const int r = it / LL1_TC, i = it - r * LL1_TC, gi = cx0 + i;
-    if (gi >= halfx) continue;
-    const short *s = &sin[r][2 * i + 2];  // s[k] = sample 2 gi + k of the row
-    const int s0 = s[0], s1 = s[1];
-    const int h = (short)(gi == halfx - 1 ? s1 - s0 : s1 - tdiv2(s0 + s[2]));
-    int l;
-    if (gi == 0) {
-      l = (short)(s0 + tdiv2(h));
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= halfx) return;
+  const int slot = slot0 + blockIdx.z;
+  const int j0 = blockIdx.y * LL1_SEG, j1 = min(j0 + LL1_SEG, halfy);
+  // low-pass sample gi of input row y (row pass)
+  auto rowlow = [&](int y) -> int {
+    const unsigned *w = reinterpret_cast<const unsigned *>(src.row(slot, y) + 2 * gi);
+    const unsigned c = w[0];
+    const int s0 = (short)(c & 0xffffu), s1 = (int)c >> 16;
+    int h;
+    if (gi == halfx - 1) {
+      h = (short)(s1 - s0);
     } else {
-      const int hp = (short)(s[-1] - tdiv2(s[-2] + s0));
-      l = (short)(s0 + tdiv4(h + hp));
+      const int s2 = (short)(w[1] & 0xffffu);
+      h = (short)(s1 - tdiv2(s0 + s2));
     }
-    RL[r][i] = (short)l;
-  }
-  __syncthreads();
-  uint8_t *out = dst + (long long)(f0 + blockIdx.z) * frame_stride + comp_off;
-  for (int it = threadIdx.x; it < LL1_TR * LL1_TC; it += 256) {
-    const int j = it / LL1_TC, i = it - j * LL1_TC, gj = ry0 + j, gi = cx0 + i;
-    if (gj >= halfy || gi >= halfx) continue;
-    const int t0 = RL[2 * j + 2][i], t1 = RL[2 * j + 3][i];  // row-transformed samples of rows 2 gj, 2 gj + 1
-    const int h = (short)(gj == halfy - 1 ? t1 - t0 : t1 - tdiv2(t0 + RL[2 * j + 4][i]));
-    int l;
-    if (gj == 0) {
-      l = (short)(t0 + tdiv2(h));
+    if (gi == 0) return (short)(s0 + tdiv2(h));
+    const unsigned p = w[-1];
+    const int hp = (short)(((int)p >> 16) - tdiv2((int)(short)(p & 0xffffu) + s0));
+    return (short)(s0 + tdiv4(h + hp));
+  };
+  int e = rowlow(2 * j0), hp = 0;
+  if (j0 > 0) hp = (short)(rowlow(2 * j0 - 1) - tdiv2(rowlow(2 * j0 - 2) + e));
+  uint8_t *out = dst + (long long)(f0 + blockIdx.z) * frame_stride + comp_off + gi;
+  for (int j = j0; j < j1; j++) {
+    const int t1 = rowlow(2 * j + 1);
+    int h, e2 = 0;
+    if (j == halfy - 1) {
+      h = (short)(t1 - e);
     } else {
-      const int hp = (short)(RL[2 * j + 1][i] - tdiv2(RL[2 * j][i] + t0));
-      l = (short)(t0 + tdiv4(h + hp));
+      e2 = rowlow(2 * j + 2);
+      h = (short)(t1 - tdiv2(e + e2));
     }
-    out[(long long)gj * halfx + gi] = (uint8_t)l;  // truncation mod 256, no clamp
+    const int l = (short)(j == 0 ? e + tdiv2(h) : e + tdiv4(h + hp));
+    out[(long long)j * halfx] = (uint8_t)l;  // truncation mod 256, no clamp
+    hp = h;
+    e = e2;
   }
 }
 
@@ -1136,7 +1133,7 @@ void launch_ll1_store_u8(const Launch &L, Plane src, int slot0, int n, uint8_t *
                          long long comp_off, int f0, int Y, int X) {
   if (n <= 0) return;
   ProfScope ps_(L, KC_DWT_ROWS);
-  k_ll1_store_u8<<<dim3(((X >> 1) + LL1_TC - 1) / LL1_TC, ((Y >> 1) + LL1_TR - 1) / LL1_TR, n), 256, 0, L.stream>>>(
+  k_ll1_store_u8<<<dim3(((X >> 1) + 127) / 128, ((Y >> 1) + LL1_SEG - 1) / LL1_SEG, n), 128, 0, L.stream>>>(
       src, slot0, dst, frame_stride, comp_off, f0, Y, X);
   COUNT(L);
 }
