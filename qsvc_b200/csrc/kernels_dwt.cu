@@ -184,70 +184,77 @@ __global__ void __launch_bounds__(1024) k_dwt_cols(Plane p, int slot0, int ny, i
 // ---- first pyramid level straight from the frames ----
 // One level of dwt2d::analyze (rows, then all columns; dwt2d.cpp:76-119, 5_3.cpp:39-52, even
 // sizes) of the luma of frame f0 + z, read as bytes and written as the four sub-bands of the
-// in-place Mallat layout of slot slot0 + z.  A CTA produces D0_TR x D0_TC coefficient pairs per
-// sub-band from a (2 D0_TR + 3) x (2 D0_TC + 3) pixel tile (67 x 131: 5 % of halo rows): row pass into shared memory, column
-// pass to the plane.  Replaces load + row pass + column pass of the level (and the snapshot the
-// descent would restore it from: the frame itself is that snapshot).
-static constexpr int D0_TR = 32, D0_TC = 64, D0_ROWS = 2 * D0_TR + 3, D0_WORDS = (2 * D0_TC + 8) / 4;
-__global__ void __launch_bounds__(256) k_dwt0_u8(Plane p, int slot0, const uint8_t *__restrict__ src,
+// in-place Mallat layout of slot slot0 + z.  Replaces load + row pass + column pass of the level (and the
+// snapshot the descent would restore it from: the frame itself is that snapshot).
+// One thread owns coefficient column gi (pixel columns 2 gi - 2 .. 2 gi + 2) and walks down D0_SEG coefficient
+// rows: the row pass of a pixel row at that column is five bytes (two 16-bit loads and a byte; neighbouring
+// threads share them through L1) and yields one low and one high sample, each of which runs through its own
+// streaming column lifting (last even row and last high-pass value in registers); four 16-bit stores per step,
+// coalesced across the warp.  No shared memory, no barriers.
+static constexpr int D0_SEG = 32;
+__global__ void __launch_bounds__(128) k_dwt0_u8(Plane p, int slot0, const uint8_t *__restrict__ src,
                                                   long long frame_stride, int f0, int Y, int X) {
-  __shared__ unsigned sin[D0_ROWS][D0_WORDS];  // pixel columns 2 cx0 - 4 .. 2 cx0 + 2 D0_TC + 3
-  __shared__ short RL[D0_ROWS][D0_TC], RH[D0_ROWS][D0_TC];
-  const int slot = slot0 + blockIdx.z;
-  const uint8_t *frame = src + (long long)(f0 + blockIdx.z) * frame_stride;
   const int halfx = X >> 1, halfy = Y >> 1;
-  const int cx0 = blockIdx.x * D0_TC, ry0 = blockIdx.y * D0_TR;
-  for (int it = threadIdx.x; it < D0_ROWS * D0_WORDS; it += 256) {
-    const int r = it / D0_WORDS, w = it - r * D0_WORDS;
-    const int y = 2 * ry0 - 2 + r, x = 2 * cx0 - 4 + 4 * w;
-    unsigned v = 0;
-    if (y >= 0 && y < Y && x >= 0 && x < X) v = *reinterpret_cast<const unsigned *>(frame + (long long)y * X + x);
-    sin[r][w] = v;
-  }
-  __syncthreads();
-  for (int it = threadIdx.x; it < D0_ROWS * D0_TC; it += 256) {
-    const int r = it / D0_TC, i = it - r * D0_TC, gi = cx0 + i;
-    if (gi >= halfx) continue;
-    const uint8_t *s = reinterpret_cast<const uint8_t *>(sin[r]) + 2 * i + 4;  // s[k] = pixel 2 gi + k
-    const int s0 = s[0], s1 = s[1];
-    const int h = (short)(gi == halfx - 1 ? s1 - s0 : s1 - tdiv2(s0 + s[2]));
-    int l;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= halfx) return;
+  const int slot = slot0 + blockIdx.z;
+  const uint8_t *frame = src + (long long)(f0 + blockIdx.z) * frame_stride + 2 * gi;
+  const int j0 = blockIdx.y * D0_SEG, j1 = min(j0 + D0_SEG, halfy);
+  // low (l) and high (h) sample gi of pixel row y
+  auto rowpass = [&](int y, int &l, int &h) {
+    const uint8_t *r = frame + (unsigned)(y * X);
+    const unsigned c = *reinterpret_cast<const unsigned short *>(r);
+    const int s0 = c & 0xff, s1 = c >> 8;
+    h = gi == halfx - 1 ? s1 - s0 : s1 - tdiv2(s0 + (int)r[2]);
     if (gi == 0) {
-      l = (short)(s0 + tdiv2(h));
+      l = s0 + tdiv2(h);
     } else {
-      const int hp = (short)(s[-1] - tdiv2(s[-2] + s0));
-      l = (short)(s0 + tdiv4(h + hp));
+      const unsigned q = *reinterpret_cast<const unsigned short *>(r - 2);
+      const int hp = (int)(q >> 8) - tdiv2((int)(q & 0xff) + s0);
+      l = s0 + tdiv4(h + hp);
     }
-    RL[r][i] = (short)l;
-    RH[r][i] = (short)h;
+  };
+  int el, eh, hpl = 0, hph = 0;  // per band: last even row, last column high-pass value
+  rowpass(2 * j0, el, eh);
+  if (j0 > 0) {
+    int al, ah, bl, bh;
+    rowpass(2 * j0 - 1, al, ah);
+    rowpass(2 * j0 - 2, bl, bh);
+    hpl = (short)(al - tdiv2(bl + el));
+    hph = (short)(ah - tdiv2(bh + eh));
   }
-  __syncthreads();
-  for (int it = threadIdx.x; it < D0_TR * 2 * D0_TC; it += 256) {
-    const int j = it / (2 * D0_TC), c = it - j * (2 * D0_TC), gj = ry0 + j;
-    const int which = c >= D0_TC, i = which ? c - D0_TC : c, gi = cx0 + i;
-    if (gj >= halfy || gi >= halfx) continue;
-    const short(*col)[D0_TC] = which ? RH : RL;  // col[r][i]: row-transformed sample of pixel row 2 ry0 - 2 + r
-    const int t0 = col[2 * j + 2][i], t1 = col[2 * j + 3][i];
-    const int h = (short)(gj == halfy - 1 ? t1 - t0 : t1 - tdiv2(t0 + col[2 * j + 4][i]));
-    int l;
-    if (gj == 0) {
-      l = (short)(t0 + tdiv2(h));
+  for (int j = j0; j < j1; j++) {
+    int ol, oh, nl = 0, nh = 0;
+    rowpass(2 * j + 1, ol, oh);
+    int hl, hh;
+    if (j == halfy - 1) {
+      hl = (short)(ol - el);
+      hh = (short)(oh - eh);
     } else {
-      const int hp = (short)(col[2 * j + 1][i] - tdiv2(col[2 * j][i] + t0));
-      l = (short)(t0 + tdiv4(h + hp));
+      rowpass(2 * j + 2, nl, nh);
+      hl = (short)(ol - tdiv2(el + nl));
+      hh = (short)(oh - tdiv2(eh + nh));
     }
-    const int x = (which ? halfx : 0) + gi;
-    p.row(slot, gj)[x] = (short)l;
-    p.row(slot, halfy + gj)[x] = (short)h;
+    const int ll = j == 0 ? el + tdiv2(hl) : el + tdiv4(hl + hpl);
+    const int lh = j == 0 ? eh + tdiv2(hh) : eh + tdiv4(hh + hph);
+    short *top = p.row(slot, j), *bot = p.row(slot, halfy + j);
+    top[gi] = (short)ll;
+    top[halfx + gi] = (short)lh;
+    bot[gi] = (short)hl;
+    bot[halfx + gi] = (short)hh;
+    hpl = hl;
+    hph = hh;
+    el = nl;
+    eh = nh;
   }
 }
 
 void launch_dwt0_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8_t *src, long long frame_stride,
                     int f0, int Y, int X) {
   if (nslots <= 0) return;
-  dim3 grid(((X >> 1) + D0_TC - 1) / D0_TC, ((Y >> 1) + D0_TR - 1) / D0_TR, nslots);
+  dim3 grid(((X >> 1) + 127) / 128, ((Y >> 1) + D0_SEG - 1) / D0_SEG, nslots);
   ProfScope ps_(L, KC_DWT_ROWS);
-  k_dwt0_u8<<<grid, 256, 0, L.stream>>>(p, slot0, src, frame_stride, f0, Y, X);
+  k_dwt0_u8<<<grid, 128, 0, L.stream>>>(p, slot0, src, frame_stride, f0, Y, X);
   COUNT(L);
 }
 
