@@ -417,7 +417,12 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       for (int l = l0; l < L; l++) {
         launch_region_copy(Lh, img, 0, nslots, Y >> l, X >> l, snap + snap_off[l], (long long)snap_per_slot,
                            snap_pitch[l], true);
-        launch_dwt_level(Lh, img, 0, nslots, Y >> l, X >> l, false);
+        // the snapshot is also the transform's input: rows and columns in one pass, no in-place hazard
+        if (dwt_snap_supported(Y >> l, X >> l, snap_pitch[l], snap + snap_off[l], (long long)snap_per_slot))
+          launch_dwt_snap(Lh, img, 0, nslots, snap + snap_off[l], (long long)snap_per_slot, snap_pitch[l], Y >> l,
+                          X >> l);
+        else
+          launch_dwt_level(Lh, img, 0, nslots, Y >> l, X >> l, false);
       }
     } else {
       dwt_analyze(Lh, img, 0, nslots, Y, X, L);
@@ -629,7 +634,12 @@ static int me_level(qsvc_ctx *c, const uint8_t *even, long long even_stride, con
       for (int l = 0; l < L; l++) {
         launch_region_copy(Lh, img, 0, nslots, Y >> l, X >> l, snap + snap_off[l], (long long)snap_per_slot,
                            snap_pitch[l], true);
-        launch_dwt_level(Lh, img, 0, nslots, Y >> l, X >> l, false);
+        // the snapshot is also the transform's input: rows and columns in one pass, no in-place hazard
+        if (dwt_snap_supported(Y >> l, X >> l, snap_pitch[l], snap + snap_off[l], (long long)snap_per_slot))
+          launch_dwt_snap(Lh, img, 0, nslots, snap + snap_off[l], (long long)snap_per_slot, snap_pitch[l], Y >> l,
+                          X >> l);
+        else
+          launch_dwt_level(Lh, img, 0, nslots, Y >> l, X >> l, false);
       }
     } else {
       dwt_analyze(Lh, img, 0, nslots, Y, X, L);

@@ -64,6 +64,11 @@ int dwt_init_attributes();
 void launch_dwt_level(const Launch &L, Plane p, int slot0, int nslots, int ny, int nx,
                       bool synth);
 // first analysis level of even-sized pictures straight from the frames' luma (load + rows + columns fused)
+// one analysis level of the region whose int16 snapshot is `snap` (launch_region_copy), written in place: the
+// four sub-bands from one pass over the snapshot (even sizes, even pitch)
+bool dwt_snap_supported(int ny, int nx, int pitch, const short *snap, long long snap_slot_stride);
+void launch_dwt_snap(const Launch &L, Plane p, int slot0, int nslots, const short *snap, long long snap_slot_stride,
+                     int pitch, int ny, int nx);
 void launch_dwt0_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8_t *src, long long frame_stride,
                     int f0, int Y, int X);
 // dwt2d::analyze(sig, y, x, levels) / dwt2d::synthesize(sig, y, x, levels)

@@ -258,6 +258,79 @@ void launch_dwt0_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8
   COUNT(L);
 }
 
+// The same level from an int16 snapshot of the LL region (invertible pyramids: the region is copied out before it
+// is transformed, to be restored by the descent): snap (ny x nx, row pitch `pitch`, slot s at snap + s *
+// snap_slot_stride) -> the four sub-bands of the region, in place in plane p.  ny, nx even, pitch even.
+__global__ void __launch_bounds__(128) k_dwt_snap(Plane p, int slot0, const short *__restrict__ snap,
+                                                   long long snap_slot_stride, int pitch, int ny, int nx) {
+  const int halfx = nx >> 1, halfy = ny >> 1;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= halfx) return;
+  const int slot = slot0 + blockIdx.z;
+  const short *col = snap + (long long)slot * snap_slot_stride + 2 * gi;
+  const int j0 = blockIdx.y * D0_SEG, j1 = min(j0 + D0_SEG, halfy);
+  auto rowpass = [&](int y, int &l, int &h) {
+    const unsigned *w = reinterpret_cast<const unsigned *>(col + (long long)y * pitch);
+    const unsigned c = w[0];
+    const int s0 = (short)(c & 0xffffu), s1 = (int)c >> 16;
+    h = (short)(gi == halfx - 1 ? s1 - s0 : s1 - tdiv2(s0 + (int)(short)(w[1] & 0xffffu)));
+    if (gi == 0) {
+      l = (short)(s0 + tdiv2(h));
+    } else {
+      const unsigned q = w[-1];
+      const int hp = (short)(((int)q >> 16) - tdiv2((int)(short)(q & 0xffffu) + s0));
+      l = (short)(s0 + tdiv4(h + hp));
+    }
+  };
+  int el, eh, hpl = 0, hph = 0;
+  rowpass(2 * j0, el, eh);
+  if (j0 > 0) {
+    int al, ah, bl, bh;
+    rowpass(2 * j0 - 1, al, ah);
+    rowpass(2 * j0 - 2, bl, bh);
+    hpl = (short)(al - tdiv2(bl + el));
+    hph = (short)(ah - tdiv2(bh + eh));
+  }
+  for (int j = j0; j < j1; j++) {
+    int ol, oh, nl = 0, nh = 0;
+    rowpass(2 * j + 1, ol, oh);
+    int hl, hh;
+    if (j == halfy - 1) {
+      hl = (short)(ol - el);
+      hh = (short)(oh - eh);
+    } else {
+      rowpass(2 * j + 2, nl, nh);
+      hl = (short)(ol - tdiv2(el + nl));
+      hh = (short)(oh - tdiv2(eh + nh));
+    }
+    const int ll = (short)(j == 0 ? el + tdiv2(hl) : el + tdiv4(hl + hpl));
+    const int lh = (short)(j == 0 ? eh + tdiv2(hh) : eh + tdiv4(hh + hph));
+    short *top = p.row(slot, j), *bot = p.row(slot, halfy + j);
+    top[gi] = (short)ll;
+    top[halfx + gi] = (short)lh;
+    bot[gi] = (short)hl;
+    bot[halfx + gi] = (short)hh;
+    hpl = hl;
+    hph = hh;
+    el = nl;
+    eh = nh;
+  }
+}
+
+bool dwt_snap_supported(int ny, int nx, int pitch, const short *snap, long long snap_slot_stride) {
+  return ny >= 2 && nx >= 2 && !(ny & 1) && !(nx & 1) && !(pitch & 1) && !(snap_slot_stride & 1) &&
+         (((uintptr_t)snap) & 3) == 0;
+}
+
+void launch_dwt_snap(const Launch &L, Plane p, int slot0, int nslots, const short *snap, long long snap_slot_stride,
+                     int pitch, int ny, int nx) {
+  if (nslots <= 0) return;
+  dim3 grid(((nx >> 1) + 127) / 128, ((ny >> 1) + D0_SEG - 1) / D0_SEG, nslots);
+  ProfScope ps_(L, KC_DWT_ROWS);
+  k_dwt_snap<<<grid, 128, 0, L.stream>>>(p, slot0, snap, snap_slot_stride, pitch, ny, nx);
+  COUNT(L);
+}
+
 int dwt_init_attributes() {
   cudaError_t e;
   e = cudaFuncSetAttribute(k_dwt_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
