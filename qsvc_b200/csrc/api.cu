@@ -266,6 +266,26 @@ static bool me_fused_ok(int X, int Y, int bs, int bd, int sr, int a) {
   return true;
 }
 
+// dwt_analyze (dwt2d.cpp:76-119) with a scratch copy: a level whose region has even sizes is copied out and
+// transformed back in one pass (k_dwt_snap: rows and columns, no in-place hazard); other levels run the generic
+// row and column passes.  tmp holds one region of y x x per slot (slot stride tmp_stride shorts, pitch tmp_pitch).
+static void dwt_analyze_via_copy(const Launch &Lh, Plane img, int slot0, int nslots, int y, int x, int levels,
+                                 short *tmp, long long tmp_stride, int tmp_pitch) {
+  for (int lv = 0; lv < levels; lv++) {
+    const int nx = x, ny = y;
+    x >>= 1;
+    y >>= 1;
+    if (y == 0) y = 1;
+    if (x == 0) x = 1;
+    if (tmp && dwt_snap_supported(ny, nx, tmp_pitch, tmp, tmp_stride)) {
+      launch_region_copy(Lh, img, slot0, nslots, ny, nx, tmp + (long long)slot0 * tmp_stride, tmp_stride, tmp_pitch, true);
+      launch_dwt_snap(Lh, img, slot0, nslots, tmp, tmp_stride, tmp_pitch, ny, nx);
+    } else {
+      launch_dwt_level(Lh, img, slot0, nslots, ny, nx, false);
+    }
+  }
+}
+
 static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_stride,
                           const uint8_t *odd, long long odd_stride, int n_pairs, int X, int Y,
                           int bs, int sr, int a, int L, bool pr, int first_global, short *mv_out) {
@@ -353,12 +373,17 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       launch_load_u8(Lh, img, 2 * m + 1, n_copy, even, even_stride, 0, i0 + 1, 1, Y, X);
       launch_ring_s16(Lh, img, 2 * m + 1, n_copy, Y, X, B);
     }
+    // non-invertible pyramid: scratch copy of one level-0 region per slot for the analysis passes
+    short *tmpa = nullptr;
+    const int tmpa_pitch = (X + 7) & ~7;
+    const long long tmpa_stride = (long long)Y * tmpa_pitch;
+    if (!pr && L > 0) TRY(s.get((size_t)tmpa_stride * nslots * sizeof(short), (void **)&tmpa));
     if (!pr) {
       // carried reference[0]: one pass of the non-invertible pyramid (the sub-pixel
       // synthesis/analysis pair of the reference is an exact identity and is skipped)
       auto used_state = [&](int slot0, int n) {
         if (n <= 0) return;
-        dwt_analyze(Lh, img, slot0, n, Y, X, L);
+        dwt_analyze_via_copy(Lh, img, slot0, n, Y, X, L, tmpa, tmpa_stride, tmpa_pitch);
         for (int l = L - 1; l >= 0; --l) dwt_synthesize(Lh, img, slot0, n, desp(Y, l), desp(X, l), 1);
       };
       if (!(first_global && i0 == 0)) used_state(0, 1);
@@ -425,7 +450,7 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
           launch_dwt_level(Lh, img, 0, nslots, Y >> l, X >> l, false);
       }
     } else {
-      dwt_analyze(Lh, img, 0, nslots, Y, X, L);
+      dwt_analyze_via_copy(Lh, img, 0, nslots, Y, X, L, tmpa, tmpa_stride, tmpa_pitch);
     }
     run_search(ME_INIT, desp(BY, L), desp(BX, L), 0, L == 0);
     for (int l = L - 1; l >= 0; --l) {
