@@ -286,6 +286,19 @@ static void dwt_analyze_via_copy(const Launch &Lh, Plane img, int slot0, int nsl
   }
 }
 
+// one synthesis level (dwt_synthesize with levels = 1 on a ny x nx region) through the same scratch copy
+static void dwt_synthesize1_via_copy(const Launch &Lh, Plane img, int slot0, int nslots, int ny, int nx, short *tmp,
+                                     long long tmp_stride, int tmp_pitch) {
+  if (nx == 0) nx = 1;
+  if (ny == 0) ny = 1;
+  if (tmp && dwt_snap_supported(ny, nx, tmp_pitch, tmp, tmp_stride)) {
+    launch_region_copy(Lh, img, slot0, nslots, ny, nx, tmp + (long long)slot0 * tmp_stride, tmp_stride, tmp_pitch, true);
+    launch_syn_snap(Lh, img, slot0, nslots, tmp, tmp_stride, tmp_pitch, ny, nx);
+  } else {
+    launch_dwt_level(Lh, img, slot0, nslots, ny, nx, true);
+  }
+}
+
 static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_stride,
                           const uint8_t *odd, long long odd_stride, int n_pairs, int X, int Y,
                           int bs, int sr, int a, int L, bool pr, int first_global, short *mv_out) {
@@ -384,7 +397,8 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
       auto used_state = [&](int slot0, int n) {
         if (n <= 0) return;
         dwt_analyze_via_copy(Lh, img, slot0, n, Y, X, L, tmpa, tmpa_stride, tmpa_pitch);
-        for (int l = L - 1; l >= 0; --l) dwt_synthesize(Lh, img, slot0, n, desp(Y, l), desp(X, l), 1);
+        for (int l = L - 1; l >= 0; --l)
+          dwt_synthesize1_via_copy(Lh, img, slot0, n, desp(Y, l), desp(X, l), tmpa, tmpa_stride, tmpa_pitch);
       };
       if (!(first_global && i0 == 0)) used_state(0, 1);
       used_state(2 * m + 1, n_copy);
@@ -461,7 +475,7 @@ static int me_level_fused(qsvc_ctx *c, const uint8_t *even, long long even_strid
         launch_region_copy(Lh, img, 0, nslots, Y >> l, X >> l, snap + snap_off[l], (long long)snap_per_slot,
                            snap_pitch[l], false);
       else
-        dwt_synthesize(Lh, img, 0, nslots, desp(Y, l), desp(X, l), 1);
+        dwt_synthesize1_via_copy(Lh, img, 0, nslots, desp(Y, l), desp(X, l), tmpa, tmpa_stride, tmpa_pitch);
       run_search(ME_DESCEND, desp(BY, l), desp(BX, l), sr, l == 0);
     }
     // byte planes of the level-0 interiors and their zero-high-band interpolations

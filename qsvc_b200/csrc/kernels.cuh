@@ -69,6 +69,9 @@ void launch_dwt_level(const Launch &L, Plane p, int slot0, int nslots, int ny, i
 bool dwt_snap_supported(int ny, int nx, int pitch, const short *snap, long long snap_slot_stride);
 void launch_dwt_snap(const Launch &L, Plane p, int slot0, int nslots, const short *snap, long long snap_slot_stride,
                      int pitch, int ny, int nx);
+// one synthesis level of the region whose copy is `snap`, written in place (same conditions as launch_dwt_snap)
+void launch_syn_snap(const Launch &L, Plane p, int slot0, int nslots, const short *snap, long long snap_slot_stride,
+                     int pitch, int ny, int nx);
 void launch_dwt0_u8(const Launch &L, Plane p, int slot0, int nslots, const uint8_t *src, long long frame_stride,
                     int f0, int Y, int X);
 // dwt2d::analyze(sig, y, x, levels) / dwt2d::synthesize(sig, y, x, levels)

@@ -331,6 +331,79 @@ void launch_dwt_snap(const Launch &L, Plane p, int slot0, int nslots, const shor
   COUNT(L);
 }
 
+// One synthesis level (dwt2d.cpp:139-172: columns, then rows; 5_3.cpp:81-94) of the region whose copy is `snap`,
+// written in place in plane p.  A lane owns coefficient column gi: it runs the column synthesis of the two columns
+// it contributes to a row (gi of the row-low half, gi of the row-high half) as streaming lifting down D0_SEG
+// coefficient rows, and the row synthesis of a finished row takes the neighbours' samples by shuffle (30 owner
+// lanes per warp + one halo lane on either side).  ny, nx even.
+__global__ void __launch_bounds__(128) k_syn_snap(Plane p, int slot0, const short *__restrict__ snap,
+                                                   long long snap_slot_stride, int pitch, int ny, int nx) {
+  const int hx = nx >> 1, hy = ny >> 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gi = (blockIdx.x * 4 + warp) * 30 + lane - 1;
+  const bool owner = lane >= 1 && lane <= 30 && gi < hx;  // gi >= 0 for every lane >= 1
+  const int gc = min(max(gi, 0), hx - 1);
+  const int slot = slot0 + blockIdx.z;
+  const short *base = snap + (long long)slot * snap_slot_stride;
+  const short *cA = base + gc, *cB = base + hx + gc;
+  const int j0 = blockIdx.y * D0_SEG, j1 = min(j0 + D0_SEG, hy);
+  if ((blockIdx.x * 4 + warp) * 30 >= hx) return;  // whole warp beyond the region
+  auto ecol = [&](const short *c, int j) -> int {  // even sample 2j of the column synthesis
+    const int lo = c[(long long)j * pitch], hi = c[(long long)(hy + j) * pitch];
+    if (j == 0) return (short)(lo - tdiv2(hi));
+    return (short)(lo - tdiv4(hi + (int)c[(long long)(hy + j - 1) * pitch]));
+  };
+  const bool al4 = (((uintptr_t)p.row(slot, 0)) & 3) == 0 && !(p.S & 1);
+  auto emit = [&](int y, int a, int b) {  // row synthesis of row y from this lane's (low, high) samples
+    const int a_next = __shfl_down_sync(0xffffffffu, a, 1), b_next = __shfl_down_sync(0xffffffffu, b, 1);
+    const int b_prev = __shfl_up_sync(0xffffffffu, b, 1);
+    const int e0 = (short)(gi == 0 ? a - tdiv2(b) : a - tdiv4(b + b_prev));
+    int o;
+    if (gi == hx - 1) {
+      o = (short)(b + e0);
+    } else {
+      const int e1 = (short)(a_next - tdiv4(b_next + b));
+      o = (short)(b + tdiv2(e0 + e1));
+    }
+    if (owner) {
+      short *row = p.row(slot, y) + 2 * gi;
+      if (al4) {
+        *reinterpret_cast<unsigned *>(row) = ((unsigned)(unsigned short)e0) | ((unsigned)(unsigned short)o << 16);
+      } else {
+        row[0] = (short)e0;
+        row[1] = (short)o;
+      }
+    }
+  };
+  int eA = ecol(cA, j0), eB = ecol(cB, j0);
+  for (int j = j0; j < j1; j++) {
+    const int hiA = cA[(long long)(hy + j) * pitch], hiB = cB[(long long)(hy + j) * pitch];
+    int nA = 0, nB = 0, oA, oB;
+    if (j == hy - 1) {
+      oA = (short)(hiA + eA);
+      oB = (short)(hiB + eB);
+    } else {
+      nA = ecol(cA, j + 1);
+      nB = ecol(cB, j + 1);
+      oA = (short)(hiA + tdiv2(eA + nA));
+      oB = (short)(hiB + tdiv2(eB + nB));
+    }
+    emit(2 * j, eA, eB);
+    emit(2 * j + 1, oA, oB);
+    eA = nA;
+    eB = nB;
+  }
+}
+
+void launch_syn_snap(const Launch &L, Plane p, int slot0, int nslots, const short *snap, long long snap_slot_stride,
+                     int pitch, int ny, int nx) {
+  if (nslots <= 0) return;
+  dim3 grid(((nx >> 1) + 119) / 120, ((ny >> 1) + D0_SEG - 1) / D0_SEG, nslots);
+  ProfScope ps_(L, KC_DWT_COLS);
+  k_syn_snap<<<grid, 128, 0, L.stream>>>(p, slot0, snap, snap_slot_stride, pitch, ny, nx);
+  COUNT(L);
+}
+
 int dwt_init_attributes() {
   cudaError_t e;
   e = cudaFuncSetAttribute(k_dwt_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
