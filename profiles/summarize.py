@@ -29,7 +29,7 @@ BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 # bench.py kernel classes (csrc/kernels.cuh KC_*)
 CLASS = [("residue", r"k_mc_march|k_ll_residue|k_residue"), ("search_exact", r"k_subpel_strip|k_subpel_exact|k_strip2|k_level1_tile"),
          ("search", r"k_subpel_tma|k_subpel_fast|k_search"), ("predict", r"k_predict|k_tail_state|k_clip"),
-         ("dwt_rows", r"k_dwt_rows"), ("dwt_cols", r"k_dwt_cols"), ("update", r"k_update"), ("image", r".*")]
+         ("dwt_rows", r"k_dwt_rows|k_dwt0_u8|k_dwt_snap|k_ll1_store_u8"), ("dwt_cols", r"k_dwt_cols|k_syn_snap"), ("update", r"k_update"), ("image", r".*")]
 
 
 def kname(s):
